@@ -1,0 +1,123 @@
+"""ctypes binding of libspecloss.so (C ABI declared in include/specloss.h).
+
+The library is built in-tree by `build_library()` (nvcc, sm_100a) -- `__graft_entry__.build()`
+calls it.  There is no CPU fallback: if the shared object is missing or does not load,
+`load_library()` raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import shutil
+import subprocess
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int32, c_int64, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libspecloss.so")
+CSRC = os.path.join(_HERE, "csrc")
+ABI_VERSION = 1
+
+SPL_KIND_STFT = 0
+SPL_KIND_MEL = 1
+SPL_MAX_TRANSFORMS = 8
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+
+class SplTransform(ctypes.Structure):
+    _fields_ = [
+        ("kind", c_int32), ("n_fft", c_int32), ("hop", c_int32), ("win", c_int32),
+        ("frames_per_chunk", c_int32), ("eps", c_float),
+        ("window", c_void_p), ("twiddle", c_void_p),
+        ("n_mels", c_int32), ("inv_ln_base", c_float),
+        ("mel_row_start", c_void_p), ("mel_row_len", c_void_p), ("mel_row_ptr", c_void_p),
+        ("mel_row_val", c_void_p), ("bin_m0", c_void_p), ("bin_w0", c_void_p), ("bin_w1", c_void_p),
+        ("partials", c_void_p), ("gchunks", c_void_p),
+    ]
+
+
+class SplGeometry(ctypes.Structure):
+    _fields_ = [
+        ("n_frames", c_int32), ("n_bins", c_int32), ("n_chunks", c_int32), ("span", c_int32),
+        ("n_sums", c_int32), ("partial_count", c_int64), ("gchunk_bytes", c_int64), ("smem_bytes", c_int64),
+    ]
+
+
+EXPORTS = ("spl_abi_version", "spl_last_error", "spl_fill_twiddle", "spl_geometry_of", "spl_forward",
+           "spl_reduce", "spl_finalize", "spl_backward")
+
+
+class SpecLossError(RuntimeError):
+    pass
+
+
+def bind(lib: ctypes.CDLL) -> ctypes.CDLL:
+    """Attach argument/return types to every exported entry point."""
+    lib.spl_abi_version.restype = c_int32
+    lib.spl_abi_version.argtypes = []
+    lib.spl_last_error.restype = c_char_p
+    lib.spl_last_error.argtypes = []
+    lib.spl_fill_twiddle.restype = c_int32
+    lib.spl_fill_twiddle.argtypes = [c_int32, c_void_p]
+    lib.spl_geometry_of.restype = c_int32
+    lib.spl_geometry_of.argtypes = [POINTER(SplTransform), c_int32, c_int32, POINTER(SplGeometry)]
+    lib.spl_forward.restype = c_int32
+    lib.spl_forward.argtypes = [POINTER(SplTransform), c_int32, c_void_p, c_void_p, c_int32, c_int32, c_void_p]
+    lib.spl_reduce.restype = c_int32
+    lib.spl_reduce.argtypes = [POINTER(SplTransform), c_int32, c_int32, c_int32, c_void_p, c_void_p]
+    lib.spl_finalize.restype = c_int32
+    lib.spl_finalize.argtypes = [POINTER(SplTransform), c_int32, c_void_p, c_int64, c_int32,
+                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.spl_backward.restype = c_int32
+    lib.spl_backward.argtypes = [POINTER(SplTransform), c_int32, c_int32, c_int32, c_void_p,
+                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    ver = lib.spl_abi_version()
+    if ver != ABI_VERSION:
+        raise SpecLossError(f"libspecloss ABI version {ver}, expected {ABI_VERSION}")
+    return lib
+
+
+def check(lib: ctypes.CDLL, rc: int) -> None:
+    if rc != 0:
+        msg = lib.spl_last_error()
+        text = msg.decode() if msg else "unknown error"
+        if rc == -1:
+            # -1 = SPL_E_INVALID: the reference raises RuntimeError from torch.stft for the same inputs
+            raise RuntimeError(f"specloss: {text}")
+        raise SpecLossError(f"specloss (code {rc}): {text}")
+
+
+def build_library(verbose: bool = False) -> str:
+    """Compile csrc/specloss.cu into libspecloss.so for sm_100a (cross-compiles without a GPU)."""
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        raise SpecLossError("nvcc not found; libspecloss.so cannot be built")
+    srcs = [os.path.join(CSRC, f) for f in ("specloss.cu", "specloss_kernels.cuh", "specloss_host.inl",
+                                            "fft_codelets.cuh")]
+    hdr = os.path.join(os.path.dirname(_HERE), "include", "specloss.h")
+    newest = max(os.path.getmtime(p) for p in srcs + [hdr])
+    if os.path.exists(LIB_PATH) and os.path.getmtime(LIB_PATH) >= newest:
+        return LIB_PATH
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, srcs[0]]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise SpecLossError("nvcc failed:\n" + res.stdout + res.stderr)
+    if verbose:
+        print(res.stderr)
+    return LIB_PATH
+
+
+_LIB = None
+
+
+def load_library() -> ctypes.CDLL:
+    """Load the CUDA library.  Raises if it has not been built -- there is no fallback."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise SpecLossError(
+                f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a).  This package has no CPU or PyTorch fallback.")
+        _LIB = bind(ctypes.CDLL(LIB_PATH))
+    return _LIB

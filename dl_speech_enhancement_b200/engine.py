@@ -1,0 +1,257 @@
+"""Host-side driver of the C ABI: builds the per-resolution constant tables, sizes the per-call
+workspace and issues spl_forward / spl_reduce / [all-reduce] / spl_finalize / spl_backward.
+
+All buffers are torch tensors (device memory, caching allocator, current stream); the library
+itself never allocates or synchronises.  Nothing here computes losses or gradients in Python.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+import os
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _abi
+from ._abi import SPL_KIND_MEL, SPL_KIND_STFT, SplGeometry, SplTransform
+
+SUPPORTED_NFFT = (512, 1024, 2048)
+_SM_COUNT = 148          # B200
+
+
+def fft_geometry(n_fft: int):
+    """(L, R): lanes per frame and points per lane; mirrors spl::FftGeom in specloss_kernels.cuh."""
+    if n_fft not in SUPPORTED_NFFT:
+        raise NotImplementedError(
+            f"fft_size {n_fft} is outside the sm_100a kernels' envelope {SUPPORTED_NFFT} "
+            "(the reference accepts any size torch.stft does; this implementation raises instead of falling back)")
+    lanes = 16 if n_fft == 512 else 32
+    return lanes, n_fft // lanes
+
+
+def twiddle_table(n_fft: int) -> torch.Tensor:
+    """W_N^(n1*k2) = exp(-2 pi i n1 k2 / N), fp32 roundings of fp64 values, layout [k2][n1] (re, im)."""
+    lanes, rows = fft_geometry(n_fft)
+    e = (np.arange(rows)[:, None] * np.arange(lanes)[None, :]) % n_fft
+    th = 2.0 * np.pi * e.astype(np.float64) / n_fft
+    tab = np.stack([np.cos(th), -np.sin(th)], axis=-1).astype(np.float32)
+    return torch.from_numpy(tab.reshape(-1).copy())
+
+
+def mel_tables(melmat: np.ndarray):
+    """Band structure of the (K, n_mels) filterbank: per-row runs for the forward projection and the
+    (<= 2, adjacent) rows every bin feeds for the backward one.  Slaney/HTK triangles always satisfy
+    this; anything else raises (no dense fallback)."""
+    k_bins, n_mels = melmat.shape
+    if n_mels < 2:
+        raise NotImplementedError("num_mels < 2 is outside the kernels' envelope")
+    row_start = np.zeros(n_mels, np.int32)
+    row_len = np.zeros(n_mels, np.int32)
+    row_ptr = np.zeros(n_mels, np.int32)
+    vals = []
+    ptr = 0
+    for m in range(n_mels):
+        nz = np.flatnonzero(melmat[:, m])
+        row_ptr[m] = ptr
+        if nz.size:
+            row_start[m], row_len[m] = nz[0], nz[-1] - nz[0] + 1
+            vals.append(melmat[nz[0]:nz[-1] + 1, m].astype(np.float32))
+            ptr += int(row_len[m])
+    row_val = np.concatenate(vals) if vals else np.zeros(1, np.float32)
+    bin_m0 = np.zeros(k_bins, np.int32)
+    bin_w0 = np.zeros(k_bins, np.float32)
+    bin_w1 = np.zeros(k_bins, np.float32)
+    for k in range(k_bins):
+        nz = np.flatnonzero(melmat[k])
+        if nz.size == 0:
+            continue
+        if nz.size > 2 or (nz.size == 2 and nz[1] != nz[0] + 1):
+            raise NotImplementedError(
+                f"mel filterbank row for bin {k} feeds mels {nz.tolist()}: only banded filterbanks "
+                "(<= 2 adjacent mels per bin, e.g. librosa/Slaney triangles) are supported")
+        if nz.size == 2:
+            bin_m0[k], bin_w0[k], bin_w1[k] = nz[0], melmat[k, nz[0]], melmat[k, nz[1]]
+        elif nz[0] < n_mels - 1:
+            bin_m0[k], bin_w0[k] = nz[0], melmat[k, nz[0]]
+        else:
+            bin_m0[k], bin_w1[k] = n_mels - 2, melmat[k, nz[0]]
+    t = torch.from_numpy
+    return dict(mel_row_start=t(row_start), mel_row_len=t(row_len), mel_row_ptr=t(row_ptr),
+                mel_row_val=t(row_val), bin_m0=t(bin_m0), bin_w0=t(bin_w0), bin_w1=t(bin_w1))
+
+
+@dataclass
+class TransformPlan:
+    """One resolution of one loss, with its device-resident constant tables."""
+    kind: int
+    n_fft: int
+    hop: int
+    win: int
+    eps: float
+    window: torch.Tensor                    # (win,) fp32 -- the module's registered buffer
+    twiddle: torch.Tensor                   # (2 * n_fft,) fp32
+    n_mels: int = 0
+    inv_ln_base: float = 1.0
+    tables: dict = field(default_factory=dict)   # mel only: tensors named as the spl_transform fields
+
+    def validate(self):
+        fft_geometry(self.n_fft)
+        if not (1 <= self.win <= self.n_fft):
+            raise RuntimeError(f"win_length {self.win} must be in [1, fft_size={self.n_fft}] (torch.stft raises likewise)")
+        if not (1 <= self.hop <= self.win):
+            raise NotImplementedError(f"hop_size {self.hop} > win_length {self.win} is outside the kernels' envelope")
+        if self.window.dtype != torch.float32 or self.window.numel() != self.win:
+            raise RuntimeError("window buffer must be float32 with win_length taps (fp32-only implementation)")
+
+
+def choose_frames_per_chunk(batch: int, n_frames: int, n_fft: int) -> int:
+    """Frames walked by one warp.  Small problems want many short chunks (parallelism: the whole
+    config-2 batch is 27.6k frames for ~2.4k resident warps), big ones longer chunks (less seam
+    traffic in the gradient slots)."""
+    env = os.environ.get("SPECLOSS_FRAMES_PER_CHUNK")
+    if env:
+        m = max(1, int(env))
+    else:
+        resident = _SM_COUNT * (8 if n_fft == 2048 else 16)
+        m = int(round(batch * n_frames / (4.0 * resident)))
+        m = max(2, min(16, m))
+    if n_fft == 512 and (m & 1):        # two frames in flight per warp
+        m += 1
+    return m
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+class ForwardState:
+    """What backward needs: the ctypes transform array (pointers into the tensors kept alive here)."""
+
+    def __init__(self):
+        self.transforms = None
+        self.n = 0
+        self.keep: List[torch.Tensor] = []
+        self.coefs: Optional[torch.Tensor] = None
+        self.batch = 0
+        self.t_len = 0
+        self.has_grad = False
+        self.sc = self.mag = self.mel = None
+        self.sums: Optional[torch.Tensor] = None
+        self.geometries: List[SplGeometry] = []
+
+
+class Engine:
+    def __init__(self, lib: ctypes.CDLL):
+        self.lib = lib
+
+    # -- helpers ---------------------------------------------------------------------------------
+    def _stream(self, ref: torch.Tensor):
+        return ctypes.c_void_p(torch.cuda.current_stream(ref.device).cuda_stream) if ref.is_cuda else None
+
+    def geometry(self, tr: SplTransform, batch: int, t_len: int) -> SplGeometry:
+        g = SplGeometry()
+        _abi.check(self.lib, self.lib.spl_geometry_of(ctypes.byref(tr), batch, t_len, ctypes.byref(g)))
+        return g
+
+    # -- forward ---------------------------------------------------------------------------------
+    def forward(self, plans: Sequence[TransformPlan], x: torch.Tensor, y: torch.Tensor, need_grad: bool,
+                group=None, global_batch: Optional[int] = None) -> ForwardState:
+        """x, y: (B, T) fp32 contiguous on one device.  Launches on the current stream."""
+        if len(plans) < 1 or len(plans) > _abi.SPL_MAX_TRANSFORMS:
+            raise RuntimeError(f"{len(plans)} resolutions: supported range is 1..{_abi.SPL_MAX_TRANSFORMS}")
+        batch, t_len = x.shape
+        dev = x.device
+        st = ForwardState()
+        st.batch, st.t_len, st.has_grad, st.n = batch, t_len, need_grad, len(plans)
+        arr = (SplTransform * len(plans))()
+        n_sums_total = 0
+        for i, pl in enumerate(plans):
+            pl.validate()
+            if pl.window.device != dev or pl.twiddle.device != dev:
+                raise RuntimeError(f"loss module buffers are on {pl.window.device}, inputs on {dev}: call .to(device)")
+            tr = arr[i]
+            tr.kind, tr.n_fft, tr.hop, tr.win = pl.kind, pl.n_fft, pl.hop, pl.win
+            tr.eps = pl.eps
+            if t_len <= pl.n_fft // 2:
+                raise RuntimeError(f"reflect padding needs T > fft_size/2 (T={t_len}, fft_size={pl.n_fft}); "
+                                   "torch.stft raises for the same input")
+            n_frames = 1 + t_len // pl.hop
+            tr.frames_per_chunk = choose_frames_per_chunk(batch, n_frames, pl.n_fft)
+            tr.window, tr.twiddle = _ptr(pl.window), _ptr(pl.twiddle)
+            tr.n_mels, tr.inv_ln_base = pl.n_mels, pl.inv_ln_base
+            if pl.kind == SPL_KIND_MEL:
+                for name, t in pl.tables.items():
+                    if t.device != dev:
+                        raise RuntimeError("mel tables are not on the input device: call .to(device)")
+                    setattr(tr, name, _ptr(t))
+            g = self.geometry(tr, batch, t_len)
+            st.geometries.append(g)
+            partials = torch.empty(g.partial_count, dtype=torch.float64, device=dev)
+            st.keep.append(partials)
+            tr.partials = _ptr(partials)
+            if need_grad:
+                gch = torch.empty(g.gchunk_bytes // 4, dtype=torch.float32, device=dev)
+                st.keep.append(gch)
+                tr.gchunks = _ptr(gch)
+            else:
+                tr.gchunks = None
+            n_sums_total += g.n_sums
+            st.keep.extend([pl.window, pl.twiddle] + list(pl.tables.values()))
+        st.transforms = arr
+        stream = self._stream(x)
+        lib = self.lib
+        _abi.check(lib, lib.spl_forward(arr, len(plans), x.data_ptr(), y.data_ptr(), batch, t_len, stream))
+        sums = torch.empty(n_sums_total, dtype=torch.float64, device=dev)
+        _abi.check(lib, lib.spl_reduce(arr, len(plans), batch, t_len, sums.data_ptr(), stream))
+        if group is not None:
+            import torch.distributed as dist
+            dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)     # the single exchange step
+            if global_batch is None:
+                global_batch = batch * dist.get_world_size(group)
+        if global_batch is None:
+            global_batch = batch
+        has_stft = any(p.kind == SPL_KIND_STFT for p in plans)
+        has_mel = any(p.kind == SPL_KIND_MEL for p in plans)
+        # separate 0-dim outputs: callers scale them in place (trainer/trainerGAN.py:221,228-229)
+        st.sc = torch.empty((), dtype=torch.float32, device=dev) if has_stft else None
+        st.mag = torch.empty((), dtype=torch.float32, device=dev) if has_stft else None
+        st.mel = torch.empty((), dtype=torch.float32, device=dev) if has_mel else None
+        st.coefs = torch.empty(2 * len(plans), dtype=torch.float32, device=dev)
+        _abi.check(lib, lib.spl_finalize(arr, len(plans), sums.data_ptr(), int(global_batch), t_len,
+                                         _ptr(st.sc), _ptr(st.mag), _ptr(st.mel), st.coefs.data_ptr(), stream))
+        st.sums = sums
+        return st
+
+    # -- backward --------------------------------------------------------------------------------
+    def backward(self, st: ForwardState, g_sc: Optional[torch.Tensor], g_mag: Optional[torch.Tensor],
+                 g_mel: Optional[torch.Tensor]) -> torch.Tensor:
+        if not st.has_grad:
+            raise RuntimeError("backward requested but forward ran without gradient workspace")
+        dev = st.coefs.device
+        dx = torch.empty(st.batch, st.t_len, dtype=torch.float32, device=dev)
+
+        def scalar(g):
+            if g is None:
+                return None
+            g = g.detach().to(device=dev, dtype=torch.float32).reshape(())
+            return g.contiguous()
+
+        gs = [scalar(g_sc), scalar(g_mag), scalar(g_mel)]
+        _abi.check(self.lib, self.lib.spl_backward(st.transforms, st.n, st.batch, st.t_len, st.coefs.data_ptr(),
+                                                   _ptr(gs[0]), _ptr(gs[1]), _ptr(gs[2]), dx.data_ptr(),
+                                                   self._stream(dx)))
+        return dx
+
+
+_ENGINE: Optional[Engine] = None
+
+
+def cuda_engine() -> Engine:
+    """The process-wide engine over libspecloss.so.  Raises when the library is not built."""
+    global _ENGINE
+    if _ENGINE is None:
+        _ENGINE = Engine(_abi.load_library())
+    return _ENGINE

@@ -1,0 +1,84 @@
+"""torch.autograd.Function over the C ABI, and the functional entry point `spectral_losses`.
+
+Forward launches the fused kernels (losses AND the un-scaled waveform-gradient pieces, while the
+spectra are still on chip); backward is one gather/scale kernel.  CUDA tensors only: CPU tensors,
+non-fp32 dtypes and missing libspecloss.so raise -- there is no fallback path.
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from .engine import Engine, ForwardState, TransformPlan, cuda_engine
+from ._abi import SPL_KIND_MEL, SPL_KIND_STFT
+
+
+def _as_2d(x: torch.Tensor, name: str) -> torch.Tensor:
+    if x.dim() == 3:
+        # the reference does x.view(-1, T) (stft_loss.py:158-160), which already requires contiguity
+        x = x.reshape(-1, x.size(2))
+    elif x.dim() != 2:
+        raise RuntimeError(f"{name}: expected (B, T) or (B, C, T), got shape {tuple(x.shape)}")
+    return x.contiguous()
+
+
+def _check_inputs(x: torch.Tensor, y: torch.Tensor):
+    if not (x.is_cuda and y.is_cuda):
+        raise RuntimeError("dl_speech_enhancement_b200 losses are CUDA-only (sm_100a kernels); got a CPU tensor. "
+                           "There is no CPU fallback: use the reference modules on CPU.")
+    if x.dtype != torch.float32 or y.dtype != torch.float32:
+        raise RuntimeError(f"fp32-only implementation; got {x.dtype} / {y.dtype}")
+    if x.device != y.device:
+        raise RuntimeError("prediction and target are on different devices")
+    if x.shape != y.shape:
+        raise RuntimeError(f"shape mismatch: {tuple(x.shape)} vs {tuple(y.shape)}")
+
+
+class _SpectralLossFn(torch.autograd.Function):
+    """outputs: (sc, mag, mel) with None for the absent loss family."""
+
+    @staticmethod
+    def forward(ctx, x, y, plans, engine, group, global_batch):
+        x2, y2 = _as_2d(x, "prediction"), _as_2d(y, "target")
+        need_grad = ctx.needs_input_grad[0]
+        st = engine.forward(plans, x2.detach(), y2.detach(), need_grad, group, global_batch)
+        ctx.state = st
+        ctx.engine = engine
+        ctx.x_shape = x.shape
+        ctx.set_materialize_grads(False)
+        outs = tuple(t for t in (st.sc, st.mag, st.mel) if t is not None)
+        ctx.layout = (st.sc is not None, st.mel is not None)
+        ctx.mark_non_differentiable()  # nothing: all outputs differentiable w.r.t. x
+        return outs
+
+    @staticmethod
+    def backward(ctx, *grads):
+        has_stft, has_mel = ctx.layout
+        g = list(grads)
+        g_sc = g_mag = g_mel = None
+        if has_stft:
+            g_sc, g_mag = g[0], g[1]
+            g = g[2:]
+        if has_mel:
+            g_mel = g[0]
+        if ctx.needs_input_grad[1]:
+            raise NotImplementedError(
+                "gradient w.r.t. the target is not implemented (no caller in the reference needs it: "
+                "trainer/denoise.py:75, autoencoder.py:98, vocoder.py:76 pass a constant target)")
+        dx = ctx.engine.backward(ctx.state, g_sc, g_mag, g_mel)
+        ctx.state = None   # release the gradient workspace
+        return dx.view(ctx.x_shape), None, None, None, None, None
+
+
+def spectral_losses(x: torch.Tensor, y: torch.Tensor, plans: Sequence[TransformPlan],
+                    group=None, global_batch: Optional[int] = None, engine: Optional[Engine] = None):
+    """Returns the tuple of 0-dim losses the plans define: (sc, mag) and/or (mel,), in that order.
+
+    group: a torch.distributed process group whose ranks hold disjoint utterances of one logical
+    batch; the partial sums are all-reduced so every rank returns the full-batch losses and its
+    own rows' gradients."""
+    if engine is None:
+        _check_inputs(x, y)
+        engine = cuda_engine()
+    return _SpectralLossFn.apply(x, y, tuple(plans), engine, group, global_batch)

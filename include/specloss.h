@@ -1,0 +1,105 @@
+/* specloss.h -- C ABI of the B200 (sm_100a) spectral-loss library (libspecloss.so).
+ *
+ * The reference (s194584/dl-speech-enhancement) has no native layer and no FFI: its boundary
+ * for this path is the Python nn.Module contract
+ *     MultiResolutionSTFTLoss.forward(x, y) -> (sc_loss, mag_loss)   losses/stft_loss.py:146-170
+ *     MultiMelSpectrogramLoss.forward(y_hat, y) -> mel_loss          losses/mel_loss.py:140-156
+ * called from trainer/trainerGAN.py:220,227 and train_denoise.py:139.  The entry points below are
+ * what a ctypes binding behind those two forward() methods (and their autograd backward) needs;
+ * INTEGRATION.md shows that binding.  Each function cites the reference code it replaces.
+ *
+ * Conventions
+ *   - every pointer marked "device" is a CUDA device pointer owned by the caller; the library
+ *     never allocates, frees or synchronises, and launches on the stream it is given;
+ *   - return value 0 = ok, negative = error (SPL_E_*); spl_last_error() gives the message of the
+ *     last failing call on the calling thread;
+ *   - fp32 data, fp64 partial sums; n_fft in {512, 1024, 2048}; hop <= win <= n_fft.
+ */
+#ifndef SPECLOSS_H
+#define SPECLOSS_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPL_ABI_VERSION 1
+
+#define SPL_OK 0
+#define SPL_E_INVALID (-1)   /* bad argument / outside the supported envelope */
+#define SPL_E_CUDA (-2)      /* CUDA runtime error (message carries cudaGetErrorString) */
+
+#define SPL_KIND_STFT 0      /* spectral convergence + log-magnitude L1 (stft_loss.py:80-117) */
+#define SPL_KIND_MEL 1       /* log-mel L1 (mel_loss.py:74-94,153)                            */
+#define SPL_MAX_TRANSFORMS 8
+
+/* One resolution of one loss.  Plain data; build it once per module and reuse it. */
+typedef struct spl_transform {
+  int32_t kind;              /* SPL_KIND_* */
+  int32_t n_fft, hop, win;   /* torch.stft(x, n_fft, hop, win, window), center=True, reflect pad */
+  int32_t frames_per_chunk;  /* consecutive frames walked by one warp (>= 1; even if n_fft==512) */
+  float eps;                 /* clamp on |X|^2: 1e-7 (stft_loss.py:19) / 1e-10 (mel_loss.py:35); mel reuses it on the mel energies */
+  const float* window;       /* device, `win` taps (the module's registered buffer) */
+  const float* twiddle;      /* device, 2*n_fft floats written by spl_fill_twiddle() */
+  /* --- mel only (kind == SPL_KIND_MEL); NULL / 0 otherwise --- */
+  int32_t n_mels;
+  float inv_ln_base;         /* 1/ln(log_base); 1 for log_base=None (mel_loss.py:63-71) */
+  const int32_t* mel_row_start; /* device [n_mels]: first bin of the row's non-zero run */
+  const int32_t* mel_row_len;   /* device [n_mels]: length of that run (0 = empty filter) */
+  const int32_t* mel_row_ptr;   /* device [n_mels]: offset of the run's weights in mel_row_val */
+  const float* mel_row_val;     /* device: melmat[k, m] for the runs, row after row */
+  const int32_t* bin_m0;        /* device [n_fft/2+1]: bin k feeds mel rows m0 and m0+1 only */
+  const float* bin_w0;          /* device [n_fft/2+1]: melmat[k, m0]   */
+  const float* bin_w1;          /* device [n_fft/2+1]: melmat[k, m0+1] */
+  /* --- per-call workspace, sized by spl_geometry() --- */
+  double* partials;          /* device [partial_count] */
+  void* gchunks;             /* device [gchunk_bytes]; NULL = forward only (torch.no_grad) */
+} spl_transform;
+
+typedef struct spl_geometry {
+  int32_t n_frames;          /* 1 + T / hop */
+  int32_t n_bins;            /* n_fft / 2 + 1 */
+  int32_t n_chunks;          /* per utterance */
+  int32_t span;              /* gradient slot length per chunk, in elements */
+  int32_t n_sums;            /* 3 (S1, S2, S3) for STFT, 1 (S4) for mel */
+  int64_t partial_count;     /* doubles in `partials` */
+  int64_t gchunk_bytes;      /* bytes in `gchunks` */
+  int64_t smem_bytes;        /* dynamic shared memory per CTA of the transform kernel */
+} spl_geometry;
+
+int32_t spl_abi_version(void);
+const char* spl_last_error(void);
+
+/* Host-side table: W_N^(n1*k2) rounded from fp64, layout [k2][n1] (2*n_fft floats, host memory). */
+int32_t spl_fill_twiddle(int32_t n_fft, float* host_out);
+
+/* Sizes of the per-call workspace for batch (B, T).  Host only. */
+int32_t spl_geometry_of(const spl_transform* t, int32_t B, int32_t T, spl_geometry* out);
+
+/* Forward of every transform in ts[0..n): replaces stft()/STFTLoss.forward (stft_loss.py:19-35,
+ * 100-117) and MelSpectrogram.forward (mel_loss.py:74-94) for x and y at once.  Writes per-chunk
+ * partial sums and, when gchunks != NULL, the un-scaled waveform-gradient pieces of dL/dx. */
+int32_t spl_forward(const spl_transform* ts, int32_t n, const float* x, const float* y,
+                    int32_t B, int32_t T, void* stream);
+
+/* Deterministic reduction of the partial sums into sums[sum of n_sums] (device doubles), in the
+ * order of ts.  Multi-GPU: all-reduce `sums` (SUM) between this call and spl_finalize(). */
+int32_t spl_reduce(const spl_transform* ts, int32_t n, int32_t B, int32_t T, double* sums, void* stream);
+
+/* Losses from the sums: replaces SpectralConvergenceLoss/LogSTFTMagnitudeLoss (stft_loss.py:56,77),
+ * the means over resolutions (stft_loss.py:161-168, mel_loss.py:151-154) and F.l1_loss (mel_loss.py:153).
+ * B_global is the batch over all ranks.  sc/mag/mel are separate device scalars (NULL to skip);
+ * coefs[2*n] receives the backward coefficients consumed by spl_backward(). */
+int32_t spl_finalize(const spl_transform* ts, int32_t n, const double* sums, int64_t B_global, int32_t T,
+                     float* sc, float* mag, float* mel, float* coefs, void* stream);
+
+/* Backward: dx (B, T) = g_sc * dsc/dx + g_mag * dmag/dx + g_mel * dmel/dx -- what autograd derives for
+ * the reference modules.  g_* are device scalars (NULL = 0). */
+int32_t spl_backward(const spl_transform* ts, int32_t n, int32_t B, int32_t T, const float* coefs,
+                     const float* g_sc, const float* g_mag, const float* g_mel, float* dx, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPECLOSS_H */

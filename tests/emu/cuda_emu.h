@@ -1,0 +1,38 @@
+// Minimal SIMT emulation of the CUDA constructs used by specloss_kernels.cuh, for the CPU
+// test-suite only (tests/emu/specloss_emu.cpp).  One emulated warp = 32 host threads in lock
+// step: __syncwarp() is a barrier, __shfl_xor_sync() a barrier-protected exchange.
+#pragma once
+#include <algorithm>
+#include <barrier>
+#include <cmath>
+#include <cstddef>
+
+#define __device__
+#define __host__
+#define __global__
+#define __forceinline__ inline
+#define __restrict__
+#define __align__(n)
+
+struct float2 { float x, y; };
+static inline float2 make_float2(float x, float y) { return float2{x, y}; }
+
+struct EmuWarp {
+  std::barrier<> bar{32};
+  float slots[32];
+};
+extern thread_local EmuWarp* emu_warp;
+extern thread_local int emu_lane;
+
+static inline void __syncwarp() { emu_warp->bar.arrive_and_wait(); }
+static inline void __syncthreads() { emu_warp->bar.arrive_and_wait(); }   // emulated CTAs are one warp wide
+static inline float __shfl_xor_sync(unsigned, float v, int lane_mask) {
+  emu_warp->slots[emu_lane] = v;
+  emu_warp->bar.arrive_and_wait();
+  const float r = emu_warp->slots[emu_lane ^ lane_mask];
+  emu_warp->bar.arrive_and_wait();
+  return r;
+}
+template <typename T> static inline T __ldg(const T* p) { return *p; }
+static inline float rsqrtf(float x) { return 1.0f / std::sqrt(x); }
+using std::min;

@@ -1,0 +1,87 @@
+// CPU SIMT emulation backend of the C ABI in include/specloss.h -- TEST INFRASTRUCTURE ONLY.
+// Runs the very same device code (specloss_kernels.cuh) and host logic (specloss_host.inl) as
+// libspecloss.so, with every CUDA thread of a warp played by a host thread.  The product never
+// loads this library; tests hand it to the host-side engine explicitly.
+#define SPECLOSS_EMU 1
+#include "../../include/specloss.h"
+#include "../../dl_speech_enhancement_b200/csrc/specloss_kernels.cuh"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+thread_local EmuWarp* emu_warp = nullptr;
+thread_local int emu_lane = 0;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+template <typename F>
+void run_warp(F&& body) {     // body(lane), 32 lanes in lock step
+  EmuWarp w;
+  std::vector<std::thread> th;
+  th.reserve(32);
+  for (int lane = 0; lane < 32; ++lane)
+    th.emplace_back([&, lane] {
+      emu_warp = &w;
+      emu_lane = lane;
+      body(lane);
+      w.bar.arrive_and_drop();
+    });
+  for (auto& t : th) t.join();
+}
+
+template <int NFFT, int KIND, bool GRAD>
+int spl_launch_transform(const spl::TransformParams& p, int n_mels, void*) {
+  using SL = spl::SmemLayout<NFFT, KIND, GRAD>;
+  const size_t words = (size_t)SL::words_per_warp(p.ring_n, n_mels) * spl::kWarpsPerCta;
+  const long long groups = (long long)p.B * p.n_chunks;
+  const int grid = (int)((groups + spl::kWarpsPerCta - 1) / spl::kWarpsPerCta);
+  std::vector<std::thread> blocks;
+  const int par = std::max(1u, std::thread::hardware_concurrency());
+  for (int b0 = 0; b0 < grid; b0 += par) {
+    blocks.clear();
+    for (int block = b0; block < std::min(grid, b0 + par); ++block)
+      blocks.emplace_back([&, block] {
+        std::vector<float> smem(words, -12345.0f);   // poison: uninitialised reads show up as garbage
+        for (int warp = 0; warp < spl::kWarpsPerCta; ++warp)
+          run_warp([&](int lane) { spl::transform_body<NFFT, KIND, GRAD>(p, smem.data(), block, warp * 32 + lane); });
+      });
+    for (auto& t : blocks) t.join();
+  }
+  return SPL_OK;
+}
+
+int spl_launch_reduce(const spl::ReduceParams& rp, void*) {
+  for (int block = 0; block < rp.n_sums; ++block) {
+    double sh[32];
+    run_warp([&](int lane) { spl::reduce_body(rp, sh, block, lane, 32); });
+  }
+  return SPL_OK;
+}
+
+int spl_launch_finalize(const spl::FinalizeParams& fp, void*) {
+  spl::finalize_body(fp);
+  return SPL_OK;
+}
+
+int spl_launch_combine(const spl::CombineParams& cp, void*) {
+  const long long total = (long long)cp.B * cp.T;
+  for (long long g = 0; g < total; ++g) spl::combine_body(cp, g);
+  return SPL_OK;
+}
+
+}  // namespace
+
+#include "../../dl_speech_enhancement_b200/csrc/specloss_host.inl"
