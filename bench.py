@@ -1,0 +1,314 @@
+#!/usr/bin/env python3
+"""Benchmark of the spectral-loss hot path: MultiResolutionSTFTLoss (3 resolutions) +
+MultiMelSpectrogramLoss (2048/300, 80 mels) forward+backward, audio-seconds per second.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU op sequence (oracle port)
+
+Workload (BASELINE.json configs[1]): batch 16 x 1 s synthetic 48 kHz audio per GPU (weak scaling:
+every rank holds its own 16 utterances; the loss partial sums are all-reduced over NCCL so each rank
+returns the losses of the global batch).  A step = one fwd+bwd of both criteria through the drop-in
+nn.Modules; the input pair of each step is taken round-robin from a pool larger than L2.
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+FS = 48000
+BATCH = 16
+T_LEN = 48000
+MEL_KW = dict(fs=FS, fft_sizes=[2048], hop_sizes=[300], win_lengths=[None], window="hann_window",
+              num_mels=80, fmin=0, fmax=24000, log_base=None)
+STFT_RES = [(1024, 120, 600), (2048, 240, 1200), (512, 50, 240)]
+METRIC = "spectral_loss_fwd_bwd_audio_seconds_per_second"
+UNIT = "audio-s/s"
+POOL_BYTES = 192 << 20          # > 126 MB L2
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def nominal_flops(batch, t_len):
+    """5 passes x sum_res B*F*2.5*N*log2(N)."""
+    import math
+    tot = 0.0
+    for n, hop, _ in STFT_RES + [(2048, 300, 2048)]:
+        tot += batch * (1 + t_len // hop) * 2.5 * n * math.log2(n)
+    return 5.0 * tot
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = sorted(float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit())
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the reference's ATen op sequence on the host cores (oracle port)
+# --------------------------------------------------------------------------------------------
+def cpu_reference_step_time(batch, t_len, steps, warmup):
+    import torch
+    from oracle import spectral_oracle as so     # checker/baseline only; never on the product path
+
+    torch.set_num_threads(os.cpu_count())
+    mel = so.mel_from_kwargs(**MEL_KW)
+    y_hat, y = so.synth_pair(batch, t_len, seed=0)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        so.losses_and_grad(y_hat, y, so.DEFAULT_STFT, mel, dtype=torch.float32, use_torch_stft=True)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    return times, torch.get_num_threads()
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    # bounded sample: probe one utterance, then size the per-step batch so K+W steps stay within ~2 minutes
+    probe, cores = cpu_reference_step_time(1, T_LEN, 1, 1)
+    budget = 120.0 / max(1, args.steps + args.warmup)
+    b = int(max(1, min(BATCH, budget / max(probe[0], 1e-6))))
+    times, cores = cpu_reference_step_time(b, T_LEN, args.steps, args.warmup)
+    ms = 1000.0 * sum(times) / len(times)
+    value = b * T_LEN / FS / (ms / 1000.0)
+    sample = f"{b} x 1 s @ 48 kHz per step (of the 16 x 1 s workload), {args.steps} steps, mean"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "configs[1]: batch 16 x 1 s synthetic 48 kHz, MR-STFT(1024/2048/512) + 80-mel hop-300, fwd+bwd",
+                       "reference_path": "torch.stft + ATen elementwise/norm/matmul + autograd on CPU (oracle port of losses/stft_loss.py, losses/mel_loss.py)"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------
+# this repo's arm
+# --------------------------------------------------------------------------------------------
+def run_ours(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+
+    import dl_speech_enhancement_b200 as pkg
+    from dl_speech_enhancement_b200.engine import cuda_engine
+
+    dev = torch.device(f"cuda:{local_rank}")
+    torch.cuda.set_device(dev)
+    group = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        group = dist.group.WORLD
+    cuda_engine()          # raises if libspecloss.so is missing -- no fallback
+
+    stft = pkg.MultiResolutionSTFTLoss().to(dev)
+    mel = pkg.MultiMelSpectrogramLoss(**MEL_KW).to(dev)
+    stft.process_group = group
+    mel.process_group = group
+
+    pair_bytes = 2 * BATCH * T_LEN * 4
+    n_pool = max(2, POOL_BYTES // pair_bytes)
+    gen = torch.Generator(device=dev).manual_seed(1000 + rank)
+    pool = []
+    for _ in range(n_pool):
+        y = 0.1 * torch.randn(BATCH, 1, T_LEN, device=dev, generator=gen)
+        y_hat = (y + 0.05 * torch.randn(BATCH, 1, T_LEN, device=dev, generator=gen)).requires_grad_(True)
+        pool.append((y_hat, y))
+
+    launches = {"n": 0}
+
+    def step(i):
+        y_hat, y = pool[i % n_pool]
+        y_hat.grad = None
+        ml = mel(y_hat, y)                 # criterion["mel"](predict_y, natural_y)   trainerGAN.py:220
+        sc, mag = stft(y_hat, y)           # criterion["stft"](predict_y, natural_y)  trainerGAN.py:227
+        (sc + mag + ml).backward()
+        launches["n"] += (1 + 2 + 1) + (3 + 2 + 1)     # transform kernels + reduce + finalize + combine, per criterion
+        return sc, mag, ml
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches["n"] = 0
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for i in range(args.steps):
+        step(args.warmup + i)
+    ev1.record()
+    barrier()
+    elapsed_ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t.item())
+    ms_per_step = elapsed_ms / args.steps
+    value = world * BATCH * T_LEN / FS / (ms_per_step / 1000.0)
+
+    # ---- e2e: host (pinned) inputs -> H2D -> fwd+bwd -> D2H of the three losses, every step -------
+    host = [(p[0].detach().cpu().pin_memory(), p[1].cpu().pin_memory()) for p in pool[:4]]
+    def e2e_step(i):
+        hx, hy = host[i % len(host)]
+        x = hx.to(dev, non_blocking=True).requires_grad_(True)
+        y = hy.to(dev, non_blocking=True)
+        ml = mel(x, y)
+        sc, mag = stft(x, y)
+        (sc + mag + ml).backward()
+        return torch.stack([sc.detach(), mag.detach(), ml.detach()]).cpu()     # D2H + sync, as .item() in the trainer
+    for i in range(max(3, args.warmup // 4)):
+        e2e_step(i)
+    barrier()
+    e_steps = max(10, args.steps // 4)
+    t0 = time.perf_counter()
+    for i in range(e_steps):
+        e2e_step(i)
+    barrier()
+    e_ms = 1000.0 * (time.perf_counter() - t0) / e_steps
+    t = torch.tensor([e_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * BATCH * T_LEN / FS / (float(t.item()) / 1000.0)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- per-kernel timing of the dominant (transform) kernels, CUDA events on the launch stream ---
+    eng = cuda_engine()
+    x2 = pool[0][0].detach().reshape(BATCH, T_LEN)
+    y2 = pool[0][1].reshape(BATCH, T_LEN)
+    kernels = []
+    for name, plans in [("stft_1024_hop120", [stft.stft_losses[0].plan()]), ("stft_2048_hop240", [stft.stft_losses[1].plan()]),
+                        ("stft_512_hop50", [stft.stft_losses[2].plan()]), ("mel_2048_hop300", mel.plans())]:
+        for _ in range(5):
+            eng.forward(plans, x2, y2, need_grad=True)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 20
+        a.record()
+        for _ in range(reps):
+            eng.forward(plans, x2, y2, need_grad=True)      # transform kernel + tiny reduce/finalize
+        b.record()
+        torch.cuda.synchronize()
+        kernels.append({"name": name, "ms": a.elapsed_time(b) / reps})
+    dom = max(kernels, key=lambda k: k["ms"])
+    hbm_peak, peak_src = peaks()
+    alg_bytes = 8.0 * BATCH * T_LEN                           # one transform launch must read y_hat and y once
+    achieved = alg_bytes / (dom["ms"] * 1e-3) / 1e9
+    step_bytes = 20.0 * BATCH * T_LEN                         # bytes_min of the whole fwd+bwd
+    flops = nominal_flops(BATCH, T_LEN)
+    roofline = {"bound": "hbm", "kernel": "transform_kernel<" + dom["name"] + ">", "achieved": achieved, "peak": hbm_peak,
+                "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes,
+                "step_hbm_frac": step_bytes / (ms_per_step * 1e-3) / 1e9 / hbm_peak,
+                "binding_roof": "fp32 CUDA-core pipe, not HBM (SURVEY 8d: ~217 FLOP/B vs ridge ~11)",
+                "fp32_nominal_tflops": flops / (ms_per_step * 1e-3) / 1e12, "fp32_peak_tflops": 74.5,
+                "fp32_frac": flops / (ms_per_step * 1e-3) / 1e12 / 74.5,
+                "kernels_ms": kernels}
+
+    # ---- CPU baseline beside it (rank 0, N=1 only): bounded sample of the same workload -------------
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        times, cores = cpu_reference_step_time(BATCH, T_LEN, 10, 1)
+        best = min(times)
+        cpu = {"value": BATCH * T_LEN / FS / best, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"the full 16 x 1 s workload, 10 steps after 1 warm-up, best step {best * 1e3:.1f} ms "
+                         f"(mean {1e3 * sum(times) / len(times):.1f} ms); torch {torch.__version__} CPU ops, {os.cpu_count()} host cores"}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "configs[1]: batch 16 x 1 s synthetic 48 kHz per GPU, MR-STFT(1024/2048/512) + 80-mel hop-300, fwd+bwd",
+                       "global_batch": world * BATCH, "samples_per_utterance": T_LEN, "fs": FS,
+                       "api": "drop-in nn.Modules (MultiResolutionSTFTLoss + MultiMelSpectrogramLoss), eager launches",
+                       "l2": f"inputs rotate through a pool of {n_pool} pairs = {n_pool * pair_bytes >> 20} MB > 126 MB L2",
+                       "parallelism": f"batch-sharded x{world}, one all-reduce of 10 fp64 partial sums per criterion"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": pair_bytes, "d2h_bytes_per_step": 12,
+                    "steps": e_steps, "timing": "wall clock around pinned H2D + fwd+bwd + D2H of the 3 losses, max over ranks"},
+            "gpu_launches": launches["n"], "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world == 1 and args.gpus > 1:
+        # not launched under torchrun: re-exec ourselves with one rank per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -42,3 +42,69 @@ def rel_l2(a, b):
     a = np.asarray(a, dtype=np.float64).ravel()
     b = np.asarray(b, dtype=np.float64).ravel()
     return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+EMU_DIR = os.path.join(ROOT, "tests", "emu")
+
+
+@pytest.fixture(scope="session")
+def emu_engine():
+    """Host-side Engine over the CPU SIMT emulation of the kernels (tests/emu/specloss_emu.cpp).
+
+    Test infrastructure: it runs the same device code and the same C-ABI host logic as
+    libspecloss.so with host threads playing the lanes, so index maps, epilogues, overlap-add
+    and the Python driver are exercised without a GPU.  The product never loads it."""
+    import ctypes
+    import subprocess
+
+    from dl_speech_enhancement_b200 import _abi
+    from dl_speech_enhancement_b200.engine import Engine
+
+    so_path = os.path.join(EMU_DIR, "libspecloss_emu.so")
+    srcs = [os.path.join(EMU_DIR, "specloss_emu.cpp"), os.path.join(EMU_DIR, "cuda_emu.h"),
+            os.path.join(ROOT, "include", "specloss.h")] + \
+        [os.path.join(_abi.CSRC, f) for f in ("specloss_kernels.cuh", "specloss_host.inl", "fft_codelets.cuh")]
+    if not os.path.exists(so_path) or os.path.getmtime(so_path) < max(os.path.getmtime(s) for s in srcs):
+        cmd = ["g++", "-std=c++20", "-O1", "-fPIC", "-shared", "-pthread", "-I" + EMU_DIR, "-o", so_path, srcs[0]]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        assert res.returncode == 0, res.stderr
+    return Engine(_abi.bind(ctypes.CDLL(so_path)))
+
+
+def plans_for(golden):
+    from dl_speech_enhancement_b200 import modules
+
+    plans = []
+    if golden["stft_kwargs"] is not None:
+        plans += modules.MultiResolutionSTFTLoss(**golden["stft_kwargs"]).plans()
+    if golden["mel_kwargs"] is not None:
+        plans += modules.MultiMelSpectrogramLoss(**golden["mel_kwargs"]).plans()
+    return plans
+
+
+def run_losses(engine, golden, device="cpu", weights=(1.0, 1.0, 1.0)):
+    """Runs the product's autograd function on a golden case; returns ([sc, mag, mel], grad ndarray)."""
+    import torch
+
+    from dl_speech_enhancement_b200.functional import spectral_losses
+
+    plans = plans_for(golden)
+    if device != "cpu":
+        for p in plans:
+            p.window, p.twiddle = p.window.to(device), p.twiddle.to(device)
+            p.tables = {k: v.to(device) for k, v in p.tables.items()}
+    x = golden["y_hat"].to(device).clone().requires_grad_(True)
+    y = golden["y"].to(device)
+    outs = spectral_losses(x, y, plans, engine=engine)
+    vals = [0.0, 0.0, 0.0]
+    w = []
+    outs = list(outs)
+    if golden["stft_kwargs"] is not None:
+        vals[0], vals[1] = float(outs[0].detach()), float(outs[1].detach())
+        w += [weights[0], weights[1]]
+    if golden["mel_kwargs"] is not None:
+        vals[2] = float(outs[-1].detach())
+        w += [weights[2]]
+    total = sum(wi * o for wi, o in zip(w, outs))
+    total.backward()
+    return vals, x.grad.detach().cpu().numpy()

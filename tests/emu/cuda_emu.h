@@ -20,6 +20,7 @@ static inline float2 make_float2(float x, float y) { return float2{x, y}; }
 struct EmuWarp {
   std::barrier<> bar{32};
   float slots[32];
+  unsigned votes[32];
 };
 extern thread_local EmuWarp* emu_warp;
 extern thread_local int emu_lane;
@@ -30,6 +31,14 @@ static inline float __shfl_xor_sync(unsigned, float v, int lane_mask) {
   emu_warp->slots[emu_lane] = v;
   emu_warp->bar.arrive_and_wait();
   const float r = emu_warp->slots[emu_lane ^ lane_mask];
+  emu_warp->bar.arrive_and_wait();
+  return r;
+}
+static inline unsigned __ballot_sync(unsigned, bool pred) {
+  emu_warp->votes[emu_lane] = pred ? 1u : 0u;
+  emu_warp->bar.arrive_and_wait();
+  unsigned r = 0;
+  for (int i = 0; i < 32; ++i) r |= emu_warp->votes[i] << i;
   emu_warp->bar.arrive_and_wait();
   return r;
 }

@@ -1,0 +1,90 @@
+"""The C-ABI library builds for sm_100a, loads, exports every symbol include/specloss.h declares,
+and rejects bad arguments with messages.  No kernel is launched here (no GPU needed)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from dl_speech_enhancement_b200 import _abi
+from dl_speech_enhancement_b200.engine import twiddle_table
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    _abi.build_library()
+    return _abi.load_library()
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "specloss.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(spl_[a-z_]+)\s*\(", src)))
+
+
+def test_header_and_binding_agree():
+    assert declared_symbols() == sorted(_abi.EXPORTS)
+
+
+def test_every_declared_symbol_is_exported(lib):
+    for name in declared_symbols():
+        assert hasattr(lib, name), name
+    assert lib.spl_abi_version() == _abi.ABI_VERSION
+
+
+def test_library_is_sm100a_and_native():
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    out = subprocess.run([cuobjdump, "-lelf", _abi.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+def test_twiddle_table_matches_native(lib):
+    for n in (512, 1024, 2048):
+        buf = np.zeros(2 * n, np.float32)
+        assert lib.spl_fill_twiddle(n, buf.ctypes.data) == 0
+        np.testing.assert_array_equal(buf, twiddle_table(n).numpy())
+    assert lib.spl_fill_twiddle(300, buf.ctypes.data) == -1
+
+
+def _tr(**kw):
+    t = _abi.SplTransform()
+    t.kind, t.n_fft, t.hop, t.win, t.frames_per_chunk, t.eps = 0, 1024, 120, 600, 4, 1e-7
+    for k, v in kw.items():
+        setattr(t, k, v)
+    return t
+
+
+def test_geometry(lib):
+    g = _abi.SplGeometry()
+    assert lib.spl_geometry_of(ctypes.byref(_tr()), 16, 48000, ctypes.byref(g)) == 0
+    assert (g.n_frames, g.n_bins, g.n_chunks, g.span, g.n_sums) == (401, 513, 101, 3 * 120 + 600, 3)
+    assert g.partial_count == 16 * 101 * 3 and g.gchunk_bytes == 16 * 101 * 960 * 8
+    assert 0 < g.smem_bytes <= 227 * 1024
+
+
+@pytest.mark.parametrize("kw,frag", [
+    (dict(n_fft=768), "n_fft"), (dict(win=2000), "win"), (dict(hop=700), "hop"),
+    (dict(frames_per_chunk=0), "frames_per_chunk"), (dict(kind=7), "kind"),
+])
+def test_invalid_arguments_are_reported(lib, kw, frag):
+    g = _abi.SplGeometry()
+    assert lib.spl_geometry_of(ctypes.byref(_tr(**kw)), 2, 4800, ctypes.byref(g)) == -1
+    assert frag in lib.spl_last_error().decode()
+
+
+def test_too_short_signal_is_an_error(lib):
+    g = _abi.SplGeometry()
+    assert lib.spl_geometry_of(ctypes.byref(_tr()), 1, 512, ctypes.byref(g)) == -1   # T <= n_fft/2
+    assert "reflect" in lib.spl_last_error().decode()
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    monkeypatch.setattr(_abi, "_LIB", None)
+    monkeypatch.setattr(_abi, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(_abi.SpecLossError):
+        _abi.load_library()
