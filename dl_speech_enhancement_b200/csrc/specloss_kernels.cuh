@@ -274,7 +274,9 @@ SPL_DEVICE void transform_body(const TransformParams& p, float* smem, int block,
         const float pxc = fmaxf(px, p.eps), pyc = fmaxf(py, p.eps);
         const float rx = rsqrtf(pxc), ry = rsqrtf(pyc);
         const float ax = pxc * rx, ay = pyc * ry;
-        const float d = ay - ax;
+        // pxc == pyc must give an exact zero: `ay - ax` alone is contracted into an FMA by nvcc and
+        // would leave the rounding error of one product behind
+        const float d = (pxc == pyc) ? 0.f : ay - ax;
         s1 = fmaf(act * d, d, s1);
         s2 = fmaf(act, pyc, s2);
         const float lr = (pxc == pyc) ? 0.f : 0.5f * fabsf(SPL_FAST_LOGF(pyc * rx * rx));
@@ -283,7 +285,7 @@ SPL_DEVICE void transform_body(const TransformParams& p, float* smem, int block,
           const float gate = (px >= p.eps) ? 1.f : 0.f;
           const float sgn = (pxc > pyc) ? 1.f : ((pxc < pyc) ? -1.f : 0.f);
           // gX = alpha * X (spectral convergence, un-scaled) and beta * X (log magnitude, un-scaled)
-          const float alpha = gate * (ax - ay) * rx;
+          const float alpha = -gate * d * rx;
           const float beta = gate * sgn * rx * rx;
           const bool self_mirror = (k == km);
           const float wgt = self_mirror ? 1.f : 0.5f;   // Hermitian extension halves interior bins

@@ -142,7 +142,7 @@ def test_sums_are_additive_over_utterances(dev):
     full = eng.forward(plans, x, t, need_grad=False).sums.cpu().numpy()
     parts = sum(eng.forward(plans, x[i:i + 8].contiguous(), t[i:i + 8].contiguous(), need_grad=False).sums.cpu().numpy()
                 for i in range(0, 32, 8))
-    np.testing.assert_allclose(full, parts, rtol=1e-12)
+    np.testing.assert_allclose(full, parts, rtol=1e-6)   # chunk size (hence fp32 summation order inside a chunk) depends on the batch
     # and two utterances of that batch directly against the oracle's sums
     _, _, sums = so.analytic(y_hat[:2], y[:2], so.DEFAULT_STFT, so.mel_from_kwargs(**MEL48), dtype=np.float64)
     two = eng.forward(plans, x[:2].contiguous(), t[:2].contiguous(), need_grad=False).sums.cpu().numpy()
