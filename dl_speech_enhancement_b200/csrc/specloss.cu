@@ -26,23 +26,30 @@ int fail(int code, const char* fmt, ...) {
     if (e_ != cudaSuccess) return fail(SPL_E_CUDA, "%s: %s", #expr, cudaGetErrorString(e_)); \
   } while (0)
 
-template <int NFFT, int KIND, bool GRAD>
+template <int NFFT, int KIND, bool GRAD, int WIN_T>
 int spl_launch_transform(const spl::TransformParams& p, int n_mels, void* stream) {
   using SL = spl::SmemLayout<NFFT, KIND, GRAD>;
   const size_t smem = (size_t)SL::words_per_warp(p.ring_n, n_mels) * 4 * spl::kWarpsPerCta;
-  auto kern = spl::transform_kernel<NFFT, KIND, GRAD>;
+  auto kern = spl::transform_kernel<NFFT, KIND, GRAD, WIN_T>;
   if (smem > 227 * 1024) return fail(SPL_E_INVALID, "shared memory %zu B exceeds 227 KB (win/hop too large)", smem);
-  // opt in to > 48 KB dynamic shared memory; the attribute is per device, so track the device too
+  // per (instantiation, device): opt in to > 48 KB dynamic shared memory and ask how many CTAs fit an SM
   static thread_local size_t configured[64] = {0};
+  static thread_local int ctas_per_sm[64] = {0};
+  static thread_local int sm_count[64] = {0};
   int dev = 0;
   SPL_CUDA(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64) return fail(SPL_E_INVALID, "device ordinal %d out of range", dev);
-  if (smem > configured[dev]) {
+  if (smem != configured[dev]) {
     SPL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SPL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm[dev], kern, spl::kWarpsPerCta * 32, smem));
+    SPL_CUDA(cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev));
     configured[dev] = smem;
   }
+  // persistent-style launch: at most one resident wave, warps stride over the chunks
   const long long groups = (long long)p.B * p.n_chunks;
-  const unsigned grid = (unsigned)((groups + spl::kWarpsPerCta - 1) / spl::kWarpsPerCta);
+  const long long need = (groups + spl::kWarpsPerCta - 1) / spl::kWarpsPerCta;
+  const long long wave = (long long)sm_count[dev] * (ctas_per_sm[dev] > 0 ? ctas_per_sm[dev] : 1);
+  const unsigned grid = (unsigned)(need < wave ? need : wave);
   kern<<<grid, spl::kWarpsPerCta * 32, smem, static_cast<cudaStream_t>(stream)>>>(p);
   SPL_CUDA(cudaGetLastError());
   return SPL_OK;

@@ -2,7 +2,7 @@
 // the CUDA backend (specloss.cu) and by the CPU SIMT emulator used in the test-suite
 // (tests/emu/specloss_emu.cpp).  The includer provides, before including this file:
 //   int fail(int code, const char* fmt, ...);
-//   template <int NFFT, int KIND, bool GRAD> int spl_launch_transform(const spl::TransformParams&, int n_mels, void* stream);
+//   template <int NFFT, int KIND, bool GRAD, int WIN_T> int spl_launch_transform(const spl::TransformParams&, int n_mels, void* stream);
 //   int spl_launch_reduce(const spl::ReduceParams&, void* stream);
 //   int spl_launch_finalize(const spl::FinalizeParams&, void* stream);
 //   int spl_launch_combine(const spl::CombineParams&, void* stream);
@@ -44,13 +44,23 @@ void geometry(const spl_transform* t, int B, int T, spl_geometry* g) {
   g->smem_bytes = (int64_t)words * 4 * spl::kWarpsPerCta;
 }
 
-template <int NFFT>
-int launch_nfft(const spl::TransformParams& p, int kind, bool grad, int n_mels, void* s) {
+template <int NFFT, int WIN_T>
+int launch_win(const spl::TransformParams& p, int kind, bool grad, int n_mels, void* s) {
   if (kind == SPL_KIND_STFT)
-    return grad ? spl_launch_transform<NFFT, spl::kKindStft, true>(p, n_mels, s)
-                : spl_launch_transform<NFFT, spl::kKindStft, false>(p, n_mels, s);
-  return grad ? spl_launch_transform<NFFT, spl::kKindMel, true>(p, n_mels, s)
-              : spl_launch_transform<NFFT, spl::kKindMel, false>(p, n_mels, s);
+    return grad ? spl_launch_transform<NFFT, spl::kKindStft, true, WIN_T>(p, n_mels, s)
+                : spl_launch_transform<NFFT, spl::kKindStft, false, WIN_T>(p, n_mels, s);
+  return grad ? spl_launch_transform<NFFT, spl::kKindMel, true, WIN_T>(p, n_mels, s)
+              : spl_launch_transform<NFFT, spl::kKindMel, false, WIN_T>(p, n_mels, s);
+}
+
+// Window lengths of the shipped configurations get kernels with the window support known at compile
+// time (zero taps pruned); every other (n_fft, win) pair runs the generic kernel of that n_fft.
+int launch_any(const spl::TransformParams& p, int n_fft, int kind, bool grad, int n_mels, void* s) {
+  if (n_fft == 1024) return p.win == 600 ? launch_win<1024, 600>(p, kind, grad, n_mels, s) : launch_win<1024, 0>(p, kind, grad, n_mels, s);
+  if (n_fft == 512) return p.win == 240 ? launch_win<512, 240>(p, kind, grad, n_mels, s) : launch_win<512, 0>(p, kind, grad, n_mels, s);
+  if (p.win == 1200) return launch_win<2048, 1200>(p, kind, grad, n_mels, s);
+  if (p.win == 2048) return launch_win<2048, 2048>(p, kind, grad, n_mels, s);
+  return launch_win<2048, 0>(p, kind, grad, n_mels, s);
 }
 
 }  // namespace
@@ -94,7 +104,7 @@ int32_t spl_forward(const spl_transform* ts, int32_t n, const float* x, const fl
     if (!t->window || !t->twiddle || !t->partials) return fail(SPL_E_INVALID, "transform %d: null window/twiddle/partials", r);
     if (frames_in_flight(t->n_fft) == 2 && (t->frames_per_chunk & 1))
       return fail(SPL_E_INVALID, "transform %d: frames_per_chunk must be even for n_fft=512", r);
-    if (t->kind == SPL_KIND_MEL && (!t->mel_row_start || !t->mel_row_len || !t->mel_row_ptr || !t->mel_row_val ||
+    if (t->kind == SPL_KIND_MEL && (!t->mel_row_val || !t->mel_tasks || t->mel_rounds < 1 ||
                                      !t->bin_m0 || !t->bin_w0 || !t->bin_w1))
       return fail(SPL_E_INVALID, "transform %d: null mel table", r);
     spl_geometry g;
@@ -109,13 +119,11 @@ int32_t spl_forward(const spl_transform* ts, int32_t n, const float* x, const fl
     p.partials = t->partials; p.gchunks = t->gchunks;
     p.n_mels = t->kind == SPL_KIND_MEL ? t->n_mels : 0;
     p.inv_ln_base = t->inv_ln_base;
-    p.mel_row_start = t->mel_row_start; p.mel_row_len = t->mel_row_len; p.mel_row_ptr = t->mel_row_ptr;
-    p.mel_row_val = t->mel_row_val; p.bin_m0 = t->bin_m0; p.bin_w0 = t->bin_w0; p.bin_w1 = t->bin_w1;
+    p.mel_row_val = t->mel_row_val; p.mel_tasks = t->mel_tasks; p.mel_rounds = t->mel_rounds;
+    p.bin_m0 = t->bin_m0; p.bin_w0 = t->bin_w0; p.bin_w1 = t->bin_w1;
     const bool grad = t->gchunks != nullptr;
     void* s = stream;
-    if (t->n_fft == 512) rc = launch_nfft<512>(p, t->kind, grad, p.n_mels, s);
-    else if (t->n_fft == 1024) rc = launch_nfft<1024>(p, t->kind, grad, p.n_mels, s);
-    else rc = launch_nfft<2048>(p, t->kind, grad, p.n_mels, s);
+    rc = launch_any(p, t->n_fft, t->kind, grad, p.n_mels, s);
     if (rc) return rc;
   }
   return SPL_OK;

@@ -41,26 +41,59 @@ def twiddle_table(n_fft: int) -> torch.Tensor:
     return torch.from_numpy(tab.reshape(-1).copy())
 
 
-def mel_tables(melmat: np.ndarray):
-    """Band structure of the (K, n_mels) filterbank: per-row runs for the forward projection and the
-    (<= 2, adjacent) rows every bin feeds for the backward one.  Slaney/HTK triangles always satisfy
-    this; anything else raises (no dense fallback)."""
+MEL_ITER_TARGET = 8      # bins summed per lane per round of the projection schedule
+
+
+def mel_tables(melmat: np.ndarray, lanes: int = 32):
+    """Band structure of the (K, n_mels) filterbank, as the kernels consume it.
+
+    Forward projection: every mel row is a run of consecutive non-zero bins; a group of 1..`lanes`
+    lanes (power of two, sized so each lane sums about MEL_ITER_TARGET bins) strides over the run and
+    the group is reduced with shuffles.  Groups are packed into rounds of `lanes` lanes, largest
+    first, which keeps them aligned to their size.
+    Backward projection: every bin feeds at most two adjacent rows m0, m0+1.
+    Slaney/HTK triangles always satisfy both; anything else raises (there is no dense fallback)."""
     k_bins, n_mels = melmat.shape
-    if n_mels < 2:
-        raise NotImplementedError("num_mels < 2 is outside the kernels' envelope")
-    row_start = np.zeros(n_mels, np.int32)
-    row_len = np.zeros(n_mels, np.int32)
-    row_ptr = np.zeros(n_mels, np.int32)
-    vals = []
+    if not (2 <= n_mels <= 0xffe):
+        raise NotImplementedError("num_mels must be in [2, 4094] for the sm_100a kernels")
+    vals, rows = [], []
     ptr = 0
     for m in range(n_mels):
         nz = np.flatnonzero(melmat[:, m])
-        row_ptr[m] = ptr
-        if nz.size:
-            row_start[m], row_len[m] = nz[0], nz[-1] - nz[0] + 1
-            vals.append(melmat[nz[0]:nz[-1] + 1, m].astype(np.float32))
-            ptr += int(row_len[m])
+        start, length = (int(nz[0]), int(nz[-1] - nz[0] + 1)) if nz.size else (0, 0)
+        if length:
+            vals.append(melmat[start:start + length, m].astype(np.float32))
+        rows.append((m, start, length, ptr))
+        ptr += length
     row_val = np.concatenate(vals) if vals else np.zeros(1, np.float32)
+
+    def group_size(length):
+        g = 1
+        while g < lanes and g * MEL_ITER_TARGET < length:
+            g *= 2
+        return g
+
+    groups = sorted(((group_size(ln), m, st, ln, pt) for m, st, ln, pt in rows), key=lambda t: (-t[0], t[1]))
+    rounds, cur, used = [], [], 0
+    for g in groups:
+        if used + g[0] > lanes:
+            rounds.append(cur)
+            cur, used = [], 0
+        cur.append(g)
+        used += g[0]
+    if cur:
+        rounds.append(cur)
+    tasks = np.zeros((len(rounds), lanes, 4), np.int32)
+    for r, grp_list in enumerate(rounds):
+        lane = 0
+        iters = max((-(-ln // g) for g, _, _, ln, _ in grp_list), default=0)
+        tasks[r, :, 0] = 0xfff | (1 << 12) | (iters << 20)             # idle lanes
+        for g, m, st, ln, pt in grp_list:
+            for j in range(g):
+                cnt = max(0, -(-(ln - j) // g))
+                tasks[r, lane + j] = (m | (g << 12) | (iters << 20), st + j, cnt, pt + j)
+            lane += g
+
     bin_m0 = np.zeros(k_bins, np.int32)
     bin_w0 = np.zeros(k_bins, np.float32)
     bin_w1 = np.zeros(k_bins, np.float32)
@@ -79,8 +112,8 @@ def mel_tables(melmat: np.ndarray):
         else:
             bin_m0[k], bin_w1[k] = n_mels - 2, melmat[k, nz[0]]
     t = torch.from_numpy
-    return dict(mel_row_start=t(row_start), mel_row_len=t(row_len), mel_row_ptr=t(row_ptr),
-                mel_row_val=t(row_val), bin_m0=t(bin_m0), bin_w0=t(bin_w0), bin_w1=t(bin_w1))
+    return dict(mel_row_val=t(row_val), mel_tasks=t(tasks.reshape(-1).copy()),
+                bin_m0=t(bin_m0), bin_w0=t(bin_w0), bin_w1=t(bin_w1))
 
 
 @dataclass
@@ -187,6 +220,7 @@ class Engine:
                     if t.device != dev:
                         raise RuntimeError("mel tables are not on the input device: call .to(device)")
                     setattr(tr, name, _ptr(t))
+                tr.mel_rounds = pl.tables["mel_tasks"].numel() // (4 * fft_geometry(pl.n_fft)[0])
             g = self.geometry(tr, batch, t_len)
             st.geometries.append(g)
             partials = torch.empty(g.partial_count, dtype=torch.float64, device=dev)

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SPL_ABI_VERSION 1
+#define SPL_ABI_VERSION 2
 
 #define SPL_OK 0
 #define SPL_E_INVALID (-1)   /* bad argument / outside the supported envelope */
@@ -45,10 +45,11 @@ typedef struct spl_transform {
   /* --- mel only (kind == SPL_KIND_MEL); NULL / 0 otherwise --- */
   int32_t n_mels;
   float inv_ln_base;         /* 1/ln(log_base); 1 for log_base=None (mel_loss.py:63-71) */
-  const int32_t* mel_row_start; /* device [n_mels]: first bin of the row's non-zero run */
-  const int32_t* mel_row_len;   /* device [n_mels]: length of that run (0 = empty filter) */
-  const int32_t* mel_row_ptr;   /* device [n_mels]: offset of the run's weights in mel_row_val */
-  const float* mel_row_val;     /* device: melmat[k, m] for the runs, row after row */
+  const float* mel_row_val;     /* device: melmat[k, m] over each row's run of non-zero bins, row after row */
+  const int32_t* mel_tasks;     /* device [mel_rounds * L * 4]: projection schedule, L = 16 (n_fft 512) or 32;
+                                   per (round, lane): {row | group<<12 | round_iters<<20, first bin, iterations,
+                                   offset of the first weight in mel_row_val}; row 0xfff = idle lane */
+  int32_t mel_rounds;
   const int32_t* bin_m0;        /* device [n_fft/2+1]: bin k feeds mel rows m0 and m0+1 only */
   const float* bin_w0;          /* device [n_fft/2+1]: melmat[k, m0]   */
   const float* bin_w1;          /* device [n_fft/2+1]: melmat[k, m0+1] */

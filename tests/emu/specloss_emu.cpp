@@ -42,12 +42,13 @@ void run_warp(F&& body) {     // body(lane), 32 lanes in lock step
   for (auto& t : th) t.join();
 }
 
-template <int NFFT, int KIND, bool GRAD>
+template <int NFFT, int KIND, bool GRAD, int WIN_T>
 int spl_launch_transform(const spl::TransformParams& p, int n_mels, void*) {
   using SL = spl::SmemLayout<NFFT, KIND, GRAD>;
   const size_t words = (size_t)SL::words_per_warp(p.ring_n, n_mels) * spl::kWarpsPerCta;
   const long long groups = (long long)p.B * p.n_chunks;
-  const int grid = (int)((groups + spl::kWarpsPerCta - 1) / spl::kWarpsPerCta);
+  const int need = (int)((groups + spl::kWarpsPerCta - 1) / spl::kWarpsPerCta);
+  const int grid = std::min(need, 5);      // fewer CTAs than chunks: exercises the grid-stride loop
   std::vector<std::thread> blocks;
   const int par = std::max(1u, std::thread::hardware_concurrency());
   for (int b0 = 0; b0 < grid; b0 += par) {
@@ -56,7 +57,7 @@ int spl_launch_transform(const spl::TransformParams& p, int n_mels, void*) {
       blocks.emplace_back([&, block] {
         std::vector<float> smem(words, -12345.0f);   // poison: uninitialised reads show up as garbage
         for (int warp = 0; warp < spl::kWarpsPerCta; ++warp)
-          run_warp([&](int lane) { spl::transform_body<NFFT, KIND, GRAD>(p, smem.data(), block, warp * 32 + lane); });
+          run_warp([&](int lane) { spl::transform_body<NFFT, KIND, GRAD, WIN_T>(p, smem.data(), block, warp * 32 + lane, grid); });
       });
     for (auto& t : blocks) t.join();
   }

@@ -24,13 +24,25 @@ def test_matches_oracle_and_torchaudio(sr, n_fft, n_mels, fmin, fmax):
 
 
 @pytest.mark.parametrize("sr,n_fft,n_mels,fmin,fmax", CASES)
-def test_band_tables_reproduce_matrix(sr, n_fft, n_mels, fmin, fmax):
+@pytest.mark.parametrize("lanes", [16, 32])
+def test_band_tables_reproduce_matrix(sr, n_fft, n_mels, fmin, fmax, lanes):
     w = melfb.mel_filterbank(sr, n_fft, n_mels, fmin, fmax).T        # (K, M) as the melmat buffer
-    t = {k: v.numpy() for k, v in mel_tables(w).items()}
+    t = {k: v.numpy() for k, v in mel_tables(w, lanes=lanes).items()}
+    tasks = t["mel_tasks"].reshape(-1, lanes, 4)
     rebuilt = np.zeros_like(w)
-    for m in range(n_mels):
-        s, n, p = t["mel_row_start"][m], t["mel_row_len"][m], t["mel_row_ptr"][m]
-        rebuilt[s:s + n, m] = t["mel_row_val"][p:p + n]
+    seen = set()
+    for r in range(tasks.shape[0]):
+        for lane in range(lanes):
+            head, k0, cnt, off = tasks[r, lane]
+            row, grp, iters = head & 0xfff, (head >> 12) & 0xff, head >> 20
+            if row == 0xfff:
+                assert cnt == 0
+                continue
+            assert cnt <= iters and (lane % grp) == (lane - (lane // grp) * grp)
+            seen.add(row)
+            for s in range(cnt):
+                rebuilt[k0 + s * grp, row] += t["mel_row_val"][off + s * grp]
+    assert seen == set(range(n_mels))               # empty filters still get a (zero-length) task
     np.testing.assert_array_equal(rebuilt, w)
     rebuilt2 = np.zeros_like(w)
     k = np.arange(w.shape[0])
