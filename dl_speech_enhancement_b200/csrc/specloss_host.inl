@@ -12,6 +12,13 @@ bool supported_nfft(int n) { return n == 512 || n == 1024 || n == 2048; }
 
 int frames_in_flight(int n_fft) { return n_fft == 512 ? 2 : 1; }
 
+// overlap-add ring per warp; none when every chunk is a single frame (the frame is its own slot)
+int ring_entries(const spl_transform* t) {
+  const int fpw = frames_in_flight(t->n_fft);
+  if (fpw == 1 && t->frames_per_chunk == 1) return 0;
+  return t->win + (fpw - 1) * t->hop;
+}
+
 int check_transform(const spl_transform* t, int B, int T) {
   if (!t) return fail(SPL_E_INVALID, "null transform");
   if (t->kind != SPL_KIND_STFT && t->kind != SPL_KIND_MEL) return fail(SPL_E_INVALID, "kind %d unknown", t->kind);
@@ -34,7 +41,7 @@ void geometry(const spl_transform* t, int B, int T, spl_geometry* g) {
   g->n_sums = t->kind == SPL_KIND_STFT ? 3 : 1;
   g->partial_count = (int64_t)B * g->n_chunks * g->n_sums;
   g->gchunk_bytes = (int64_t)B * g->n_chunks * g->span * (t->kind == SPL_KIND_STFT ? 8 : 4);
-  const int ring_n = t->win + (frames_in_flight(t->n_fft) - 1) * t->hop;
+  const int ring_n = ring_entries(t);
   int words = 0;
 #define SPL_WORDS(N)                                                                                        \
   words = t->kind == SPL_KIND_STFT ? spl::SmemLayout<N, spl::kKindStft, true>::words_per_warp(ring_n, 0)    \
@@ -104,8 +111,7 @@ int32_t spl_forward(const spl_transform* ts, int32_t n, const float* x, const fl
     if (!t->window || !t->twiddle || !t->partials) return fail(SPL_E_INVALID, "transform %d: null window/twiddle/partials", r);
     if (frames_in_flight(t->n_fft) == 2 && (t->frames_per_chunk & 1))
       return fail(SPL_E_INVALID, "transform %d: frames_per_chunk must be even for n_fft=512", r);
-    if (t->kind == SPL_KIND_MEL && (!t->mel_row_val || !t->mel_tasks || t->mel_rounds < 1 ||
-                                     !t->bin_m0 || !t->bin_w0 || !t->bin_w1))
+    if (t->kind == SPL_KIND_MEL && (!t->mel_tasks || !t->mel_entries || t->mel_rounds < 1 || !t->bin_tab))
       return fail(SPL_E_INVALID, "transform %d: null mel table", r);
     spl_geometry g;
     geometry(t, B, T, &g);
@@ -114,13 +120,13 @@ int32_t spl_forward(const spl_transform* ts, int32_t n, const float* x, const fl
     p.x = x; p.y = y; p.B = B; p.T = T;
     p.hop = t->hop; p.win = t->win; p.left = (t->n_fft - t->win) / 2;
     p.n_frames = g.n_frames; p.m = t->frames_per_chunk; p.n_chunks = g.n_chunks; p.span = g.span;
-    p.ring_n = t->win + (frames_in_flight(t->n_fft) - 1) * t->hop;
+    p.ring_n = ring_entries(t);
     p.eps = t->eps; p.window = t->window; p.twiddle = reinterpret_cast<const float2*>(t->twiddle);
     p.partials = t->partials; p.gchunks = t->gchunks;
     p.n_mels = t->kind == SPL_KIND_MEL ? t->n_mels : 0;
     p.inv_ln_base = t->inv_ln_base;
-    p.mel_row_val = t->mel_row_val; p.mel_tasks = t->mel_tasks; p.mel_rounds = t->mel_rounds;
-    p.bin_m0 = t->bin_m0; p.bin_w0 = t->bin_w0; p.bin_w1 = t->bin_w1;
+    p.mel_tasks = t->mel_tasks; p.mel_entries = t->mel_entries; p.mel_rounds = t->mel_rounds;
+    p.bin_tab = t->bin_tab;
     const bool grad = t->gchunks != nullptr;
     void* s = stream;
     rc = launch_any(p, t->n_fft, t->kind, grad, p.n_mels, s);

@@ -16,6 +16,7 @@
 #include <cuda_runtime.h>
 #endif
 #include <stdint.h>
+#include <string.h>
 
 #define SPL_DEVICE __device__ __forceinline__
 #include "fft_codelets.cuh"
@@ -67,12 +68,10 @@ struct TransformParams {
   // mel only
   int n_mels;
   float inv_ln_base;     // 1 / ln(log_base)  (1 for natural log)
-  const float* mel_row_val;   // melmat[k, m] over every row's run of non-zero bins, row after row
-  const void* mel_tasks;      // MelTask[mel_rounds][L]: balanced projection schedule
+  const void* mel_tasks;      // int4[mel_rounds][L]: {row | group << 12 | iters << 20, first entry row, -, -}
+  const void* mel_entries;    // int2[sum iters][L]: {slot offset of the bin's amplitudes, weight bits}
   int mel_rounds;
-  const int* bin_m0;          // per bin: the two (adjacent) mel rows it feeds are m0, m0 + 1
-  const float* bin_w0;
-  const float* bin_w1;
+  const void* bin_tab;        // int4[K]: {m0, bits(W[k,m0]), bits(W[k,m0+1]), 0}: bin k feeds rows m0, m0+1 only
 };
 
 SPL_DEVICE float2 cmul(float2 a, float2 w) {            // a * w
@@ -99,7 +98,7 @@ struct SmemLayout {
   static __host__ __device__ int words_per_warp(int ring_n, int n_mels) {
     int w = FPW * BUF_F2 * 2;
     if (GRAD) w += (KIND == kKindStft ? 2 : 1) * ((ring_n + 3) & ~3);
-    if (KIND == kKindMel) w += FPW * ((n_mels + 3) & ~3);
+    if (KIND == kKindMel) w += FPW * 2 * ((n_mels + 3) & ~3);
     return (w + 3) & ~3;
   }
 };
@@ -155,10 +154,13 @@ SPL_DEVICE int reflect(int s, int T) {
   return s >= T ? 2 * (T - 1) - s : s;
 }
 
-// mel projection schedule entry (host-built, see engine.py:mel_schedule): one per (round, lane)
-//   x: row | group << 12 | round_iters << 20   (row 0xfff = idle lane)
-//   y: first bin of this lane   z: iterations of this lane   w: offset of its first weight
-struct MelTask { int x, y, z, w; };
+SPL_DEVICE float bits_to_float(int b) {
+#ifdef SPECLOSS_EMU
+  float f; memcpy(&f, &b, 4); return f;
+#else
+  return __int_as_float(b);
+#endif
+}
 
 // ---------------------------------------------------------------------------------------------
 // The transform kernel body.  One warp walks chunks of `m` consecutive frames of one utterance
@@ -180,7 +182,9 @@ SPL_DEVICE void transform_body(const TransformParams& p, float* smem, int block,
   float* ring_base = wsm + FPW * SL::BUF_F2 * 2;
   float2* ring2 = reinterpret_cast<float2*>(ring_base);              // stft: (u, v)
   float* ring1 = ring_base;                                          // mel : u
-  float* gm_s = ring_base + (GRAD ? (KIND == kKindStft ? 2 : 1) * align4(p.ring_n) : 0) + h * align4(p.n_mels);
+  float2* msum = reinterpret_cast<float2*>(ring_base + (GRAD ? (KIND == kKindStft ? 2 : 1) * align4(p.ring_n) : 0)) +
+                 h * align4(p.n_mels);              // mel: per-row (Mx, My), then (gM, -)
+  const bool no_ring = (FPW == 1) && (p.m == 1);    // one frame per chunk: windowed frame goes straight to its slot
   const float2* __restrict__ tw = p.twiddle;
   const float* __restrict__ wtab = p.window;
   const int total_chunks = p.B * p.n_chunks;
@@ -192,7 +196,7 @@ SPL_DEVICE void transform_body(const TransformParams& p, float* smem, int block,
     const float* __restrict__ xb = p.x + (size_t)b * p.T;
     const float* __restrict__ yb = p.y + (size_t)b * p.T;
 
-    if (GRAD) {
+    if (GRAD && !no_ring) {
       if (KIND == kKindStft) for (int i = lane; i < p.ring_n; i += 32) ring2[i] = make_float2(0.f, 0.f);
       else                   for (int i = lane; i < p.ring_n; i += 32) ring1[i] = 0.f;
       __syncwarp();
@@ -244,7 +248,7 @@ SPL_DEVICE void transform_body(const TransformParams& p, float* smem, int block,
           // ---- D. gradient spectrum H (slot layout) -> inverse DFT via swapped components ------
 #pragma unroll
           for (int n2 = 0; n2 < R; ++n2) {
-            const float2 v = buf[pos<NFFT>(l + L * n2)];
+            const float2 v = buf[(l + L * (n2 % (R / L))) * (L + 1) + n2 / (R / L)];   // element n = l + L*n2
             re[n2] = v.y;
             im[n2] = v.x;
           }
@@ -253,18 +257,33 @@ SPL_DEVICE void transform_body(const TransformParams& p, float* smem, int block,
         fft_core<NFFT>(re, im, buf, tw, l);
         if (job == 1) {
           // ---- E. window, overlap-add into the ring (slot holds (imag, real) = (v, u) swapped) --
-#pragma unroll 1
-          for (int hh = 0; hh < FPW; ++hh) {
-            if (h == hh && active) {
-              const int base = (jc * p.hop) % p.ring_n;
-              // first / last register slot with any live tap (compile-time when WIN_T > 0)
-              const int n2_lo = left / L, n2_hi = (left + win - 1) / L;
+          const int n2_lo = left / L, n2_hi = (left + win - 1) / L;      // register slots with live taps
+          if (no_ring) {
+            if (active) {
 #pragma unroll 4
               for (int n2 = n2_lo; n2 <= n2_hi; ++n2) {
                 const int tap = L * n2 - left + l;
                 if (tap >= 0 && tap < win) {
                   const float w = __ldg(&wtab[tap]);
-                  const float2 v = buf[pos<NFFT>(l + L * n2)];
+                  const float2 v = buf[(l + L * (n2 % (R / L))) * (L + 1) + n2 / (R / L)];
+                  if (KIND == kKindStft) out2[tap] = make_float2(v.y * w, v.x * w);
+                  else                   out1[tap] = v.y * w;
+                }
+              }
+            }
+            __syncwarp();
+            continue;
+          }
+#pragma unroll 1
+          for (int hh = 0; hh < FPW; ++hh) {
+            if (h == hh && active) {
+              const int base = (jc * p.hop) % p.ring_n;
+#pragma unroll 4
+              for (int n2 = n2_lo; n2 <= n2_hi; ++n2) {
+                const int tap = L * n2 - left + l;
+                if (tap >= 0 && tap < win) {
+                  const float w = __ldg(&wtab[tap]);
+                  const float2 v = buf[(l + L * (n2 % (R / L))) * (L + 1) + n2 / (R / L)];
                   int idx = base + tap;
                   idx -= (idx >= p.ring_n) ? p.ring_n : 0;
                   if (KIND == kKindStft) {
@@ -283,21 +302,26 @@ SPL_DEVICE void transform_body(const TransformParams& p, float* smem, int block,
           continue;
         }
         // ---- C. job 0 epilogue ------------------------------------------------------------------
+        // Bin k = row + R*col sits at buf[row*(L+1) + col].  A lane owns rows l + L*j; for col < L/2 the
+        // bin is k < N/2 and its mirror N-k is (R - row, L-1-col) -- or (0, L-col) inside row 0.  Bins 0
+        // and N/2 (row 0, cols 0 and L/2) mirror themselves; lane 0 handles N/2 as the extra pair.
+        constexpr int NP = (R / L) * (L / 2);             // pairs per lane
         if (KIND == kKindStft) {
           // Z = FFT(x + i y):  2X[k] = Z[k] + conj Z[N-k],  2Y[k] = -i (Z[k] - conj Z[N-k]).
           // Everything below works on the doubled spectra (powers x4, magnitudes x2); the sums are
           // rescaled once per chunk and the gradient factors absorb the scale.
           const float eps4 = 4.f * p.eps;
           if (active) {
-#pragma unroll 2
-            for (int i = 0; i <= NPAIR; ++i) {
-              const bool extra = (i == NPAIR);          // bin N/2: lane 0 of the group only
+#pragma unroll 4
+            for (int i = 0; i <= NP; ++i) {
+              const bool extra = (i == NP);
               if (extra && l != 0) break;
-              const int k = extra ? HALF : l + L * i;
-              const int km = (NFFT - k) & (NFFT - 1);
-              const bool self_mirror = (k == km);       // k = 0 or N/2
-              const int pk = pos<NFFT>(k), pm = pos<NFFT>(km);
-              const float2 a = buf[pk], bm = buf[pm];
+              const int j = extra ? 0 : i / (L / 2), cidx = extra ? L / 2 : i % (L / 2);
+              const int row = l + L * j;
+              const bool self_mirror = extra || (row == 0 && cidx == 0);
+              float2* qa = buf + row * (L + 1) + cidx;
+              float2* qb = self_mirror ? qa : (row == 0 ? buf + (L - cidx) : buf + (R - row) * (L + 1) + (L - 1 - cidx));
+              const float2 a = *qa, bm = *qb;
               const float xr = a.x + bm.x, xi = a.y - bm.y;                       // 2 X[k]
               const float yr = frame_equal ? xr : a.y + bm.y;                     // 2 Y[k]
               const float yi = frame_equal ? xi : bm.x - a.x;
@@ -320,8 +344,8 @@ SPL_DEVICE void transform_body(const TransformParams& p, float* smem, int block,
                 const float bsel = (pxc > pyc) ? rx2 : ((pxc < pyc) ? -rx2 : 0.f);
                 const float gi = gate ? 2.f * wgt * bsel : 0.f;
                 const float p1 = gr * xr, p2 = gi * xi, p3 = gr * xi, p4 = gi * xr;
-                buf[pk] = make_float2(p1 - p2, p3 + p4);                    // (gr + i gi) * (2X)
-                if (!self_mirror) buf[pm] = make_float2(p1 + p2, p4 - p3);  // (gr + i gi) * conj(2X)
+                *qa = make_float2(p1 - p2, p3 + p4);                    // (gr + i gi) * (2X)
+                if (!self_mirror) *qb = make_float2(p1 + p2, p4 - p3);  // (gr + i gi) * conj(2X)
               }
             }
           } else if (GRAD) {
@@ -329,83 +353,86 @@ SPL_DEVICE void transform_body(const TransformParams& p, float* smem, int block,
           }
         } else {
           // ---- mel: amplitudes -> banded projection -> log-mel L1 -> gradient spectrum ------------
-          // pass 1: X stays at pos(k); (Ax, Ay) parked at pos(N-k); bin 0's amplitudes and the raw
-          // Z[N/2] go to the two spare pad slots of rows 0 and 1.
+          // pass 1: X stays in the bin's own slot; (Ax, Ay) are parked in the mirror slot; bin 0 parks
+          // them in the pad slot of row 0, bin N/2 keeps them in place and moves X to the pad slot of row 1.
           constexpr int EX0 = L, EX1 = (L + 1) + L;
-#pragma unroll 2
-          for (int i = 0; i <= NPAIR; ++i) {
-            const bool extra = (i == NPAIR);
+#pragma unroll 4
+          for (int i = 0; i <= NP; ++i) {
+            const bool extra = (i == NP);
             if (extra && l != 0) break;
-            const int k = extra ? HALF : l + L * i;
-            const int km = (NFFT - k) & (NFFT - 1);
-            const int pk = pos<NFFT>(k), pm = pos<NFFT>(km);
-            const float2 a = buf[pk], bm = buf[pm];
+            const int j = extra ? 0 : i / (L / 2), cidx = extra ? L / 2 : i % (L / 2);
+            const int row = l + L * j;
+            const bool self_mirror = extra || (row == 0 && cidx == 0);
+            float2* qa = buf + row * (L + 1) + cidx;
+            float2* qb = self_mirror ? qa : (row == 0 ? buf + (L - cidx) : buf + (R - row) * (L + 1) + (L - 1 - cidx));
+            const float2 a = *qa, bm = *qb;
             const float xr = 0.5f * (a.x + bm.x), xi = 0.5f * (a.y - bm.y);
             const float yr = frame_equal ? xr : 0.5f * (a.y + bm.y);
             const float yi = frame_equal ? xi : 0.5f * (bm.x - a.x);
             const float pxc = fmaxf(fmaf(xr, xr, xi * xi), p.eps), pyc = fmaxf(fmaf(yr, yr, yi * yi), p.eps);
             const float2 amp = make_float2(pxc * rsqrtf(pxc), pyc * rsqrtf(pyc));
-            if (k == 0) { buf[EX0] = amp; buf[pk] = make_float2(xr, xi); }
-            else if (extra) { buf[EX1] = make_float2(xr, xi); buf[pk] = amp; }
-            else { buf[pk] = make_float2(xr, xi); buf[pm] = amp; }
+            if (extra) { buf[EX1] = make_float2(xr, xi); *qa = amp; }
+            else { *qa = make_float2(xr, xi); *(self_mirror ? buf + EX0 : qb) = amp; }
           }
           __syncwarp();
-          // pass 2: balanced projection.  Every mel row is summed by a group of 1..L lanes (host-built
-          // schedule), then reduced with shuffles.
+          // pass 2: balanced projection.  Every mel row is summed by a group of 1..L lanes walking a
+          // host-built table of (amplitude slot, weight) entries, then reduced with shuffles.
           for (int r = 0; r < p.mel_rounds; ++r) {
             const int4 tk = __ldg(reinterpret_cast<const int4*>(p.mel_tasks) + r * L + l);
             const int row = tk.x & 0xfff, grp = (tk.x >> 12) & 0xff, iters = tk.x >> 20;
-            const float* __restrict__ wv = p.mel_row_val + tk.w;
+            const int2* __restrict__ en = reinterpret_cast<const int2*>(p.mel_entries) + (size_t)tk.y * L + l;
             float mx = 0.f, my = 0.f;
+#pragma unroll 4
             for (int s = 0; s < iters; ++s) {
-              if (s < tk.z) {
-                const int k = tk.y + s * grp;
-                const float2 amp = buf[k == 0 ? EX0 : pos<NFFT>(NFFT - k)];
-                const float w = __ldg(&wv[s * grp]);
-                mx = fmaf(amp.x, w, mx);
-                my = fmaf(amp.y, w, my);
-              }
+              const int2 e = __ldg(en + s * L);
+              const float2 amp = buf[e.x];
+              const float w = bits_to_float(e.y);
+              mx = fmaf(amp.x, w, mx);
+              my = fmaf(amp.y, w, my);
             }
 #pragma unroll
             for (int o = 1; o < L; o <<= 1) {
               const float tx = __shfl_xor_sync(0xffffffffu, mx, o), ty = __shfl_xor_sync(0xffffffffu, my, o);
               if (o < grp) { mx += tx; my += ty; }
             }
-            if (row != 0xfff && (l & (grp - 1)) == 0) {
-              const float mxc = fmaxf(mx, p.eps), myc = fmaxf(my, p.eps);
-              const float dl = (mxc == myc) ? 0.f : (logf(mxc) - logf(myc)) * p.inv_ln_base;
-              if (active) s1 += fabsf(dl);
-              if (GRAD) {
-                const float sgn = (dl > 0.f) ? 1.f : ((dl < 0.f) ? -1.f : 0.f);
-                gm_s[row] = (mx >= p.eps) ? sgn * p.inv_ln_base / mxc : 0.f;
-              }
+            if (row != 0xfff && (l & (grp - 1)) == 0) msum[row] = make_float2(mx, my);
+          }
+          __syncwarp();
+          for (int row = l; row < p.n_mels; row += L) {
+            const float2 mm = msum[row];
+            const float mxc = fmaxf(mm.x, p.eps), myc = fmaxf(mm.y, p.eps);
+            const float dl = (mxc == myc) ? 0.f : (logf(mxc) - logf(myc)) * p.inv_ln_base;
+            if (active) s1 += fabsf(dl);
+            if (GRAD) {
+              const float sgn = (dl > 0.f) ? 1.f : ((dl < 0.f) ? -1.f : 0.f);
+              msum[row].x = (mm.x >= p.eps) ? sgn * p.inv_ln_base / mxc : 0.f;     // gM[row]
             }
           }
           __syncwarp();
           if (GRAD) {
             // pass 3: gA[k] = sum_m gM[m] W[k,m] (<= 2 adjacent rows), H[k] = w gA gate / Ax * X
-#pragma unroll 2
-            for (int i = 0; i <= NPAIR; ++i) {
-              const bool extra = (i == NPAIR);
+#pragma unroll 4
+            for (int i = 0; i <= NP; ++i) {
+              const bool extra = (i == NP);
               if (extra && l != 0) break;
-              const int k = extra ? HALF : l + L * i;
-              const int km = (NFFT - k) & (NFFT - 1);
-              const int pk = pos<NFFT>(k), pm = pos<NFFT>(km);
-              const float2 xk = extra ? buf[EX1] : buf[pk];
-              const float2 amp = (k == 0) ? buf[EX0] : buf[pm];
-              const int m0 = __ldg(&p.bin_m0[k]);
-              const float ga = fmaf(gm_s[m0], __ldg(&p.bin_w0[k]), gm_s[m0 + 1] * __ldg(&p.bin_w1[k]));
+              const int j = extra ? 0 : i / (L / 2), cidx = extra ? L / 2 : i % (L / 2);
+              const int row = l + L * j;
+              const bool self_mirror = extra || (row == 0 && cidx == 0);
+              float2* qa = buf + row * (L + 1) + cidx;
+              float2* qb = self_mirror ? qa : (row == 0 ? buf + (L - cidx) : buf + (R - row) * (L + 1) + (L - 1 - cidx));
+              const float2 xk = extra ? buf[EX1] : *qa;
+              const int4 bt = __ldg(reinterpret_cast<const int4*>(p.bin_tab) + (row + R * cidx));
+              const float ga = fmaf(msum[bt.x].x, bits_to_float(bt.y), msum[bt.x + 1].x * bits_to_float(bt.z));
               const float px = fmaf(xk.x, xk.x, xk.y * xk.y);
-              const bool self_mirror = (k == km);
-              const float g = (active && px >= p.eps) ? (self_mirror ? 1.f : 0.5f) * ga / amp.x : 0.f;
-              buf[pk] = make_float2(g * xk.x, g * xk.y);
-              if (!self_mirror) buf[pm] = make_float2(g * xk.x, -g * xk.y);
+              const float g = (active && px >= p.eps) ? (self_mirror ? 1.f : 0.5f) * ga * rsqrtf(px) : 0.f;
+              *qa = make_float2(g * xk.x, g * xk.y);
+              if (!self_mirror) *qb = make_float2(g * xk.x, -g * xk.y);
             }
           }
         }
         __syncwarp();
       }  // job
-      if (GRAD) {
+      if (GRAD && !no_ring) {
         // ---- F. flush the ring entries no later frame of this chunk touches ----------------------
         const int done = min(m_c, (step + 1) * FPW);
         const int limit = (done == m_c) ? span_c : done * p.hop;

@@ -41,31 +41,36 @@ def twiddle_table(n_fft: int) -> torch.Tensor:
     return torch.from_numpy(tab.reshape(-1).copy())
 
 
-MEL_ITER_TARGET = 8      # bins summed per lane per round of the projection schedule
+MEL_ITER_TARGET = 16     # bins summed per lane per round of the projection schedule
 
 
-def mel_tables(melmat: np.ndarray, lanes: int = 32):
+def slot_offset(n_fft: int, k: int) -> int:
+    """float2 index of spectrum element k inside a frame slot: row k % R (pitch L + 1), column k // R."""
+    lanes, rows = fft_geometry(n_fft)
+    return (k % rows) * (lanes + 1) + k // rows
+
+
+def mel_tables(melmat: np.ndarray, n_fft: int):
     """Band structure of the (K, n_mels) filterbank, as the kernels consume it.
 
-    Forward projection: every mel row is a run of consecutive non-zero bins; a group of 1..`lanes`
-    lanes (power of two, sized so each lane sums about MEL_ITER_TARGET bins) strides over the run and
-    the group is reduced with shuffles.  Groups are packed into rounds of `lanes` lanes, largest
-    first, which keeps them aligned to their size.
+    Forward projection: every mel row is a run of consecutive non-zero bins; a group of 1..L lanes
+    (power of two, sized so each lane sums about MEL_ITER_TARGET bins) strides over the run and the
+    group is reduced with shuffles.  Groups are packed into rounds of L lanes, largest first, which
+    keeps them aligned to their size.  Each lane walks a dense list of (amplitude slot, weight)
+    entries, so the inner loop has no index arithmetic; padding entries carry weight 0.
+    The amplitudes of bin k are parked by the kernel in the slot of the mirror bin n_fft - k (bin 0: the
+    pad slot of row 0), see specloss_kernels.cuh.
     Backward projection: every bin feeds at most two adjacent rows m0, m0+1.
     Slaney/HTK triangles always satisfy both; anything else raises (there is no dense fallback)."""
+    lanes, _ = fft_geometry(n_fft)
     k_bins, n_mels = melmat.shape
+    assert k_bins == n_fft // 2 + 1
     if not (2 <= n_mels <= 0xffe):
         raise NotImplementedError("num_mels must be in [2, 4094] for the sm_100a kernels")
-    vals, rows = [], []
-    ptr = 0
+    rows = []
     for m in range(n_mels):
         nz = np.flatnonzero(melmat[:, m])
-        start, length = (int(nz[0]), int(nz[-1] - nz[0] + 1)) if nz.size else (0, 0)
-        if length:
-            vals.append(melmat[start:start + length, m].astype(np.float32))
-        rows.append((m, start, length, ptr))
-        ptr += length
-    row_val = np.concatenate(vals) if vals else np.zeros(1, np.float32)
+        rows.append((m, int(nz[0]), int(nz[-1] - nz[0] + 1)) if nz.size else (m, 0, 0))
 
     def group_size(length):
         g = 1
@@ -73,7 +78,7 @@ def mel_tables(melmat: np.ndarray, lanes: int = 32):
             g *= 2
         return g
 
-    groups = sorted(((group_size(ln), m, st, ln, pt) for m, st, ln, pt in rows), key=lambda t: (-t[0], t[1]))
+    groups = sorted(((group_size(ln), m, st, ln) for m, st, ln in rows), key=lambda t: (-t[0], t[1]))
     rounds, cur, used = [], [], 0
     for g in groups:
         if used + g[0] > lanes:
@@ -84,19 +89,26 @@ def mel_tables(melmat: np.ndarray, lanes: int = 32):
     if cur:
         rounds.append(cur)
     tasks = np.zeros((len(rounds), lanes, 4), np.int32)
+    entries = []
+    amp_slot = lambda k: lanes if k == 0 else slot_offset(n_fft, n_fft - k)      # noqa: E731
     for r, grp_list in enumerate(rounds):
-        lane = 0
-        iters = max((-(-ln // g) for g, _, _, ln, _ in grp_list), default=0)
+        iters = max((-(-ln // g) for g, _, _, ln in grp_list), default=0)
+        ent = np.zeros((iters, lanes, 2), np.int32)
         tasks[r, :, 0] = 0xfff | (1 << 12) | (iters << 20)             # idle lanes
-        for g, m, st, ln, pt in grp_list:
+        tasks[r, :, 1] = len(entries)
+        lane = 0
+        for g, m, st, ln in grp_list:
             for j in range(g):
-                cnt = max(0, -(-(ln - j) // g))
-                tasks[r, lane + j] = (m | (g << 12) | (iters << 20), st + j, cnt, pt + j)
+                tasks[r, lane + j, 0] = m | (g << 12) | (iters << 20)
+                for s_i, k in enumerate(range(st + j, st + ln, g)):
+                    ent[s_i, lane + j, 0] = amp_slot(k)
+                    ent[s_i, lane + j, 1] = np.float32(melmat[k, m]).view(np.int32)
             lane += g
+        entries.extend(ent)
+    entries = np.stack(entries) if entries else np.zeros((1, lanes, 2), np.int32)
 
-    bin_m0 = np.zeros(k_bins, np.int32)
-    bin_w0 = np.zeros(k_bins, np.float32)
-    bin_w1 = np.zeros(k_bins, np.float32)
+    bin_tab = np.zeros((k_bins, 4), np.int32)
+    f2i = lambda v: np.float32(v).view(np.int32)                                 # noqa: E731
     for k in range(k_bins):
         nz = np.flatnonzero(melmat[k])
         if nz.size == 0:
@@ -106,14 +118,14 @@ def mel_tables(melmat: np.ndarray, lanes: int = 32):
                 f"mel filterbank row for bin {k} feeds mels {nz.tolist()}: only banded filterbanks "
                 "(<= 2 adjacent mels per bin, e.g. librosa/Slaney triangles) are supported")
         if nz.size == 2:
-            bin_m0[k], bin_w0[k], bin_w1[k] = nz[0], melmat[k, nz[0]], melmat[k, nz[1]]
+            bin_tab[k, :3] = (nz[0], f2i(melmat[k, nz[0]]), f2i(melmat[k, nz[1]]))
         elif nz[0] < n_mels - 1:
-            bin_m0[k], bin_w0[k] = nz[0], melmat[k, nz[0]]
+            bin_tab[k, :3] = (nz[0], f2i(melmat[k, nz[0]]), 0)
         else:
-            bin_m0[k], bin_w1[k] = n_mels - 2, melmat[k, nz[0]]
+            bin_tab[k, :3] = (n_mels - 2, 0, f2i(melmat[k, nz[0]]))
     t = torch.from_numpy
-    return dict(mel_row_val=t(row_val), mel_tasks=t(tasks.reshape(-1).copy()),
-                bin_m0=t(bin_m0), bin_w0=t(bin_w0), bin_w1=t(bin_w1))
+    return dict(mel_tasks=t(tasks.reshape(-1).copy()), mel_entries=t(entries.reshape(-1).copy()),
+                bin_tab=t(bin_tab.reshape(-1).copy()))
 
 
 @dataclass
@@ -143,11 +155,17 @@ class TransformPlan:
 def choose_frames_per_chunk(batch: int, n_frames: int, n_fft: int) -> int:
     """Frames walked by one warp.  Small problems want many short chunks (parallelism: the whole
     config-2 batch is 27.6k frames for ~2.4k resident warps), big ones longer chunks (less seam
-    traffic in the gradient slots)."""
+    traffic in the gradient slots).  SPECLOSS_FRAMES_PER_CHUNK overrides: "4" or "1024:2,2048:1,512:4"."""
     env = os.environ.get("SPECLOSS_FRAMES_PER_CHUNK")
+    m = None
     if env:
-        m = max(1, int(env))
-    else:
+        if ":" in env:
+            spec = dict(item.split(":") for item in env.split(","))
+            if str(n_fft) in spec:
+                m = max(1, int(spec[str(n_fft)]))
+        else:
+            m = max(1, int(env))
+    if m is None:
         resident = _SM_COUNT * (8 if n_fft == 2048 else 16)
         m = int(round(batch * n_frames / (4.0 * resident)))
         m = max(2, min(16, m))

@@ -126,11 +126,11 @@ class MelSpectrogram(torch.nn.Module):
             raise ValueError(f"log_base: {log_base} is not supported.")
         self.num_mels = num_mels
         self.register_buffer("_twiddle", twiddle_table(fft_size), persistent=False)
-        for name, t in mel_tables(mel.T, lanes=fft_geometry(fft_size)[0]).items():
+        for name, t in mel_tables(mel.T, fft_size).items():
             self.register_buffer("_" + name, t, persistent=False)
 
     def plan(self) -> TransformPlan:
-        tables = {n: getattr(self, "_" + n) for n in ("mel_row_val", "mel_tasks", "bin_m0", "bin_w0", "bin_w1")}
+        tables = {n: getattr(self, "_" + n) for n in ("mel_tasks", "mel_entries", "bin_tab")}
         inv_ln = 1.0 if self.log_base is None else 1.0 / math.log(self.log_base)
         return TransformPlan(SPL_KIND_MEL, self.fft_size, self.hop_size, self.win_length, self.eps,
                              self.window, self._twiddle, self.num_mels, inv_ln, tables)

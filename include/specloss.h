@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SPL_ABI_VERSION 2
+#define SPL_ABI_VERSION 3
 
 #define SPL_OK 0
 #define SPL_E_INVALID (-1)   /* bad argument / outside the supported envelope */
@@ -38,21 +38,20 @@ extern "C" {
 typedef struct spl_transform {
   int32_t kind;              /* SPL_KIND_* */
   int32_t n_fft, hop, win;   /* torch.stft(x, n_fft, hop, win, window), center=True, reflect pad */
-  int32_t frames_per_chunk;  /* consecutive frames walked by one warp (>= 1; even if n_fft==512) */
+  int32_t frames_per_chunk;  /* consecutive frames walked by one warp (>= 1; even if n_fft==512); 1 = no
+                                shared-memory overlap-add, every windowed frame goes straight to its slot */
   float eps;                 /* clamp on |X|^2: 1e-7 (stft_loss.py:19) / 1e-10 (mel_loss.py:35); mel reuses it on the mel energies */
   const float* window;       /* device, `win` taps (the module's registered buffer) */
   const float* twiddle;      /* device, 2*n_fft floats written by spl_fill_twiddle() */
   /* --- mel only (kind == SPL_KIND_MEL); NULL / 0 otherwise --- */
   int32_t n_mels;
   float inv_ln_base;         /* 1/ln(log_base); 1 for log_base=None (mel_loss.py:63-71) */
-  const float* mel_row_val;     /* device: melmat[k, m] over each row's run of non-zero bins, row after row */
-  const int32_t* mel_tasks;     /* device [mel_rounds * L * 4]: projection schedule, L = 16 (n_fft 512) or 32;
-                                   per (round, lane): {row | group<<12 | round_iters<<20, first bin, iterations,
-                                   offset of the first weight in mel_row_val}; row 0xfff = idle lane */
+  const int32_t* mel_tasks;     /* device [mel_rounds * L * 4] (L = 16 for n_fft 512, else 32): per (round, lane)
+                                   {row | group<<12 | iters<<20, first entry row of the round, 0, 0}; row 0xfff = idle */
+  const int32_t* mel_entries;   /* device [sum(iters) * L * 2]: per (entry row, lane) {slot offset of the bin's
+                                   amplitudes inside the frame slot, bits of melmat[k, m]}; padding = {0, 0.0f} */
   int32_t mel_rounds;
-  const int32_t* bin_m0;        /* device [n_fft/2+1]: bin k feeds mel rows m0 and m0+1 only */
-  const float* bin_w0;          /* device [n_fft/2+1]: melmat[k, m0]   */
-  const float* bin_w1;          /* device [n_fft/2+1]: melmat[k, m0+1] */
+  const int32_t* bin_tab;       /* device [(n_fft/2+1) * 4]: {m0, bits(melmat[k,m0]), bits(melmat[k,m0+1]), 0} */
   /* --- per-call workspace, sized by spl_geometry() --- */
   double* partials;          /* device [partial_count] */
   void* gchunks;             /* device [gchunk_bytes]; NULL = forward only (torch.no_grad) */

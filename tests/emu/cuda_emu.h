@@ -16,6 +16,7 @@
 
 struct float2 { float x, y; };
 struct int4 { int x, y, z, w; };
+struct int2 { int x, y; };
 static inline float __fmul_rn(float a, float b) { return a * b; }
 static inline float __fsub_rn(float a, float b) { return a - b; }
 static inline float2 make_float2(float x, float y) { return float2{x, y}; }

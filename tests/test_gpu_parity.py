@@ -150,15 +150,23 @@ def test_sums_are_additive_over_utterances(dev):
 
 
 def test_long_form_24k(dev):
-    """BASELINE configs[4] shape per utterance: 60 s @ 24 kHz (framing / overlap-add stress), vs the oracle."""
+    """BASELINE configs[4] shape per utterance: 60 s @ 24 kHz (framing / overlap-add stress), vs the oracle.
+    At 1.2e7 bins per resolution the reference's own fp32 torch.norm / mean accumulate ~1e-4 of error
+    (see oracle/spectral_oracle.py:mr_stft_loss), so the fp64 oracle is the yardstick here and the fp32
+    route is only required to be as close to us as it is to fp64."""
     from oracle import spectral_oracle as so
     y_hat, y = so.synth_pair(2, 1440000, seed=6)
     stft, mel = _modules({}, MEL24, dev)
     vals, grad = _run(stft, mel, y_hat, y, dev)
-    ref, gref = so.losses_and_grad(y_hat, y, so.DEFAULT_STFT, so.mel_from_kwargs(**MEL24), dtype=torch.float32,
-                                   use_torch_stft=True)
-    np.testing.assert_allclose(vals, ref, rtol=LOSS_RTOL)
-    assert rel_l2(grad, gref.numpy()) <= GRAD_RTOL
+    ref64, gref64 = so.losses_and_grad(y_hat, y, so.DEFAULT_STFT, so.mel_from_kwargs(**MEL24), dtype=torch.float64)
+    ref32, gref32 = so.losses_and_grad(y_hat, y, so.DEFAULT_STFT, so.mel_from_kwargs(**MEL24), dtype=torch.float32,
+                                       use_torch_stft=True)
+    print("ours", vals, "ref64", ref64, "ref32", ref32)
+    np.testing.assert_allclose(vals, ref64, rtol=LOSS_RTOL)
+    assert rel_l2(grad, gref64.numpy()) <= GRAD_RTOL
+    yard = max(abs(a - b) / abs(b) for a, b in zip(ref32, ref64))
+    assert max(abs(a - b) / abs(b) for a, b in zip(vals, ref32)) <= max(LOSS_RTOL, 2 * yard)
+    assert rel_l2(grad, gref32.numpy()) <= max(GRAD_RTOL, 2 * rel_l2(gref32.numpy(), gref64.numpy()))
 
 
 @pytest.mark.parametrize("m", ["1", "2", "5", "16", "40"])

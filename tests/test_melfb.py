@@ -24,33 +24,41 @@ def test_matches_oracle_and_torchaudio(sr, n_fft, n_mels, fmin, fmax):
 
 
 @pytest.mark.parametrize("sr,n_fft,n_mels,fmin,fmax", CASES)
-@pytest.mark.parametrize("lanes", [16, 32])
-def test_band_tables_reproduce_matrix(sr, n_fft, n_mels, fmin, fmax, lanes):
+def test_band_tables_reproduce_matrix(sr, n_fft, n_mels, fmin, fmax):
+    from dl_speech_enhancement_b200.engine import fft_geometry, slot_offset
+    lanes, _ = fft_geometry(n_fft)
     w = melfb.mel_filterbank(sr, n_fft, n_mels, fmin, fmax).T        # (K, M) as the melmat buffer
-    t = {k: v.numpy() for k, v in mel_tables(w, lanes=lanes).items()}
+    t = {k: v.numpy() for k, v in mel_tables(w, n_fft).items()}
     tasks = t["mel_tasks"].reshape(-1, lanes, 4)
+    entries = t["mel_entries"].reshape(-1, lanes, 2)
+    slot_to_bin = {(lanes if k == 0 else slot_offset(n_fft, n_fft - k)): k for k in range(w.shape[0])}
+    assert len(slot_to_bin) == w.shape[0]           # amplitude slots are distinct
     rebuilt = np.zeros_like(w)
     seen = set()
     for r in range(tasks.shape[0]):
         for lane in range(lanes):
-            head, k0, cnt, off = tasks[r, lane]
+            head, base = tasks[r, lane, 0], tasks[r, lane, 1]
             row, grp, iters = head & 0xfff, (head >> 12) & 0xff, head >> 20
-            if row == 0xfff:
-                assert cnt == 0
-                continue
-            assert cnt <= iters and (lane % grp) == (lane - (lane // grp) * grp)
-            seen.add(row)
-            for s in range(cnt):
-                rebuilt[k0 + s * grp, row] += t["mel_row_val"][off + s * grp]
-    assert seen == set(range(n_mels))               # empty filters still get a (zero-length) task
+            for s in range(iters):
+                off, wbits = entries[base + s, lane]
+                wt = np.int32(wbits).view(np.float32)
+                if row == 0xfff:
+                    assert wt == 0
+                elif wt != 0:
+                    rebuilt[slot_to_bin[off], row] += wt
+            if row != 0xfff:
+                seen.add(row)
+                assert lane % grp == lane - (lane // grp) * grp
+    assert seen == set(range(n_mels))               # empty filters still get a task
     np.testing.assert_array_equal(rebuilt, w)
+    bt = t["bin_tab"].reshape(-1, 4)
     rebuilt2 = np.zeros_like(w)
     k = np.arange(w.shape[0])
-    rebuilt2[k, t["bin_m0"]] += t["bin_w0"]
-    rebuilt2[k, t["bin_m0"] + 1] += t["bin_w1"]
+    rebuilt2[k, bt[:, 0]] += bt[:, 1].view(np.float32)
+    rebuilt2[k, bt[:, 0] + 1] += bt[:, 2].view(np.float32)
     np.testing.assert_array_equal(rebuilt2, w)
 
 
 def test_dense_filterbank_rejected():
     with pytest.raises(NotImplementedError):
-        mel_tables(np.ones((513, 8), np.float32))
+        mel_tables(np.ones((513, 8), np.float32), 1024)
