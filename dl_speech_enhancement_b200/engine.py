@@ -166,9 +166,14 @@ def choose_frames_per_chunk(batch: int, n_frames: int, n_fft: int) -> int:
         else:
             m = max(1, int(env))
     if m is None:
-        resident = _SM_COUNT * (8 if n_fft == 2048 else 16)
-        m = int(round(batch * n_frames / (4.0 * resident)))
-        m = max(2, min(16, m))
+        if n_fft == 2048:
+            # one frame per chunk: no overlap-add ring in shared memory, 12 instead of 8 warps per SM
+            # (measured on B200, config 2: mel 154 -> 84 us, stft-2048 93 -> 60 us)
+            m = 1
+        else:
+            resident = _SM_COUNT * 16
+            m = int(round(batch * n_frames / (4.0 * resident)))
+            m = max(2, min(16, m))
     if n_fft == 512 and (m & 1):        # two frames in flight per warp
         m += 1
     return m
