@@ -15,7 +15,7 @@ from ctypes import POINTER, c_char_p, c_double, c_float, c_int32, c_int64, c_voi
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libspecloss.so")
 CSRC = os.path.join(_HERE, "csrc")
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 SPL_KIND_STFT = 0
 SPL_KIND_MEL = 1
@@ -33,7 +33,7 @@ class SplTransform(ctypes.Structure):
         ("frames_per_chunk", c_int32), ("eps", c_float),
         ("window", c_void_p), ("twiddle", c_void_p),
         ("n_mels", c_int32), ("inv_ln_base", c_float),
-        ("mel_tasks", c_void_p), ("mel_entries", c_void_p), ("mel_rounds", c_int32), ("bin_tab", c_void_p),
+        ("mel_tasks", c_void_p), ("mel_entries", c_void_p), ("mel_rounds", c_int32), ("mel_entry_rows", c_int32), ("bin_tab", c_void_p),
         ("partials", c_void_p), ("gchunks", c_void_p),
     ]
 
@@ -41,7 +41,7 @@ class SplTransform(ctypes.Structure):
 class SplGeometry(ctypes.Structure):
     _fields_ = [
         ("n_frames", c_int32), ("n_bins", c_int32), ("n_chunks", c_int32), ("span", c_int32),
-        ("n_sums", c_int32), ("partial_count", c_int64), ("gchunk_bytes", c_int64), ("smem_bytes", c_int64),
+        ("n_sums", c_int32), ("partial_count", c_int64), ("gchunk_bytes", c_int64), ("smem_table_bytes", c_int64), ("smem_warp_bytes", c_int64),
     ]
 
 

@@ -26,31 +26,41 @@ int fail(int code, const char* fmt, ...) {
     if (e_ != cudaSuccess) return fail(SPL_E_CUDA, "%s: %s", #expr, cudaGetErrorString(e_)); \
   } while (0)
 
+constexpr size_t kMaxSmem = 227 * 1024;
+
 template <int NFFT, int KIND, bool GRAD, int WIN_T>
 int spl_launch_transform(const spl::TransformParams& p, int n_mels, void* stream) {
   using SL = spl::SmemLayout<NFFT, KIND, GRAD>;
-  const size_t smem = (size_t)SL::words_per_warp(p.ring_n, n_mels) * 4 * spl::kWarpsPerCta;
+  constexpr int L = spl::FftGeom<NFFT>::L;
+  const spl::CtaTables ct = spl::cta_tables(NFFT, p.win, KIND, L, p.mel_rounds, p.mel_entry_rows);
+  const size_t table_bytes = (size_t)ct.total * 4;
+  const size_t warp_bytes = (size_t)SL::words_per_warp(p.ring_n, n_mels) * 4;
+  if (table_bytes + warp_bytes > kMaxSmem)
+    return fail(SPL_E_INVALID, "shared memory %zu B (tables) + %zu B (one warp) exceeds 227 KB", table_bytes, warp_bytes);
   auto kern = spl::transform_kernel<NFFT, KIND, GRAD, WIN_T>;
-  if (smem > 227 * 1024) return fail(SPL_E_INVALID, "shared memory %zu B exceeds 227 KB (win/hop too large)", smem);
-  // per (instantiation, device): opt in to > 48 KB dynamic shared memory and ask how many CTAs fit an SM
-  static thread_local size_t configured[64] = {0};
-  static thread_local int ctas_per_sm[64] = {0};
+  // per (instantiation, device): opt in to the full 227 KB of dynamic shared memory
+  static thread_local bool configured[64] = {false};
   static thread_local int sm_count[64] = {0};
   int dev = 0;
   SPL_CUDA(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64) return fail(SPL_E_INVALID, "device ordinal %d out of range", dev);
-  if (smem != configured[dev]) {
-    SPL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    SPL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm[dev], kern, spl::kWarpsPerCta * 32, smem));
+  if (!configured[dev]) {
+    SPL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
     SPL_CUDA(cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev));
-    configured[dev] = smem;
+    configured[dev] = true;
   }
-  // persistent-style launch: at most one resident wave, warps stride over the chunks
-  const long long groups = (long long)p.B * p.n_chunks;
-  const long long need = (groups + spl::kWarpsPerCta - 1) / spl::kWarpsPerCta;
-  const long long wave = (long long)sm_count[dev] * (ctas_per_sm[dev] > 0 ? ctas_per_sm[dev] : 1);
-  const unsigned grid = (unsigned)(need < wave ? need : wave);
-  kern<<<grid, spl::kWarpsPerCta * 32, smem, static_cast<cudaStream_t>(stream)>>>(p);
+  // One persistent CTA per SM.  Warps per CTA: as many as registers (launch bounds) and shared memory
+  // allow, but no more than needed to give every SM work; warps then stride over the chunks.
+  const long long chunks = (long long)p.B * p.n_chunks;
+  int wpc = spl::MaxWarps<NFFT>::value;
+  const int by_smem = (int)((kMaxSmem - table_bytes) / warp_bytes);
+  if (by_smem < wpc) wpc = by_smem;
+  const long long spread = (chunks + sm_count[dev] - 1) / sm_count[dev];
+  if (spread < wpc) wpc = (int)(spread < 1 ? 1 : spread);
+  const long long need = (chunks + wpc - 1) / wpc;
+  const unsigned grid = (unsigned)(need < sm_count[dev] ? need : sm_count[dev]);
+  const size_t smem = table_bytes + warp_bytes * wpc;
+  kern<<<grid, wpc * 32, smem, static_cast<cudaStream_t>(stream)>>>(p);
   SPL_CUDA(cudaGetLastError());
   return SPL_OK;
 }

@@ -48,7 +48,10 @@ void geometry(const spl_transform* t, int B, int T, spl_geometry* g) {
                                    : spl::SmemLayout<N, spl::kKindMel, true>::words_per_warp(ring_n, t->n_mels)
   if (t->n_fft == 512) { SPL_WORDS(512); } else if (t->n_fft == 1024) { SPL_WORDS(1024); } else { SPL_WORDS(2048); }
 #undef SPL_WORDS
-  g->smem_bytes = (int64_t)words * 4 * spl::kWarpsPerCta;
+  const int lanes = t->n_fft == 512 ? 16 : 32;
+  const spl::CtaTables ct = spl::cta_tables(t->n_fft, t->win, t->kind, lanes, t->mel_rounds, t->mel_entry_rows);
+  g->smem_table_bytes = (int64_t)ct.total * 4;
+  g->smem_warp_bytes = (int64_t)words * 4;
 }
 
 template <int NFFT, int WIN_T>
@@ -111,7 +114,7 @@ int32_t spl_forward(const spl_transform* ts, int32_t n, const float* x, const fl
     if (!t->window || !t->twiddle || !t->partials) return fail(SPL_E_INVALID, "transform %d: null window/twiddle/partials", r);
     if (frames_in_flight(t->n_fft) == 2 && (t->frames_per_chunk & 1))
       return fail(SPL_E_INVALID, "transform %d: frames_per_chunk must be even for n_fft=512", r);
-    if (t->kind == SPL_KIND_MEL && (!t->mel_tasks || !t->mel_entries || t->mel_rounds < 1 || !t->bin_tab))
+    if (t->kind == SPL_KIND_MEL && (!t->mel_tasks || !t->mel_entries || t->mel_rounds < 1 || t->mel_entry_rows < 1 || !t->bin_tab))
       return fail(SPL_E_INVALID, "transform %d: null mel table", r);
     spl_geometry g;
     geometry(t, B, T, &g);
@@ -125,7 +128,9 @@ int32_t spl_forward(const spl_transform* ts, int32_t n, const float* x, const fl
     p.partials = t->partials; p.gchunks = t->gchunks;
     p.n_mels = t->kind == SPL_KIND_MEL ? t->n_mels : 0;
     p.inv_ln_base = t->inv_ln_base;
-    p.mel_tasks = t->mel_tasks; p.mel_entries = t->mel_entries; p.mel_rounds = t->mel_rounds;
+    p.mel_tasks = t->mel_tasks; p.mel_entries = t->mel_entries;
+    p.mel_rounds = t->kind == SPL_KIND_MEL ? t->mel_rounds : 0;
+    p.mel_entry_rows = t->kind == SPL_KIND_MEL ? t->mel_entry_rows : 0;
     p.bin_tab = t->bin_tab;
     const bool grad = t->gchunks != nullptr;
     void* s = stream;

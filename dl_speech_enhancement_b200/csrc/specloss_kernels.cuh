@@ -29,7 +29,6 @@
 
 namespace spl {
 
-constexpr int kWarpsPerCta = 4;
 constexpr int kKindStft = 0;
 constexpr int kKindMel = 1;
 
@@ -69,8 +68,9 @@ struct TransformParams {
   int n_mels;
   float inv_ln_base;     // 1 / ln(log_base)  (1 for natural log)
   const void* mel_tasks;      // int4[mel_rounds][L]: {row | group << 12 | iters << 20, first entry row, -, -}
-  const void* mel_entries;    // int2[sum iters][L]: {slot offset of the bin's amplitudes, weight bits}
+  const void* mel_entries;    // int2[mel_entry_rows][L]: {slot offset of the bin's amplitudes, weight bits}
   int mel_rounds;
+  int mel_entry_rows;         // sum of iters over the rounds
   const void* bin_tab;        // int4[K]: {m0, bits(W[k,m0]), bits(W[k,m0+1]), 0}: bin k feeds rows m0, m0+1 only
 };
 
@@ -87,7 +87,25 @@ SPL_DEVICE float warp_sum(float v) {
   return v;
 }
 
+// Constant tables of a transform, staged once per CTA in shared memory (one persistent CTA per SM):
+// at 200+ KB of shared memory per SM the L1 keeps only ~28 KB, and twiddles + window + mel tables
+// (30-64 KB) would otherwise be re-fetched from L2 at every frame (r1c profile: long-scoreboard 3.7/issue).
+struct CtaTables {
+  int tw, win, tasks, entries, bintab, total;     // word offsets
+};
 SPL_DEVICE int align4(int n) { return (n + 3) & ~3; }
+static __host__ __device__ inline CtaTables cta_tables(int n_fft, int win, int kind, int lanes, int mel_rounds,
+                                                       int mel_entry_rows) {
+  CtaTables t;
+  int o = 0;
+  t.tw = o;      o += 2 * n_fft;
+  t.win = o;     o += (win + 3) & ~3;
+  t.tasks = o;   o += kind == kKindMel ? 4 * mel_rounds * lanes : 0;
+  t.entries = o; o += kind == kKindMel ? ((2 * mel_entry_rows * lanes + 3) & ~3) : 0;
+  t.bintab = o;  o += kind == kKindMel ? 4 * (n_fft / 2 + 1) : 0;
+  t.total = o;
+  return t;
+}
 
 // shared memory carve-up per warp (in 4-byte words); the host side uses the same function
 template <int NFFT, int KIND, bool GRAD>
@@ -120,14 +138,14 @@ SPL_DEVICE int pos(int k) {
 // ---------------------------------------------------------------------------------------------
 template <int NFFT>
 SPL_DEVICE void fft_core(float (&re)[FftGeom<NFFT>::R], float (&im)[FftGeom<NFFT>::R],
-                         float2* buf, const float2* __restrict__ tw, int l) {
+                         float2* buf, const float2* tw, int l) {
   using G = FftGeom<NFFT>;
   constexpr int L = G::L, R = G::R, RPL = R / L;
   Dft<R>::run(re, im);
 #pragma unroll
   for (int k2 = 0; k2 < R; ++k2) {
     float2 v = make_float2(re[k2], im[k2]);
-    if (k2 > 0) v = cmul(v, __ldg(&tw[k2 * L + l]));
+    if (k2 > 0) v = cmul(v, tw[k2 * L + l]);
     buf[k2 * (L + 1) + l] = v;
   }
   __syncwarp();
@@ -167,17 +185,43 @@ SPL_DEVICE float bits_to_float(int b) {
 // (grid-stride over chunks).  WIN_T > 0: window length known at compile time (shipped configs),
 // which prunes the zero taps out of the load, the first butterflies and the overlap-add.
 // ---------------------------------------------------------------------------------------------
+// CTA prologue: every thread copies its share of the constant tables into shared memory.
+template <int NFFT, int KIND>
+SPL_DEVICE void cta_load_tables(const TransformParams& p, float* smem, int tid, int nthreads) {
+  constexpr int L = FftGeom<NFFT>::L;
+  const CtaTables ct = cta_tables(NFFT, p.win, KIND, L, p.mel_rounds, p.mel_entry_rows);
+  const float* tw = reinterpret_cast<const float*>(p.twiddle);
+  for (int i = tid; i < 2 * NFFT; i += nthreads) smem[ct.tw + i] = __ldg(&tw[i]);
+  for (int i = tid; i < p.win; i += nthreads) smem[ct.win + i] = __ldg(&p.window[i]);
+  if (KIND == kKindMel) {
+    int* ism = reinterpret_cast<int*>(smem);
+    const int* a = reinterpret_cast<const int*>(p.mel_tasks);
+    const int* b = reinterpret_cast<const int*>(p.mel_entries);
+    const int* c = reinterpret_cast<const int*>(p.bin_tab);
+    for (int i = tid; i < 4 * p.mel_rounds * L; i += nthreads) ism[ct.tasks + i] = __ldg(&a[i]);
+    for (int i = tid; i < 2 * p.mel_entry_rows * L; i += nthreads) ism[ct.entries + i] = __ldg(&b[i]);
+    for (int i = tid; i < 4 * (NFFT / 2 + 1); i += nthreads) ism[ct.bintab + i] = __ldg(&c[i]);
+  }
+}
+
 template <int NFFT, int KIND, bool GRAD, int WIN_T>
-SPL_DEVICE void transform_body(const TransformParams& p, float* smem, int block, int tid, int grid) {
+SPL_DEVICE void transform_body(const TransformParams& p, float* smem, int block, int tid, int grid, int wpc) {
   using G = FftGeom<NFFT>;
   using SL = SmemLayout<NFFT, KIND, GRAD>;
-  constexpr int L = G::L, R = G::R, FPW = SL::FPW, HALF = NFFT / 2, NPAIR = NFFT / (2 * L);
+  constexpr int L = G::L, R = G::R, FPW = SL::FPW, HALF = NFFT / 2;
   const int warp = tid >> 5, lane = tid & 31;
   const int l = lane & (L - 1), h = lane / L;
   const int win = WIN_T > 0 ? WIN_T : p.win;
   const int left = WIN_T > 0 ? (NFFT - WIN_T) / 2 : p.left;
 
-  float* wsm = smem + (size_t)warp * SL::words_per_warp(p.ring_n, p.n_mels);
+  const CtaTables ct = cta_tables(NFFT, p.win, KIND, L, p.mel_rounds, p.mel_entry_rows);
+  const float2* tw = reinterpret_cast<const float2*>(smem + ct.tw);
+  const float* wtab = smem + ct.win;
+  const int4* mel_tasks = reinterpret_cast<const int4*>(smem + ct.tasks);
+  const int2* mel_entries = reinterpret_cast<const int2*>(smem + ct.entries);
+  const int4* bin_tab = reinterpret_cast<const int4*>(smem + ct.bintab);
+
+  float* wsm = smem + ct.total + (size_t)warp * SL::words_per_warp(p.ring_n, p.n_mels);
   float2* buf = reinterpret_cast<float2*>(wsm) + h * SL::BUF_F2;     // this frame slot
   float* ring_base = wsm + FPW * SL::BUF_F2 * 2;
   float2* ring2 = reinterpret_cast<float2*>(ring_base);              // stft: (u, v)
@@ -185,11 +229,9 @@ SPL_DEVICE void transform_body(const TransformParams& p, float* smem, int block,
   float2* msum = reinterpret_cast<float2*>(ring_base + (GRAD ? (KIND == kKindStft ? 2 : 1) * align4(p.ring_n) : 0)) +
                  h * align4(p.n_mels);              // mel: per-row (Mx, My), then (gM, -)
   const bool no_ring = (FPW == 1) && (p.m == 1);    // one frame per chunk: windowed frame goes straight to its slot
-  const float2* __restrict__ tw = p.twiddle;
-  const float* __restrict__ wtab = p.window;
   const int total_chunks = p.B * p.n_chunks;
 
-  for (int chunk_id = block * kWarpsPerCta + warp; chunk_id < total_chunks; chunk_id += grid * kWarpsPerCta) {
+  for (int chunk_id = block * wpc + warp; chunk_id < total_chunks; chunk_id += grid * wpc) {
     const int b = chunk_id / p.n_chunks, c = chunk_id - b * p.n_chunks;
     const int t0 = c * p.m;
     const int m_c = min(p.m, p.n_frames - t0);
@@ -230,7 +272,7 @@ SPL_DEVICE void transform_body(const TransformParams& p, float* smem, int block,
             if (active && (all_lanes || (tap >= 0 && tap < win))) {
               int s = s0 + L * n2 + l;
               if (!interior) s = reflect(s, p.T);
-              const float w = __ldg(&wtab[tap]);
+              const float w = wtab[tap];
               xv = __ldg(&xb[s]) * w;
               yv = __ldg(&yb[s]) * w;
             }
@@ -264,7 +306,7 @@ SPL_DEVICE void transform_body(const TransformParams& p, float* smem, int block,
               for (int n2 = n2_lo; n2 <= n2_hi; ++n2) {
                 const int tap = L * n2 - left + l;
                 if (tap >= 0 && tap < win) {
-                  const float w = __ldg(&wtab[tap]);
+                  const float w = wtab[tap];
                   const float2 v = buf[(l + L * (n2 % (R / L))) * (L + 1) + n2 / (R / L)];
                   if (KIND == kKindStft) out2[tap] = make_float2(v.y * w, v.x * w);
                   else                   out1[tap] = v.y * w;
@@ -282,7 +324,7 @@ SPL_DEVICE void transform_body(const TransformParams& p, float* smem, int block,
               for (int n2 = n2_lo; n2 <= n2_hi; ++n2) {
                 const int tap = L * n2 - left + l;
                 if (tap >= 0 && tap < win) {
-                  const float w = __ldg(&wtab[tap]);
+                  const float w = wtab[tap];
                   const float2 v = buf[(l + L * (n2 % (R / L))) * (L + 1) + n2 / (R / L)];
                   int idx = base + tap;
                   idx -= (idx >= p.ring_n) ? p.ring_n : 0;
@@ -378,13 +420,13 @@ SPL_DEVICE void transform_body(const TransformParams& p, float* smem, int block,
           // pass 2: balanced projection.  Every mel row is summed by a group of 1..L lanes walking a
           // host-built table of (amplitude slot, weight) entries, then reduced with shuffles.
           for (int r = 0; r < p.mel_rounds; ++r) {
-            const int4 tk = __ldg(reinterpret_cast<const int4*>(p.mel_tasks) + r * L + l);
+            const int4 tk = mel_tasks[r * L + l];
             const int row = tk.x & 0xfff, grp = (tk.x >> 12) & 0xff, iters = tk.x >> 20;
-            const int2* __restrict__ en = reinterpret_cast<const int2*>(p.mel_entries) + (size_t)tk.y * L + l;
+            const int2* en = mel_entries + tk.y * L + l;
             float mx = 0.f, my = 0.f;
 #pragma unroll 4
             for (int s = 0; s < iters; ++s) {
-              const int2 e = __ldg(en + s * L);
+              const int2 e = en[s * L];
               const float2 amp = buf[e.x];
               const float w = bits_to_float(e.y);
               mx = fmaf(amp.x, w, mx);
@@ -421,7 +463,7 @@ SPL_DEVICE void transform_body(const TransformParams& p, float* smem, int block,
               float2* qa = buf + row * (L + 1) + cidx;
               float2* qb = self_mirror ? qa : (row == 0 ? buf + (L - cidx) : buf + (R - row) * (L + 1) + (L - 1 - cidx));
               const float2 xk = extra ? buf[EX1] : *qa;
-              const int4 bt = __ldg(reinterpret_cast<const int4*>(p.bin_tab) + (row + R * cidx));
+              const int4 bt = bin_tab[row + R * cidx];
               const float ga = fmaf(msum[bt.x].x, bits_to_float(bt.y), msum[bt.x + 1].x * bits_to_float(bt.z));
               const float px = fmaf(xk.x, xk.x, xk.y * xk.y);
               const float g = (active && px >= p.eps) ? (self_mirror ? 1.f : 0.5f) * ga * rsqrtf(px) : 0.f;
@@ -585,11 +627,16 @@ SPL_DEVICE void combine_body(const CombineParams& p, long long gid) {
 }
 
 #ifndef SPECLOSS_EMU
-// register budget: 3 CTAs (12 warps) per SM for the 64-point-per-lane kernels, 4 for the others
+// One persistent CTA per SM: up to 12 warps (168 registers) for the 64-point-per-lane kernels, 16 (128
+// registers) for the others; the host picks the actual warp count from the shared-memory budget.
+template <int NFFT> struct MaxWarps { static constexpr int value = NFFT == 2048 ? 12 : 16; };
+
 template <int NFFT, int KIND, bool GRAD, int WIN_T>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, NFFT == 2048 ? 3 : 4) transform_kernel(const TransformParams p) {
+__global__ void __launch_bounds__(MaxWarps<NFFT>::value * 32, 1) transform_kernel(const TransformParams p) {
   extern __shared__ __align__(16) float smem_dyn[];
-  transform_body<NFFT, KIND, GRAD, WIN_T>(p, smem_dyn, blockIdx.x, threadIdx.x, gridDim.x);
+  cta_load_tables<NFFT, KIND>(p, smem_dyn, threadIdx.x, blockDim.x);
+  __syncthreads();
+  transform_body<NFFT, KIND, GRAD, WIN_T>(p, smem_dyn, blockIdx.x, threadIdx.x, gridDim.x, blockDim.x >> 5);
 }
 __global__ void __launch_bounds__(256) reduce_kernel(const ReduceParams p) {
   __shared__ double sh[256];

@@ -243,7 +243,9 @@ class Engine:
                     if t.device != dev:
                         raise RuntimeError("mel tables are not on the input device: call .to(device)")
                     setattr(tr, name, _ptr(t))
-                tr.mel_rounds = pl.tables["mel_tasks"].numel() // (4 * fft_geometry(pl.n_fft)[0])
+                lanes = fft_geometry(pl.n_fft)[0]
+                tr.mel_rounds = pl.tables["mel_tasks"].numel() // (4 * lanes)
+                tr.mel_entry_rows = pl.tables["mel_entries"].numel() // (2 * lanes)
             g = self.geometry(tr, batch, t_len)
             st.geometries.append(g)
             partials = torch.empty(g.partial_count, dtype=torch.float64, device=dev)

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SPL_ABI_VERSION 3
+#define SPL_ABI_VERSION 4
 
 #define SPL_OK 0
 #define SPL_E_INVALID (-1)   /* bad argument / outside the supported envelope */
@@ -51,6 +51,7 @@ typedef struct spl_transform {
   const int32_t* mel_entries;   /* device [sum(iters) * L * 2]: per (entry row, lane) {slot offset of the bin's
                                    amplitudes inside the frame slot, bits of melmat[k, m]}; padding = {0, 0.0f} */
   int32_t mel_rounds;
+  int32_t mel_entry_rows;       /* sum of iters over the rounds */
   const int32_t* bin_tab;       /* device [(n_fft/2+1) * 4]: {m0, bits(melmat[k,m0]), bits(melmat[k,m0+1]), 0} */
   /* --- per-call workspace, sized by spl_geometry() --- */
   double* partials;          /* device [partial_count] */
@@ -65,7 +66,8 @@ typedef struct spl_geometry {
   int32_t n_sums;            /* 3 (S1, S2, S3) for STFT, 1 (S4) for mel */
   int64_t partial_count;     /* doubles in `partials` */
   int64_t gchunk_bytes;      /* bytes in `gchunks` */
-  int64_t smem_bytes;        /* dynamic shared memory per CTA of the transform kernel */
+  int64_t smem_table_bytes;  /* shared memory per CTA for the constant tables (twiddle, window, mel tables) */
+  int64_t smem_warp_bytes;   /* shared memory per warp (frame slot(s), overlap-add ring, mel scratch) */
 } spl_geometry;
 
 int32_t spl_abi_version(void);

@@ -45,10 +45,13 @@ void run_warp(F&& body) {     // body(lane), 32 lanes in lock step
 template <int NFFT, int KIND, bool GRAD, int WIN_T>
 int spl_launch_transform(const spl::TransformParams& p, int n_mels, void*) {
   using SL = spl::SmemLayout<NFFT, KIND, GRAD>;
-  const size_t words = (size_t)SL::words_per_warp(p.ring_n, n_mels) * spl::kWarpsPerCta;
-  const long long groups = (long long)p.B * p.n_chunks;
-  const int need = (int)((groups + spl::kWarpsPerCta - 1) / spl::kWarpsPerCta);
-  const int grid = std::min(need, 5);      // fewer CTAs than chunks: exercises the grid-stride loop
+  constexpr int L = spl::FftGeom<NFFT>::L;
+  const spl::CtaTables ct = spl::cta_tables(NFFT, p.win, KIND, L, p.mel_rounds, p.mel_entry_rows);
+  const int wpc = 3;                       // odd on purpose; fewer warps than chunks exercises the stride loop
+  const size_t words = (size_t)ct.total + (size_t)SL::words_per_warp(p.ring_n, n_mels) * wpc;
+  const long long chunks = (long long)p.B * p.n_chunks;
+  const int need = (int)((chunks + wpc - 1) / wpc);
+  const int grid = std::min(need, 5);
   std::vector<std::thread> blocks;
   const int par = std::max(1u, std::thread::hardware_concurrency());
   for (int b0 = 0; b0 < grid; b0 += par) {
@@ -56,8 +59,11 @@ int spl_launch_transform(const spl::TransformParams& p, int n_mels, void*) {
     for (int block = b0; block < std::min(grid, b0 + par); ++block)
       blocks.emplace_back([&, block] {
         std::vector<float> smem(words, -12345.0f);   // poison: uninitialised reads show up as garbage
-        for (int warp = 0; warp < spl::kWarpsPerCta; ++warp)
-          run_warp([&](int lane) { spl::transform_body<NFFT, KIND, GRAD, WIN_T>(p, smem.data(), block, warp * 32 + lane, grid); });
+        for (int tid = 0; tid < wpc * 32; ++tid) spl::cta_load_tables<NFFT, KIND>(p, smem.data(), tid, wpc * 32);
+        for (int warp = 0; warp < wpc; ++warp)
+          run_warp([&](int lane) {
+            spl::transform_body<NFFT, KIND, GRAD, WIN_T>(p, smem.data(), block, warp * 32 + lane, grid, wpc);
+          });
       });
     for (auto& t : blocks) t.join();
   }

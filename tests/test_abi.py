@@ -64,7 +64,7 @@ def test_geometry(lib):
     assert lib.spl_geometry_of(ctypes.byref(_tr()), 16, 48000, ctypes.byref(g)) == 0
     assert (g.n_frames, g.n_bins, g.n_chunks, g.span, g.n_sums) == (401, 513, 101, 3 * 120 + 600, 3)
     assert g.partial_count == 16 * 101 * 3 and g.gchunk_bytes == 16 * 101 * 960 * 8
-    assert 0 < g.smem_bytes <= 227 * 1024
+    assert g.smem_table_bytes == (2 * 1024 + 600) * 4 and 0 < g.smem_warp_bytes <= 32 * 1024
 
 
 @pytest.mark.parametrize("kw,frag", [
