@@ -77,10 +77,16 @@ int spl_launch_finalize(const spl::FinalizeParams& fp, void* stream) {
   return SPL_OK;
 }
 
+int spl_launch_reduce_finalize(const spl::ReduceFinalizeParams& rf, void* stream) {
+  spl::reduce_finalize_kernel<<<rf.r.n_sums, 256, 0, static_cast<cudaStream_t>(stream)>>>(rf);
+  SPL_CUDA(cudaGetLastError());
+  return SPL_OK;
+}
+
 int spl_launch_combine(const spl::CombineParams& cp, void* stream) {
-  const long long total = (long long)cp.B * cp.T;
-  const unsigned grid = (unsigned)((total + 255) / 256);
-  spl::combine_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(cp);
+  const long long total = (long long)cp.B * ((cp.T + 3) / 4);
+  const unsigned grid = (unsigned)((total + 127) / 128);
+  spl::combine_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(cp);
   SPL_CUDA(cudaGetLastError());
   return SPL_OK;
 }

@@ -5,6 +5,7 @@
 //   template <int NFFT, int KIND, bool GRAD, int WIN_T> int spl_launch_transform(const spl::TransformParams&, int n_mels, void* stream);
 //   int spl_launch_reduce(const spl::ReduceParams&, void* stream);
 //   int spl_launch_finalize(const spl::FinalizeParams&, void* stream);
+//   int spl_launch_reduce_finalize(const spl::ReduceFinalizeParams&, void* stream);
 //   int spl_launch_combine(const spl::CombineParams&, void* stream);
 namespace {
 
@@ -140,48 +141,75 @@ int32_t spl_forward(const spl_transform* ts, int32_t n, const float* x, const fl
   return SPL_OK;
 }
 
-int32_t spl_reduce(const spl_transform* ts, int32_t n, int32_t B, int32_t T, double* sums, void* stream) {
-  if (n < 1 || n > SPL_MAX_TRANSFORMS || !sums) return fail(SPL_E_INVALID, "spl_reduce: bad n or null sums");
-  spl::ReduceParams rp;
-  std::memset(&rp, 0, sizeof(rp));
+static int build_reduce(const spl_transform* ts, int n, int B, int T, double* sums, spl::ReduceParams* rp) {
+  std::memset(rp, 0, sizeof(*rp));
   int k = 0;
   for (int r = 0; r < n; ++r) {
     int rc = check_transform(ts + r, B, T);
     if (rc) return rc;
+    if (!ts[r].partials) return fail(SPL_E_INVALID, "transform %d: null partials", r);
     spl_geometry g;
     geometry(ts + r, B, T, &g);
     for (int j = 0; j < g.n_sums; ++j) {
       if (k >= 16) return fail(SPL_E_INVALID, "too many sums");
-      rp.base[k] = ts[r].partials + j;
-      rp.stride[k] = g.n_sums;
-      rp.count[k] = (int)((int64_t)B * g.n_chunks);
+      rp->base[k] = ts[r].partials + j;
+      rp->stride[k] = g.n_sums;
+      rp->count[k] = (int)((int64_t)B * g.n_chunks);
       ++k;
     }
   }
-  rp.n_sums = k;
-  rp.out = sums;
+  rp->n_sums = k;
+  rp->out = sums;
+  return SPL_OK;
+}
+
+static int build_finalize(const spl_transform* ts, int n, const double* sums, int64_t B_global, int T,
+                          float* sc, float* mag, float* mel, float* coefs, spl::FinalizeParams* fp) {
+  if (B_global < 1) return fail(SPL_E_INVALID, "B_global %lld < 1", (long long)B_global);
+  std::memset(fp, 0, sizeof(*fp));
+  fp->n = n;
+  int ofs = 0;
+  for (int r = 0; r < n; ++r) {
+    int rc = check_transform(ts + r, 1, T);
+    if (rc) return rc;
+    const double frames = 1 + T / ts[r].hop;
+    fp->kind[r] = ts[r].kind;
+    fp->sum_ofs[r] = ofs;
+    if (ts[r].kind == SPL_KIND_STFT) { fp->count[r] = (double)B_global * frames * (ts[r].n_fft / 2 + 1); ofs += 3; }
+    else { fp->count[r] = (double)B_global * frames * ts[r].n_mels; ofs += 1; }
+  }
+  fp->sums = sums; fp->sc = sc; fp->mag = mag; fp->mel = mel; fp->coefs = coefs;
+  return SPL_OK;
+}
+
+int32_t spl_reduce(const spl_transform* ts, int32_t n, int32_t B, int32_t T, double* sums, void* stream) {
+  if (n < 1 || n > SPL_MAX_TRANSFORMS || !sums) return fail(SPL_E_INVALID, "spl_reduce: bad n or null sums");
+  spl::ReduceParams rp;
+  int rc = build_reduce(ts, n, B, T, sums, &rp);
+  if (rc) return rc;
   return spl_launch_reduce(rp, stream);
 }
 
 int32_t spl_finalize(const spl_transform* ts, int32_t n, const double* sums, int64_t B_global, int32_t T,
                      float* sc, float* mag, float* mel, float* coefs, void* stream) {
   if (n < 1 || n > SPL_MAX_TRANSFORMS || !sums || !coefs) return fail(SPL_E_INVALID, "spl_finalize: bad n or null sums/coefs");
-  if (B_global < 1) return fail(SPL_E_INVALID, "spl_finalize: B_global %lld < 1", (long long)B_global);
   spl::FinalizeParams fp;
-  std::memset(&fp, 0, sizeof(fp));
-  fp.n = n;
-  int ofs = 0;
-  for (int r = 0; r < n; ++r) {
-    int rc = check_transform(ts + r, 1, T);
-    if (rc) return rc;
-    const double frames = 1 + T / ts[r].hop;
-    fp.kind[r] = ts[r].kind;
-    fp.sum_ofs[r] = ofs;
-    if (ts[r].kind == SPL_KIND_STFT) { fp.count[r] = (double)B_global * frames * (ts[r].n_fft / 2 + 1); ofs += 3; }
-    else { fp.count[r] = (double)B_global * frames * ts[r].n_mels; ofs += 1; }
-  }
-  fp.sums = sums; fp.sc = sc; fp.mag = mag; fp.mel = mel; fp.coefs = coefs;
+  int rc = build_finalize(ts, n, sums, B_global, T, sc, mag, mel, coefs, &fp);
+  if (rc) return rc;
   return spl_launch_finalize(fp, stream);
+}
+
+int32_t spl_reduce_finalize(const spl_transform* ts, int32_t n, int32_t B, int32_t T, double* sums,
+                            float* sc, float* mag, float* mel, float* coefs, uint32_t* counter, void* stream) {
+  if (n < 1 || n > SPL_MAX_TRANSFORMS || !sums || !coefs || !counter)
+    return fail(SPL_E_INVALID, "spl_reduce_finalize: bad n or null sums/coefs/counter");
+  spl::ReduceFinalizeParams rf;
+  int rc = build_reduce(ts, n, B, T, sums, &rf.r);
+  if (rc) return rc;
+  rc = build_finalize(ts, n, sums, B, T, sc, mag, mel, coefs, &rf.f);
+  if (rc) return rc;
+  rf.counter = counter;
+  return spl_launch_reduce_finalize(rf, stream);
 }
 
 int32_t spl_backward(const spl_transform* ts, int32_t n, int32_t B, int32_t T, const float* coefs,

@@ -549,13 +549,13 @@ SPL_DEVICE void finalize_body(const FinalizeParams& p) {
   for (int r = 0; r < p.n; ++r) {
     const double* s = p.sums + p.sum_ofs[r];
     if (p.kind[r] == kKindStft) {
-      const double d = sqrt(s[0]), ny = sqrt(s[1]);
+      const double d = sqrt(__ldcg(&s[0])), ny = sqrt(__ldcg(&s[1]));
       sc += d / ny;
-      mag += s[2] / p.count[r];
+      mag += __ldcg(&s[2]) / p.count[r];
       p.coefs[2 * r] = (d > 0.0) ? (float)(1.0 / (n_stft * d * ny)) : 0.f;
       p.coefs[2 * r + 1] = (float)(1.0 / (n_stft * p.count[r]));
     } else {
-      mel += s[0] / p.count[r];
+      mel += __ldcg(&s[0]) / p.count[r];
       p.coefs[2 * r] = (float)(1.0 / (n_mel * p.count[r]));
       p.coefs[2 * r + 1] = 0.f;
     }
@@ -585,6 +585,7 @@ struct CombineParams {
   int B, T;
 };
 
+// overlap-added value at one padded position (used for the reflect-fold margins)
 SPL_DEVICE float gather_padded(const CombineEntry& e, int b, int ppos, float cu, float cv) {
   const int q_abs = ppos - e.left;
   if (q_abs < 0 || q_abs >= (e.n_frames - 1) * e.hop + e.win) return 0.f;
@@ -608,23 +609,93 @@ SPL_DEVICE float gather_padded(const CombineEntry& e, int b, int ppos, float cu,
   return acc;
 }
 
+// same for four consecutive padded positions ppos0 .. ppos0+3: one chunk walk, 16-byte loads when the
+// four samples sit inside one slot and the address is aligned (always the case for the shipped configs)
+SPL_DEVICE void gather_padded4(const CombineEntry& e, int b, int ppos0, float cu, float cv, float (&acc)[4]) {
+  const int q0 = ppos0 - e.left;
+  if (q0 + 3 < 0 || q0 >= (e.n_frames - 1) * e.hop + e.win) return;
+  const int mh = e.m * e.hop;
+  int c = min((q0 + 3) / mh, e.n_chunks - 1);
+  for (; c >= 0; --c) {
+    const int q = q0 - c * mh;
+    if (q >= e.span) break;
+    const int m_c = min(e.m, e.n_frames - c * e.m);
+    const int lim = (m_c - 1) * e.hop + e.win;
+    const size_t o = ((size_t)b * e.n_chunks + c) * e.span + q;     // meaningful for q >= 0 only
+    if (e.kind == kKindStft) {
+      const float2* src = reinterpret_cast<const float2*>(e.chunks);
+      if (q >= 0 && q + 3 < lim && (o & 1) == 0) {
+        const float4 v0 = __ldg(reinterpret_cast<const float4*>(src + o));
+        const float4 v1 = __ldg(reinterpret_cast<const float4*>(src + o + 2));
+        acc[0] = fmaf(cu, v0.x, fmaf(cv, v0.y, acc[0]));
+        acc[1] = fmaf(cu, v0.z, fmaf(cv, v0.w, acc[1]));
+        acc[2] = fmaf(cu, v1.x, fmaf(cv, v1.y, acc[2]));
+        acc[3] = fmaf(cu, v1.z, fmaf(cv, v1.w, acc[3]));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (q + j >= 0 && q + j < lim) {
+            const float2 v = __ldg(src + (o + j));
+            acc[j] = fmaf(cu, v.x, fmaf(cv, v.y, acc[j]));
+          }
+      }
+    } else {
+      const float* src = reinterpret_cast<const float*>(e.chunks);
+      if (q >= 0 && q + 3 < lim && (o & 3) == 0) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(src + o));
+        acc[0] = fmaf(cu, v.x, acc[0]); acc[1] = fmaf(cu, v.y, acc[1]);
+        acc[2] = fmaf(cu, v.z, acc[2]); acc[3] = fmaf(cu, v.w, acc[3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (q + j >= 0 && q + j < lim) acc[j] = fmaf(cu, __ldg(src + (o + j)), acc[j]);
+      }
+    }
+  }
+}
+
+// one thread = four consecutive output samples of one utterance
 SPL_DEVICE void combine_body(const CombineParams& p, long long gid) {
-  if (gid >= (long long)p.B * p.T) return;
-  const int b = (int)(gid / p.T), i = (int)(gid - (long long)b * p.T);
+  const int quads = (p.T + 3) >> 2;
+  if (gid >= (long long)p.B * quads) return;
+  const int b = (int)(gid / quads), i0 = 4 * (int)(gid - (long long)b * quads);
   const float gsc = p.g_sc ? *p.g_sc : 0.f, gmag = p.g_mag ? *p.g_mag : 0.f, gmel = p.g_mel ? *p.g_mel : 0.f;
-  float acc = 0.f;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
   for (int r = 0; r < p.n; ++r) {
     const CombineEntry& e = p.e[r];
     float cu, cv;
     if (e.kind == kKindStft) { cu = gsc * p.coefs[2 * r]; cv = gmag * p.coefs[2 * r + 1]; }
     else { cu = gmel * p.coefs[2 * r]; cv = 0.f; }
     const int P = e.half;
-    acc += gather_padded(e, b, P + i, cu, cv);
-    if (i >= 1 && i <= P) acc += gather_padded(e, b, P - i, cu, cv);
-    if (i >= p.T - 1 - P && i <= p.T - 2) acc += gather_padded(e, b, P + 2 * (p.T - 1) - i, cu, cv);
+    gather_padded4(e, b, P + i0, cu, cv, acc);
+    if (i0 <= P || i0 + 3 >= p.T - 1 - P) {          // reflect-fold margins
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int i = i0 + j;
+        if (i >= 1 && i <= P) acc[j] += gather_padded(e, b, P - i, cu, cv);
+        if (i >= p.T - 1 - P && i <= p.T - 2) acc[j] += gather_padded(e, b, P + 2 * (p.T - 1) - i, cu, cv);
+      }
+    }
   }
-  p.dx[gid] = acc;
+  float* out = p.dx + (size_t)b * p.T + i0;
+  if ((p.T & 3) == 0) {
+    *reinterpret_cast<float4*>(out) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (i0 + j < p.T) out[j] = acc[j];
+  }
 }
+
+// ---------------------------------------------------------------------------------------------
+// reduce + finalize in one launch (single-GPU path): the last CTA to finish its column computes
+// the losses.  `counter` must be zero before the first use; atomicInc wraps it back to zero.
+// ---------------------------------------------------------------------------------------------
+struct ReduceFinalizeParams {
+  ReduceParams r;
+  FinalizeParams f;
+  unsigned* counter;
+};
 
 #ifndef SPECLOSS_EMU
 // One persistent CTA per SM: up to 12 warps (168 registers) for the 64-point-per-lane kernels, 16 (128
@@ -645,8 +716,22 @@ __global__ void __launch_bounds__(256) reduce_kernel(const ReduceParams p) {
 __global__ void finalize_kernel(const FinalizeParams p) {
   if (threadIdx.x == 0 && blockIdx.x == 0) finalize_body(p);
 }
-__global__ void __launch_bounds__(256) combine_kernel(const CombineParams p) {
-  combine_body(p, (long long)blockIdx.x * 256 + threadIdx.x);
+__global__ void __launch_bounds__(256) reduce_finalize_kernel(const ReduceFinalizeParams p) {
+  __shared__ double sh[256];
+  __shared__ bool last;
+  reduce_body(p.r, sh, blockIdx.x, threadIdx.x, 256);
+  if (threadIdx.x == 0) {
+    __threadfence();
+    last = atomicInc(p.counter, gridDim.x - 1) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    __threadfence();
+    finalize_body(p.f);
+  }
+}
+__global__ void __launch_bounds__(128) combine_kernel(const CombineParams p) {
+  combine_body(p, (long long)blockIdx.x * 128 + threadIdx.x);
 }
 #endif
 

@@ -184,27 +184,42 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
 
 
 class ForwardState:
-    """What backward needs: the ctypes transform array (pointers into the tensors kept alive here)."""
+    """What backward needs: the ctypes transform array (pointers into the workspace kept alive here)."""
+    __slots__ = ("transforms", "n", "keep", "coefs", "batch", "t_len", "has_grad", "sc", "mag", "mel", "sums",
+                 "n_launches")
 
     def __init__(self):
         self.transforms = None
         self.n = 0
-        self.keep: List[torch.Tensor] = []
-        self.coefs: Optional[torch.Tensor] = None
-        self.batch = 0
-        self.t_len = 0
+        self.keep = None
+        self.coefs = self.sums = None
+        self.batch = self.t_len = 0
         self.has_grad = False
         self.sc = self.mag = self.mel = None
-        self.sums: Optional[torch.Tensor] = None
-        self.geometries: List[SplGeometry] = []
+        self.n_launches = 0
+
+
+def _align(n: int, a: int = 256) -> int:
+    return (n + a - 1) // a * a
+
+
+class _Recipe:
+    """Everything about a (plan list, batch shape, grad mode) that does not change from call to call:
+    the filled ctypes transform array and the carve-up of the single per-call workspace buffer."""
+    __slots__ = ("template", "nbytes", "n", "off_partials", "off_gchunks", "off_sums", "off_coefs", "ws_bytes",
+                 "n_sums", "has_stft", "has_mel", "keep")
 
 
 class Engine:
     def __init__(self, lib: ctypes.CDLL):
         self.lib = lib
+        self._recipes = {}
+        self._counters = {}
+        self.launches = 0          # kernels launched so far (bench.py reports the per-step count)
 
     # -- helpers ---------------------------------------------------------------------------------
-    def _stream(self, ref: torch.Tensor):
+    @staticmethod
+    def _stream(ref: torch.Tensor):
         return ctypes.c_void_p(torch.cuda.current_stream(ref.device).cuda_stream) if ref.is_cuda else None
 
     def geometry(self, tr: SplTransform, batch: int, t_len: int) -> SplGeometry:
@@ -212,30 +227,38 @@ class Engine:
         _abi.check(self.lib, self.lib.spl_geometry_of(ctypes.byref(tr), batch, t_len, ctypes.byref(g)))
         return g
 
-    # -- forward ---------------------------------------------------------------------------------
-    def forward(self, plans: Sequence[TransformPlan], x: torch.Tensor, y: torch.Tensor, need_grad: bool,
-                group=None, global_batch: Optional[int] = None) -> ForwardState:
-        """x, y: (B, T) fp32 contiguous on one device.  Launches on the current stream."""
+    def _counter(self, dev) -> torch.Tensor:
+        c = self._counters.get(dev)
+        if c is None:
+            c = self._counters[dev] = torch.zeros(1, dtype=torch.int32, device=dev)
+        return c
+
+    def _recipe(self, plans: Sequence[TransformPlan], batch: int, t_len: int, need_grad: bool, dev) -> _Recipe:
+        key = (tuple((p.kind, p.n_fft, p.hop, p.win, p.eps, p.n_mels, p.inv_ln_base, p.window.data_ptr(),
+                      p.twiddle.data_ptr()) + tuple(t.data_ptr() for t in p.tables.values()) for p in plans),
+               batch, t_len, need_grad, str(dev), os.environ.get("SPECLOSS_FRAMES_PER_CHUNK"))
+        rec = self._recipes.get(key)
+        if rec is not None:
+            return rec
         if len(plans) < 1 or len(plans) > _abi.SPL_MAX_TRANSFORMS:
             raise RuntimeError(f"{len(plans)} resolutions: supported range is 1..{_abi.SPL_MAX_TRANSFORMS}")
-        batch, t_len = x.shape
-        dev = x.device
-        st = ForwardState()
-        st.batch, st.t_len, st.has_grad, st.n = batch, t_len, need_grad, len(plans)
-        arr = (SplTransform * len(plans))()
-        n_sums_total = 0
+        n = len(plans)
+        arr = (SplTransform * n)()
+        rec = _Recipe()
+        rec.n, rec.off_partials, rec.off_gchunks, rec.keep = n, [], [], []
+        off = 0
+        n_sums = 0
         for i, pl in enumerate(plans):
             pl.validate()
             if pl.window.device != dev or pl.twiddle.device != dev:
                 raise RuntimeError(f"loss module buffers are on {pl.window.device}, inputs on {dev}: call .to(device)")
-            tr = arr[i]
-            tr.kind, tr.n_fft, tr.hop, tr.win = pl.kind, pl.n_fft, pl.hop, pl.win
-            tr.eps = pl.eps
             if t_len <= pl.n_fft // 2:
                 raise RuntimeError(f"reflect padding needs T > fft_size/2 (T={t_len}, fft_size={pl.n_fft}); "
                                    "torch.stft raises for the same input")
-            n_frames = 1 + t_len // pl.hop
-            tr.frames_per_chunk = choose_frames_per_chunk(batch, n_frames, pl.n_fft)
+            tr = arr[i]
+            tr.kind, tr.n_fft, tr.hop, tr.win = pl.kind, pl.n_fft, pl.hop, pl.win
+            tr.eps = pl.eps
+            tr.frames_per_chunk = choose_frames_per_chunk(batch, 1 + t_len // pl.hop, pl.n_fft)
             tr.window, tr.twiddle = _ptr(pl.window), _ptr(pl.twiddle)
             tr.n_mels, tr.inv_ln_base = pl.n_mels, pl.inv_ln_base
             if pl.kind == SPL_KIND_MEL:
@@ -247,41 +270,70 @@ class Engine:
                 tr.mel_rounds = pl.tables["mel_tasks"].numel() // (4 * lanes)
                 tr.mel_entry_rows = pl.tables["mel_entries"].numel() // (2 * lanes)
             g = self.geometry(tr, batch, t_len)
-            st.geometries.append(g)
-            partials = torch.empty(g.partial_count, dtype=torch.float64, device=dev)
-            st.keep.append(partials)
-            tr.partials = _ptr(partials)
+            rec.off_partials.append(off)
+            off = _align(off + 8 * g.partial_count)
             if need_grad:
-                gch = torch.empty(g.gchunk_bytes // 4, dtype=torch.float32, device=dev)
-                st.keep.append(gch)
-                tr.gchunks = _ptr(gch)
-            else:
-                tr.gchunks = None
-            n_sums_total += g.n_sums
-            st.keep.extend([pl.window, pl.twiddle] + list(pl.tables.values()))
-        st.transforms = arr
+                rec.off_gchunks.append(off)
+                off = _align(off + g.gchunk_bytes)
+            n_sums += g.n_sums
+            rec.keep.extend([pl.window, pl.twiddle] + list(pl.tables.values()))
+        rec.off_sums = off
+        off = _align(off + 8 * n_sums)
+        rec.off_coefs = off
+        off = _align(off + 4 * 2 * n)
+        rec.ws_bytes, rec.n_sums = off, n_sums
+        rec.has_stft = any(p.kind == SPL_KIND_STFT for p in plans)
+        rec.has_mel = any(p.kind == SPL_KIND_MEL for p in plans)
+        rec.template, rec.nbytes = arr, ctypes.sizeof(arr)
+        if len(self._recipes) > 64:
+            self._recipes.clear()
+        self._recipes[key] = rec
+        return rec
+
+    # -- forward ---------------------------------------------------------------------------------
+    def forward(self, plans: Sequence[TransformPlan], x: torch.Tensor, y: torch.Tensor, need_grad: bool,
+                group=None, global_batch: Optional[int] = None) -> ForwardState:
+        """x, y: (B, T) fp32 contiguous on one device.  Launches on the current stream; one workspace
+        allocation per call, no host synchronisation."""
+        batch, t_len = x.shape
+        dev = x.device
+        rec = self._recipe(plans, batch, t_len, need_grad, dev)
+        n = rec.n
+        ws = torch.empty(rec.ws_bytes, dtype=torch.uint8, device=dev)
+        base = ws.data_ptr()
+        arr = (SplTransform * n)()
+        ctypes.memmove(arr, rec.template, rec.nbytes)
+        for i in range(n):
+            arr[i].partials = base + rec.off_partials[i]
+            arr[i].gchunks = base + rec.off_gchunks[i] if need_grad else None
+        st = ForwardState()
+        st.batch, st.t_len, st.has_grad, st.n, st.transforms = batch, t_len, need_grad, n, arr
+        st.keep = (ws, rec.keep)
+        # separate 0-dim outputs: callers scale them in place (trainer/trainerGAN.py:221,228-229)
+        st.sc = torch.empty((), dtype=torch.float32, device=dev) if rec.has_stft else None
+        st.mag = torch.empty((), dtype=torch.float32, device=dev) if rec.has_stft else None
+        st.mel = torch.empty((), dtype=torch.float32, device=dev) if rec.has_mel else None
+        st.sums = ws[rec.off_sums:rec.off_sums + 8 * rec.n_sums].view(torch.float64)
+        st.coefs = ws[rec.off_coefs:rec.off_coefs + 8 * n].view(torch.float32)
         stream = self._stream(x)
         lib = self.lib
-        _abi.check(lib, lib.spl_forward(arr, len(plans), x.data_ptr(), y.data_ptr(), batch, t_len, stream))
-        sums = torch.empty(n_sums_total, dtype=torch.float64, device=dev)
-        _abi.check(lib, lib.spl_reduce(arr, len(plans), batch, t_len, sums.data_ptr(), stream))
-        if group is not None:
-            import torch.distributed as dist
-            dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)     # the single exchange step
-            if global_batch is None:
-                global_batch = batch * dist.get_world_size(group)
-        if global_batch is None:
-            global_batch = batch
-        has_stft = any(p.kind == SPL_KIND_STFT for p in plans)
-        has_mel = any(p.kind == SPL_KIND_MEL for p in plans)
-        # separate 0-dim outputs: callers scale them in place (trainer/trainerGAN.py:221,228-229)
-        st.sc = torch.empty((), dtype=torch.float32, device=dev) if has_stft else None
-        st.mag = torch.empty((), dtype=torch.float32, device=dev) if has_stft else None
-        st.mel = torch.empty((), dtype=torch.float32, device=dev) if has_mel else None
-        st.coefs = torch.empty(2 * len(plans), dtype=torch.float32, device=dev)
-        _abi.check(lib, lib.spl_finalize(arr, len(plans), sums.data_ptr(), int(global_batch), t_len,
-                                         _ptr(st.sc), _ptr(st.mag), _ptr(st.mel), st.coefs.data_ptr(), stream))
-        st.sums = sums
+        _abi.check(lib, lib.spl_forward(arr, n, x.data_ptr(), y.data_ptr(), batch, t_len, stream))
+        sums_ptr, coefs_ptr = base + rec.off_sums, base + rec.off_coefs
+        if group is None and (global_batch is None or global_batch == batch):
+            _abi.check(lib, lib.spl_reduce_finalize(arr, n, batch, t_len, sums_ptr, _ptr(st.sc), _ptr(st.mag),
+                                                    _ptr(st.mel), coefs_ptr, self._counter(dev).data_ptr(), stream))
+            st.n_launches = n + 1
+        else:
+            _abi.check(lib, lib.spl_reduce(arr, n, batch, t_len, sums_ptr, stream))
+            if group is not None:
+                import torch.distributed as dist
+                dist.all_reduce(st.sums, op=dist.ReduceOp.SUM, group=group)   # the single exchange step (SURVEY 8e)
+                if global_batch is None:
+                    global_batch = batch * dist.get_world_size(group)
+            _abi.check(lib, lib.spl_finalize(arr, n, sums_ptr, int(global_batch), t_len, _ptr(st.sc), _ptr(st.mag),
+                                             _ptr(st.mel), coefs_ptr, stream))
+            st.n_launches = n + 2
+        self.launches += st.n_launches
         return st
 
     # -- backward --------------------------------------------------------------------------------
@@ -295,13 +347,15 @@ class Engine:
         def scalar(g):
             if g is None:
                 return None
-            g = g.detach().to(device=dev, dtype=torch.float32).reshape(())
-            return g.contiguous()
+            if g.dtype != torch.float32 or g.device != dev or g.dim() != 0:
+                g = g.detach().to(device=dev, dtype=torch.float32).reshape(())
+            return g
 
-        gs = [scalar(g_sc), scalar(g_mag), scalar(g_mel)]
+        gs = (scalar(g_sc), scalar(g_mag), scalar(g_mel))
         _abi.check(self.lib, self.lib.spl_backward(st.transforms, st.n, st.batch, st.t_len, st.coefs.data_ptr(),
                                                    _ptr(gs[0]), _ptr(gs[1]), _ptr(gs[2]), dx.data_ptr(),
                                                    self._stream(dx)))
+        self.launches += 1
         return dx
 
 

@@ -24,6 +24,16 @@ from .engine import TransformPlan, fft_geometry, mel_tables, twiddle_table
 from .functional import spectral_losses
 
 
+def _cached_plans(owner, children) -> List[TransformPlan]:
+    """Plans are rebuilt only when a buffer moved (module.to(device), load_state_dict)."""
+    sig = tuple(c.window.data_ptr() for c in children) + tuple(c._twiddle.data_ptr() for c in children)
+    cache = owner.__dict__.get("_plan_cache")
+    if cache is None or cache[0] != sig:
+        cache = (sig, [c.plan() for c in children])
+        owner.__dict__["_plan_cache"] = cache
+    return cache[1]
+
+
 def _window(name: str, win_length: int) -> torch.Tensor:
     return getattr(torch, name)(win_length)          # as stft_loss.py:97 / mel_loss.py:49
 
@@ -87,7 +97,7 @@ class MultiResolutionSTFTLoss(torch.nn.Module):
         self.process_group = None      # set to a torch.distributed group to shard the batch over ranks
 
     def plans(self) -> List[TransformPlan]:
-        return [f.plan() for f in self.stft_losses]
+        return _cached_plans(self, self.stft_losses)
 
     def forward(self, x, y):
         return spectral_losses(x, y, self.plans(), group=self.process_group)
@@ -162,7 +172,7 @@ class MultiMelSpectrogramLoss(torch.nn.Module):
         self.process_group = None
 
     def plans(self) -> List[TransformPlan]:
-        return [f.plan() for f in self.mel_transfers]
+        return _cached_plans(self, self.mel_transfers)
 
     def forward(self, y_hat, y):
         (mel,) = spectral_losses(y_hat, y, self.plans(), group=self.process_group)

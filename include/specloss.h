@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SPL_ABI_VERSION 4
+#define SPL_ABI_VERSION 5
 
 #define SPL_OK 0
 #define SPL_E_INVALID (-1)   /* bad argument / outside the supported envelope */
@@ -95,6 +95,12 @@ int32_t spl_reduce(const spl_transform* ts, int32_t n, int32_t B, int32_t T, dou
  * coefs[2*n] receives the backward coefficients consumed by spl_backward(). */
 int32_t spl_finalize(const spl_transform* ts, int32_t n, const double* sums, int64_t B_global, int32_t T,
                      float* sc, float* mag, float* mel, float* coefs, void* stream);
+
+/* spl_reduce + spl_finalize in ONE launch for the unsharded case (B_global == B): the last CTA to finish
+ * its column computes the losses.  `counter` is a device uint32 that must be zero before the first call
+ * and is left at zero by every call (it may be shared by successive calls on one stream). */
+int32_t spl_reduce_finalize(const spl_transform* ts, int32_t n, int32_t B, int32_t T, double* sums,
+                            float* sc, float* mag, float* mel, float* coefs, uint32_t* counter, void* stream);
 
 /* Backward: dx (B, T) = g_sc * dsc/dx + g_mag * dmag/dx + g_mel * dmel/dx -- what autograd derives for
  * the reference modules.  g_* are device scalars (NULL = 0). */

@@ -17,6 +17,8 @@
 struct float2 { float x, y; };
 struct int4 { int x, y, z, w; };
 struct int2 { int x, y; };
+struct alignas(16) float4 { float x, y, z, w; };
+static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
 static inline float __fmul_rn(float a, float b) { return a * b; }
 static inline float __fsub_rn(float a, float b) { return a - b; }
 static inline float2 make_float2(float x, float y) { return float2{x, y}; }
@@ -47,5 +49,6 @@ static inline unsigned __ballot_sync(unsigned, bool pred) {
   return r;
 }
 template <typename T> static inline T __ldg(const T* p) { return *p; }
+template <typename T> static inline T __ldcg(const T* p) { return *p; }
 static inline float rsqrtf(float x) { return 1.0f / std::sqrt(x); }
 using std::min;

@@ -83,8 +83,14 @@ int spl_launch_finalize(const spl::FinalizeParams& fp, void*) {
   return SPL_OK;
 }
 
+int spl_launch_reduce_finalize(const spl::ReduceFinalizeParams& rf, void*) {
+  spl_launch_reduce(rf.r, nullptr);
+  spl::finalize_body(rf.f);
+  return SPL_OK;
+}
+
 int spl_launch_combine(const spl::CombineParams& cp, void*) {
-  const long long total = (long long)cp.B * cp.T;
+  const long long total = (long long)cp.B * ((cp.T + 3) / 4);
   for (long long g = 0; g < total; ++g) spl::combine_body(cp, g);
   return SPL_OK;
 }
