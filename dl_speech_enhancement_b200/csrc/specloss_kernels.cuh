@@ -141,7 +141,9 @@ SPL_DEVICE void fft_core(float (&re)[FftGeom<NFFT>::R], float (&im)[FftGeom<NFFT
                          float2* buf, const float2* tw, int l) {
   using G = FftGeom<NFFT>;
   constexpr int L = G::L, R = G::R, RPL = R / L;
+  // [region: fft_core pass A (in-lane R-point DFT)]
   Dft<R>::run(re, im);
+  // [region: fft_core twiddle + transposed store]
 #pragma unroll
   for (int k2 = 0; k2 < R; ++k2) {
     float2 v = make_float2(re[k2], im[k2]);
@@ -149,6 +151,7 @@ SPL_DEVICE void fft_core(float (&re)[FftGeom<NFFT>::R], float (&im)[FftGeom<NFFT
     buf[k2 * (L + 1) + l] = v;
   }
   __syncwarp();
+  // [region: fft_core pass B (row load, L-point DFT, row store)]
 #pragma unroll 1
   for (int j = 0; j < RPL; ++j) {
     float2* row = buf + (j * L + l) * (L + 1);
@@ -166,6 +169,7 @@ SPL_DEVICE void fft_core(float (&re)[FftGeom<NFFT>::R], float (&im)[FftGeom<NFFT
   __syncwarp();
 }
 
+// [region: misc helpers]
 // reflect index without edge repeat (torch.stft center=True, pad_mode="reflect")
 SPL_DEVICE int reflect(int s, int T) {
   s = s < 0 ? -s : s;
@@ -231,6 +235,7 @@ SPL_DEVICE void transform_body(const TransformParams& p, float* smem, int block,
   const bool no_ring = (FPW == 1) && (p.m == 1);    // one frame per chunk: windowed frame goes straight to its slot
   const int total_chunks = p.B * p.n_chunks;
 
+  // [region: chunk loop setup]
   for (int chunk_id = block * wpc + warp; chunk_id < total_chunks; chunk_id += grid * wpc) {
     const int b = chunk_id / p.n_chunks, c = chunk_id - b * p.n_chunks;
     const int t0 = c * p.m;
@@ -258,6 +263,7 @@ SPL_DEVICE void transform_body(const TransformParams& p, float* smem, int block,
       for (int job = 0; job < (GRAD ? 2 : 1); ++job) {
         float re[R], im[R];
         if (job == 0) {
+          // [region: A load taps + window + equality vote]
           // ---- A. taps of frame t: reflect-pad, window, pack z = x*w + i*y*w ---------------------
           const int s0 = t * p.hop - HALF;                         // sample index of tap n = 0
           const bool interior = (s0 + left >= 0) && (s0 + left + win <= p.T);
@@ -287,6 +293,7 @@ SPL_DEVICE void transform_body(const TransformParams& p, float* smem, int block,
           const unsigned grp_mask = (L == 32) ? 0xffffffffu : (((1u << (L & 31)) - 1u) << (h * L));
           frame_equal = (eq_bits & grp_mask) == grp_mask;
         } else {
+          // [region: D job-1 load of H]
           // ---- D. gradient spectrum H (slot layout) -> inverse DFT via swapped components ------
 #pragma unroll
           for (int n2 = 0; n2 < R; ++n2) {
@@ -298,6 +305,7 @@ SPL_DEVICE void transform_body(const TransformParams& p, float* smem, int block,
         }
         fft_core<NFFT>(re, im, buf, tw, l);
         if (job == 1) {
+          // [region: E window + overlap-add]
           // ---- E. window, overlap-add into the ring (slot holds (imag, real) = (v, u) swapped) --
           const int n2_lo = left / L, n2_hi = (left + win - 1) / L;      // register slots with live taps
           if (no_ring) {
@@ -343,6 +351,7 @@ SPL_DEVICE void transform_body(const TransformParams& p, float* smem, int block,
           }
           continue;
         }
+        // [region: C epilogue]
         // ---- C. job 0 epilogue ------------------------------------------------------------------
         // Bin k = row + R*col sits at buf[row*(L+1) + col].  A lane owns rows l + L*j; for col < L/2 the
         // bin is k < N/2 and its mirror N-k is (R - row, L-1-col) -- or (0, L-col) inside row 0.  Bins 0
@@ -475,6 +484,7 @@ SPL_DEVICE void transform_body(const TransformParams& p, float* smem, int block,
         __syncwarp();
       }  // job
       if (GRAD && !no_ring) {
+        // [region: F ring flush]
         // ---- F. flush the ring entries no later frame of this chunk touches ----------------------
         const int done = min(m_c, (step + 1) * FPW);
         const int limit = (done == m_c) ? span_c : done * p.hop;
@@ -488,6 +498,7 @@ SPL_DEVICE void transform_body(const TransformParams& p, float* smem, int block,
       }
     }  // step
 
+    // [region: partial sums]
     // ---- partial sums of this chunk (one writer per slot: deterministic) ------------------------
     s1 = warp_sum(s1);
     if (KIND == kKindStft) { s2 = warp_sum(s2); s3 = warp_sum(s3); }

@@ -166,14 +166,18 @@ def choose_frames_per_chunk(batch: int, n_frames: int, n_fft: int) -> int:
         else:
             m = max(1, int(env))
     if m is None:
+        warps = _SM_COUNT * (12 if n_fft == 2048 else 16)
+        per_warp = batch * n_frames / float(warps)
         if n_fft == 2048:
             # one frame per chunk: no overlap-add ring in shared memory, 12 instead of 8 warps per SM
             # (measured on B200, config 2: mel 154 -> 84 us, stft-2048 93 -> 60 us)
             m = 1
+        elif per_warp < 8.0:
+            # small problem: the finest granularity keeps the warps evenly loaded (config 2 has 2.7 frames
+            # of the 1024-point transform per resident warp; m = 2 would round that up to 4)
+            m = 1 if n_fft == 1024 else 2
         else:
-            resident = _SM_COUNT * 16
-            m = int(round(batch * n_frames / (4.0 * resident)))
-            m = max(2, min(16, m))
+            m = max(2, min(16, int(round(per_warp / 4.0))))
     if n_fft == 512 and (m & 1):        # two frames in flight per warp
         m += 1
     return m
