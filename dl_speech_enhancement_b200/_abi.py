@@ -21,9 +21,10 @@ SPL_KIND_STFT = 0
 SPL_KIND_MEL = 1
 SPL_MAX_TRANSFORMS = 8
 
-# -ftz=true: denormals flush to zero.  Magnitudes are clamped at >= 1e-10 before any rsqrt/log, so
-# the only effect is on FFT intermediates below 1e-38, which contribute nothing at fp32 precision.
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-ftz=true",
+# No -ftz: the packed fp32 instructions of sm_100 (FADD2/FMUL2/FFMA2) have no flush-to-zero form, and with
+# -ftz=true ptxas emulates it with extra scalar FADDs and MOVs (fft32: 216 -> 471 instructions).  The two
+# hot transcendental calls use explicit .ftz PTX instead (specloss_kernels.cuh: spl_fast_rsqrt / spl_fast_log2).
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
 

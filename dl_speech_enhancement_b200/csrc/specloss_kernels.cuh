@@ -21,10 +21,21 @@
 #define SPL_DEVICE __device__ __forceinline__
 #include "fft_codelets.cuh"
 
+// MUFU.RSQ / MUFU.LG2 without the denormal fix-up code: their arguments are clamped at >= 1e-10 first.
 #ifdef SPECLOSS_EMU
-#define SPL_FAST_LOG2F(x) log2f(x)
+static inline float spl_fast_rsqrt(float x) { return 1.0f / std::sqrt(x); }
+static inline float spl_fast_log2(float x) { return std::log2(x); }
 #else
-#define SPL_FAST_LOG2F(x) __log2f(x)   // MUFU.LG2; abs error ~1e-7 on the log-magnitude terms
+__device__ __forceinline__ float spl_fast_rsqrt(float x) {
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float spl_fast_log2(float x) {
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 #endif
 
 namespace spl {
@@ -44,9 +55,9 @@ template <> struct FftGeom<1024> { static constexpr int L = 32, R = 32; };
 template <> struct FftGeom<2048> { static constexpr int L = 32, R = 64; };
 
 template <int P> struct Dft;
-template <> struct Dft<16> { static SPL_DEVICE void run(float (&re)[16], float (&im)[16]) { fft16(re, im); } };
-template <> struct Dft<32> { static SPL_DEVICE void run(float (&re)[32], float (&im)[32]) { fft32(re, im); } };
-template <> struct Dft<64> { static SPL_DEVICE void run(float (&re)[64], float (&im)[64]) { fft64(re, im); } };
+template <> struct Dft<16> { static SPL_DEVICE void run(float2 (&v)[16]) { fft16(v); } };
+template <> struct Dft<32> { static SPL_DEVICE void run(float2 (&v)[32]) { fft32(v); } };
+template <> struct Dft<64> { static SPL_DEVICE void run(float2 (&v)[64]) { fft64(v); } };
 
 // One transform (= one STFT resolution or one mel resolution) over a batch of utterances.
 struct TransformParams {
@@ -74,11 +85,10 @@ struct TransformParams {
   const void* bin_tab;        // int4[K]: {m0, bits(W[k,m0]), bits(W[k,m0+1]), 0}: bin k feeds rows m0, m0+1 only
 };
 
-SPL_DEVICE float2 cmul(float2 a, float2 w) {            // a * w
-  return make_float2(fmaf(a.x, w.x, -a.y * w.y), fmaf(a.x, w.y, a.y * w.x));
-}
-SPL_DEVICE float2 cmul_conj(float2 a, float2 w) {       // a * conj(w)
-  return make_float2(fmaf(a.x, w.x, a.y * w.y), fmaf(a.y, w.x, -a.x * w.y));
+// a * w on the packed fp32 pipe: w.x * (a.x, a.y) + w.y * (-a.y, a.x)  (FMUL2 + FFMA2; the broadcasts
+// and the swap/negate of `a` are operand modifiers)
+SPL_DEVICE float2 cmul(float2 a, float2 w) {
+  return __ffma2_rn(make_float2(-a.y, a.x), make_float2(w.y, w.y), __fmul2_rn(a, make_float2(w.x, w.x)));
 }
 
 SPL_DEVICE float warp_sum(float v) {
@@ -137,34 +147,25 @@ SPL_DEVICE int pos(int k) {
 // read back (.y, .x).
 // ---------------------------------------------------------------------------------------------
 template <int NFFT>
-SPL_DEVICE void fft_core(float (&re)[FftGeom<NFFT>::R], float (&im)[FftGeom<NFFT>::R],
-                         float2* buf, const float2* tw, int l) {
+SPL_DEVICE void fft_core(float2 (&v)[FftGeom<NFFT>::R], float2* buf, const float2* tw, int l) {
   using G = FftGeom<NFFT>;
   constexpr int L = G::L, R = G::R, RPL = R / L;
   // [region: fft_core pass A (in-lane R-point DFT)]
-  Dft<R>::run(re, im);
+  Dft<R>::run(v);
   // [region: fft_core twiddle + transposed store]
 #pragma unroll
-  for (int k2 = 0; k2 < R; ++k2) {
-    float2 v = make_float2(re[k2], im[k2]);
-    if (k2 > 0) v = cmul(v, tw[k2 * L + l]);
-    buf[k2 * (L + 1) + l] = v;
-  }
+  for (int k2 = 0; k2 < R; ++k2) buf[k2 * (L + 1) + l] = k2 > 0 ? cmul(v[k2], tw[k2 * L + l]) : v[0];
   __syncwarp();
   // [region: fft_core pass B (row load, L-point DFT, row store)]
 #pragma unroll 1
   for (int j = 0; j < RPL; ++j) {
     float2* row = buf + (j * L + l) * (L + 1);
-    float br[L], bi[L];
+    float2 b[L];
 #pragma unroll
-    for (int n1 = 0; n1 < L; ++n1) {
-      const float2 v = row[n1];
-      br[n1] = v.x;
-      bi[n1] = v.y;
-    }
-    Dft<L>::run(br, bi);
+    for (int n1 = 0; n1 < L; ++n1) b[n1] = row[n1];
+    Dft<L>::run(b);
 #pragma unroll
-    for (int k1 = 0; k1 < L; ++k1) row[k1] = make_float2(br[k1], bi[k1]);
+    for (int k1 = 0; k1 < L; ++k1) row[k1] = b[k1];
   }
   __syncwarp();
 }
@@ -261,7 +262,7 @@ SPL_DEVICE void transform_body(const TransformParams& p, float* smem, int block,
       bool frame_equal = false;
 #pragma unroll 1
       for (int job = 0; job < (GRAD ? 2 : 1); ++job) {
-        float re[R], im[R];
+        float2 v[R];
         if (job == 0) {
           // [region: A load taps + window + equality vote]
           // ---- A. taps of frame t: reflect-pad, window, pack z = x*w + i*y*w ---------------------
@@ -271,7 +272,7 @@ SPL_DEVICE void transform_body(const TransformParams& p, float* smem, int block,
 #pragma unroll
           for (int n2 = 0; n2 < R; ++n2) {
             const int lo = L * n2 - left;                          // tap index of lane 0
-            if (WIN_T > 0 && (lo + L - 1 < 0 || lo >= WIN_T)) { re[n2] = 0.f; im[n2] = 0.f; continue; }
+            if (WIN_T > 0 && (lo + L - 1 < 0 || lo >= WIN_T)) { v[n2] = make_float2(0.f, 0.f); continue; }
             const int tap = lo + l;
             const bool all_lanes = WIN_T > 0 && lo >= 0 && lo + L - 1 < WIN_T;
             float xv = 0.f, yv = 0.f;
@@ -283,8 +284,7 @@ SPL_DEVICE void transform_body(const TransformParams& p, float* smem, int block,
               yv = __ldg(&yb[s]) * w;
             }
             same = same && (xv == yv);
-            re[n2] = xv;
-            im[n2] = yv;
+            v[n2] = make_float2(xv, yv);
           }
           // A frame whose prediction and target taps are bit-identical must contribute exactly zero
           // (the reference returns sc = mag = mel = 0 and a zero gradient for x == y); the packed FFT
@@ -297,13 +297,12 @@ SPL_DEVICE void transform_body(const TransformParams& p, float* smem, int block,
           // ---- D. gradient spectrum H (slot layout) -> inverse DFT via swapped components ------
 #pragma unroll
           for (int n2 = 0; n2 < R; ++n2) {
-            const float2 v = buf[(l + L * (n2 % (R / L))) * (L + 1) + n2 / (R / L)];   // element n = l + L*n2
-            re[n2] = v.y;
-            im[n2] = v.x;
+            const float2 hk = buf[(l + L * (n2 % (R / L))) * (L + 1) + n2 / (R / L)];   // element n = l + L*n2
+            v[n2] = make_float2(hk.y, hk.x);
           }
           __syncwarp();
         }
-        fft_core<NFFT>(re, im, buf, tw, l);
+        fft_core<NFFT>(v, buf, tw, l);
         if (job == 1) {
           // [region: E window + overlap-add]
           // ---- E. window, overlap-add into the ring (slot holds (imag, real) = (v, u) swapped) --
@@ -315,9 +314,9 @@ SPL_DEVICE void transform_body(const TransformParams& p, float* smem, int block,
                 const int tap = L * n2 - left + l;
                 if (tap >= 0 && tap < win) {
                   const float w = wtab[tap];
-                  const float2 v = buf[(l + L * (n2 % (R / L))) * (L + 1) + n2 / (R / L)];
-                  if (KIND == kKindStft) out2[tap] = make_float2(v.y * w, v.x * w);
-                  else                   out1[tap] = v.y * w;
+                  const float2 g = buf[(l + L * (n2 % (R / L))) * (L + 1) + n2 / (R / L)];
+                  if (KIND == kKindStft) out2[tap] = __fmul2_rn(make_float2(g.y, g.x), make_float2(w, w));
+                  else                   out1[tap] = g.y * w;
                 }
               }
             }
@@ -333,17 +332,11 @@ SPL_DEVICE void transform_body(const TransformParams& p, float* smem, int block,
                 const int tap = L * n2 - left + l;
                 if (tap >= 0 && tap < win) {
                   const float w = wtab[tap];
-                  const float2 v = buf[(l + L * (n2 % (R / L))) * (L + 1) + n2 / (R / L)];
+                  const float2 g = buf[(l + L * (n2 % (R / L))) * (L + 1) + n2 / (R / L)];
                   int idx = base + tap;
                   idx -= (idx >= p.ring_n) ? p.ring_n : 0;
-                  if (KIND == kKindStft) {
-                    float2 r = ring2[idx];
-                    r.x = fmaf(v.y, w, r.x);
-                    r.y = fmaf(v.x, w, r.y);
-                    ring2[idx] = r;
-                  } else {
-                    ring1[idx] = fmaf(v.y, w, ring1[idx]);
-                  }
+                  if (KIND == kKindStft) ring2[idx] = __ffma2_rn(make_float2(g.y, g.x), make_float2(w, w), ring2[idx]);
+                  else                   ring1[idx] = fmaf(g.y, w, ring1[idx]);
                 }
               }
             }
@@ -373,18 +366,18 @@ SPL_DEVICE void transform_body(const TransformParams& p, float* smem, int block,
               float2* qa = buf + row * (L + 1) + cidx;
               float2* qb = self_mirror ? qa : (row == 0 ? buf + (L - cidx) : buf + (R - row) * (L + 1) + (L - 1 - cidx));
               const float2 a = *qa, bm = *qb;
-              const float xr = a.x + bm.x, xi = a.y - bm.y;                       // 2 X[k]
-              const float yr = frame_equal ? xr : a.y + bm.y;                     // 2 Y[k]
-              const float yi = frame_equal ? xi : bm.x - a.x;
+              const float2 x2 = __fadd2_rn(a, make_float2(bm.x, -bm.y));                                 // 2 X[k]
+              const float2 y2 = frame_equal ? x2 : __fadd2_rn(make_float2(a.y, -a.x), make_float2(bm.y, bm.x));  // 2 Y[k]
+              const float xr = x2.x, xi = x2.y, yr = y2.x, yi = y2.y;
               const float px = fmaf(xr, xr, xi * xi), py = fmaf(yr, yr, yi * yi);  // 4 |X|^2, 4 |Y|^2
               const float pxc = fmaxf(px, eps4), pyc = fmaxf(py, eps4);
-              const float rx = rsqrtf(pxc), ry = rsqrtf(pyc);
+              const float rx = spl_fast_rsqrt(pxc), ry = spl_fast_rsqrt(pyc);
               const float ax = __fmul_rn(pxc, rx), ay = __fmul_rn(pyc, ry);       // 2 Ax, 2 Ay
               const float d = __fsub_rn(ay, ax);        // not contracted: exactly 0 when pxc == pyc
               const float rx2 = rx * rx;
               s1 = fmaf(d, d, s1);
               s2 += pyc;
-              s3 += (pxc == pyc) ? 0.f : fabsf(SPL_FAST_LOG2F(pyc * rx2));
+              s3 += (pxc == pyc) ? 0.f : fabsf(spl_fast_log2(pyc * rx2));
               if (GRAD) {
                 // gX = alpha X (spectral convergence) + i-slot beta X (log magnitude), both un-scaled:
                 //   alpha = gate (Ax - Ay)/Ax ,  beta = gate sign(Ax - Ay)/Ax^2 = 4 gate sign * rx2
@@ -394,9 +387,9 @@ SPL_DEVICE void transform_body(const TransformParams& p, float* smem, int block,
                 const float gr = gate ? -0.5f * wgt * d * rx : 0.f;
                 const float bsel = (pxc > pyc) ? rx2 : ((pxc < pyc) ? -rx2 : 0.f);
                 const float gi = gate ? 2.f * wgt * bsel : 0.f;
-                const float p1 = gr * xr, p2 = gi * xi, p3 = gr * xi, p4 = gi * xr;
-                *qa = make_float2(p1 - p2, p3 + p4);                    // (gr + i gi) * (2X)
-                if (!self_mirror) *qb = make_float2(p1 + p2, p4 - p3);  // (gr + i gi) * conj(2X)
+                const float2 g2 = make_float2(gi, gi), r2 = make_float2(gr, gr);
+                *qa = __ffma2_rn(make_float2(-xi, xr), g2, __fmul2_rn(x2, r2));                          // (gr + i gi) * (2X)
+                if (!self_mirror) *qb = __ffma2_rn(make_float2(xi, xr), g2, __fmul2_rn(make_float2(xr, -xi), r2));  // * conj(2X)
               }
             }
           } else if (GRAD) {
@@ -421,7 +414,7 @@ SPL_DEVICE void transform_body(const TransformParams& p, float* smem, int block,
             const float yr = frame_equal ? xr : 0.5f * (a.y + bm.y);
             const float yi = frame_equal ? xi : 0.5f * (bm.x - a.x);
             const float pxc = fmaxf(fmaf(xr, xr, xi * xi), p.eps), pyc = fmaxf(fmaf(yr, yr, yi * yi), p.eps);
-            const float2 amp = make_float2(pxc * rsqrtf(pxc), pyc * rsqrtf(pyc));
+            const float2 amp = make_float2(pxc * spl_fast_rsqrt(pxc), pyc * spl_fast_rsqrt(pyc));
             if (extra) { buf[EX1] = make_float2(xr, xi); *qa = amp; }
             else { *qa = make_float2(xr, xi); *(self_mirror ? buf + EX0 : qb) = amp; }
           }
@@ -475,7 +468,7 @@ SPL_DEVICE void transform_body(const TransformParams& p, float* smem, int block,
               const int4 bt = bin_tab[row + R * cidx];
               const float ga = fmaf(msum[bt.x].x, bits_to_float(bt.y), msum[bt.x + 1].x * bits_to_float(bt.z));
               const float px = fmaf(xk.x, xk.x, xk.y * xk.y);
-              const float g = (active && px >= p.eps) ? (self_mirror ? 1.f : 0.5f) * ga * rsqrtf(px) : 0.f;
+              const float g = (active && px >= p.eps) ? (self_mirror ? 1.f : 0.5f) * ga * spl_fast_rsqrt(px) : 0.f;
               *qa = make_float2(g * xk.x, g * xk.y);
               if (!self_mirror) *qb = make_float2(g * xk.x, -g * xk.y);
             }

@@ -19,6 +19,9 @@ struct int4 { int x, y, z, w; };
 struct int2 { int x, y; };
 struct alignas(16) float4 { float x, y, z, w; };
 static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+static inline float2 __fadd2_rn(float2 a, float2 b) { return float2{a.x + b.x, a.y + b.y}; }
+static inline float2 __fmul2_rn(float2 a, float2 b) { return float2{a.x * b.x, a.y * b.y}; }
+static inline float2 __ffma2_rn(float2 a, float2 b, float2 c) { return float2{std::fmaf(a.x, b.x, c.x), std::fmaf(a.y, b.y, c.y)}; }
 static inline float __fmul_rn(float a, float b) { return a * b; }
 static inline float __fsub_rn(float a, float b) { return a - b; }
 static inline float2 make_float2(float x, float y) { return float2{x, y}; }
