@@ -136,6 +136,12 @@ def run_ours(args, rank, local_rank, world):
     import torch
     import torch.distributed as dist
 
+    t_start = time.time()
+
+    def log(msg):
+        if args.verbose:
+            print(f"[bench r{rank} +{time.time() - t_start:6.1f}s] {msg}", file=sys.stderr, flush=True)
+
     import dl_speech_enhancement_b200 as pkg
     from dl_speech_enhancement_b200.engine import cuda_engine
 
@@ -146,6 +152,7 @@ def run_ours(args, rank, local_rank, world):
         dist.init_process_group("nccl", device_id=dev)
         group = dist.group.WORLD
     cuda_engine()          # raises if libspecloss.so is missing -- no fallback
+    log("process group + engine ready")
 
     stft = pkg.MultiResolutionSTFTLoss().to(dev)
     mel = pkg.MultiMelSpectrogramLoss(**MEL_KW).to(dev)
@@ -202,7 +209,9 @@ def run_ours(args, rank, local_rank, world):
         return float(t.item()) / steps, eng.launches - n0, clocks
 
     # ---- eager: one Python-driven launch sequence per step -----------------------------------------
+    log("pool ready, timing eager steps")
     eager_ms, eager_launches, clocks = timed(eager_step, args.steps, args.warmup, sample_clocks=True)
+    log(f"eager {eager_ms:.4f} ms/step")
     mode, ms_per_step, launches_timed = "eager launches", eager_ms, eager_launches
 
     # ---- CUDA graph: the same step captured once and replayed (inputs are copied into the graph's static
@@ -229,6 +238,7 @@ def run_ours(args, rank, local_rank, world):
     graph_ms, sets = None, None
     if not args.no_graph:
         ok = 1
+        log("capturing CUDA graphs")
         try:
             sets = [capture_set(), capture_set()]
         except Exception as exc:      # graph capture is an optimisation of the launch path, never a requirement
@@ -248,13 +258,19 @@ def run_ours(args, rank, local_rank, world):
             g0["sy"].copy_(y)
             g0["graph"].replay()
 
+        log("timing graph replays")
         graph_ms, _, clocks_g = timed(graph_step, args.steps, args.warmup, sample_clocks=True)
+        log(f"graph {graph_ms:.4f} ms/step")
         # the replayed step must reproduce the eager result bit for bit
         graph_step(0)
         ref = eager_step(0)
         torch.cuda.synchronize()
         same = all(float(a.detach()) == float(b.detach()) for a, b in zip(g0["losses"], ref))
         same = same and torch.equal(g0["sx"].grad, pool[0][0].grad)
+        flag = torch.tensor([1 if same else 0], device=dev)
+        if world > 1:
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)      # every rank must take the same branch below
+        same = bool(int(flag.item()))
         if not same:
             print("[bench] CUDA graph replay does not reproduce the eager step; ignoring it", file=sys.stderr)
             graph_ms, sets = None, None
@@ -313,6 +329,7 @@ def run_ours(args, rank, local_rank, world):
 
     e2e_loop = e2e_loop_graph if sets is not None else e2e_loop_eager
     e2e_mode = "CUDA graph replay" if sets is not None else "eager launches"
+    log("e2e (" + e2e_mode + ")")
     e2e_loop(max(3, args.warmup // 4))
     barrier()
     e_steps = max(10, args.steps // 4)
@@ -324,7 +341,9 @@ def run_ours(args, rank, local_rank, world):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * BATCH * T_LEN / FS / (float(t.item()) / 1000.0)
-
+    log("e2e done")
+    if world > 1:
+        dist.barrier()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -397,6 +416,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="skip the CUDA-graph replay measurement")
+    ap.add_argument("--verbose", action="store_true", help="stage-by-stage progress on stderr")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
