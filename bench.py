@@ -342,11 +342,33 @@ def run_ours(args, rank, local_rank, world):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * BATCH * T_LEN / FS / (float(t.item()) / 1000.0)
     log("e2e done")
-    if world > 1:
-        dist.barrier()
-    if rank != 0:
+
+    def teardown():
+        """Release the captured graphs before the communicator; never let teardown hang the job."""
+        nonlocal sets
+        for st in (sets or []):
+            st.clear()               # drops the CUDAGraph objects (they hold NCCL work when world > 1)
+        sets = None
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
         if world > 1:
-            dist.destroy_process_group()
+            done = threading.Event()
+
+            def _destroy():
+                try:
+                    dist.barrier()
+                    dist.destroy_process_group()
+                finally:
+                    done.set()
+            threading.Thread(target=_destroy, daemon=True).start()
+            if not done.wait(20.0):
+                log("process-group teardown timed out; exiting")
+                sys.stdout.flush()
+                sys.stderr.flush()
+                os._exit(0)
+    if rank != 0:
+        teardown()
         return
 
     # ---- per-kernel timing of the dominant (transform) kernels, CUDA events on the launch stream ---
@@ -404,8 +426,7 @@ def run_ours(args, rank, local_rank, world):
                                                 + e2e_mode + "), D2H of the 3 losses + stream sync; max over ranks"},
             "gpu_launches": launches_timed, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    teardown()
 
 
 def main():
