@@ -190,6 +190,92 @@ SPL_DEVICE float bits_to_float(int b) {
 // (grid-stride over chunks).  WIN_T > 0: window length known at compile time (shipped configs),
 // which prunes the zero taps out of the load, the first butterflies and the overlap-add.
 // ---------------------------------------------------------------------------------------------
+// One mirror pair (k, N-k) of the packed spectrum Z = FFT(x + i y) of an STFT-loss frame:
+//   2X[k] = Z[k] + conj Z[N-k],  2Y[k] = -i (Z[k] - conj Z[N-k]);
+// loss terms from the doubled spectra (powers x4, magnitudes x2; the chunk's sums are rescaled once), and --
+// GRAD -- the un-scaled gradient spectra written back in place:
+//   H[k] = w/2 (alpha + i beta) (2X),  H[N-k] = w/2 (alpha + i beta) conj(2X),  w = 1/2 (1 when k mirrors itself)
+//   alpha = gate (Ax - Ay)/Ax  (spectral convergence),  beta = gate sign(Ax - Ay)/Ax^2  (log magnitude).
+// EQ: prediction and target frames are bit-identical, Y := X, every difference term is exactly zero.
+template <bool GRAD, bool EQ>
+SPL_DEVICE void stft_pair(float2* qa, float2* qb, bool self, float eps4, float& s1, float& s2, float& s3) {
+  const float2 a = *qa, bm = *qb;
+  const float2 x2 = __fadd2_rn(a, make_float2(bm.x, -bm.y));
+  const float px = fmaf(x2.x, x2.x, x2.y * x2.y);
+  const float pxc = fmaxf(px, eps4);
+  if (EQ) {
+    s2 += pxc;
+    if (GRAD) {
+      *qa = make_float2(0.f, 0.f);
+      if (!self) *qb = make_float2(0.f, 0.f);
+    }
+    return;
+  }
+  const float2 y2 = __fadd2_rn(make_float2(a.y, -a.x), make_float2(bm.y, bm.x));
+  const float py = fmaf(y2.x, y2.x, y2.y * y2.y);
+  const float pyc = fmaxf(py, eps4);
+  const float rx = spl_fast_rsqrt(pxc), ry = spl_fast_rsqrt(pyc);
+  const float ax = __fmul_rn(pxc, rx), ay = __fmul_rn(pyc, ry);       // 2 Ax, 2 Ay
+  const float d = __fsub_rn(ay, ax);                                  // never contracted: 0 when pxc == pyc
+  s1 = fmaf(d, d, s1);
+  s2 += pyc;
+  s3 += fabsf(spl_fast_log2(pyc * rx * rx));
+  if (GRAD) {
+    const float wq = self ? 0.5f : 0.25f;
+    const float rxg = px >= eps4 ? rx : 0.f;                          // clamp gate of the reference
+    const float sgn = fminf(fmaxf((pxc - pyc) * 1e25f, -1.f), 1.f);   // exact sign, 0 when equal
+    const float gr = -wq * d * rxg;
+    const float gi = 4.f * wq * sgn * rx * rxg;
+    const float2 g2 = make_float2(gi, gi), r2 = make_float2(gr, gr);
+    *qa = __ffma2_rn(make_float2(-x2.y, x2.x), g2, __fmul2_rn(x2, r2));
+    if (!self) *qb = __ffma2_rn(make_float2(x2.y, x2.x), g2, __fmul2_rn(make_float2(x2.x, -x2.y), r2));
+  }
+}
+
+// all pairs of one lane: rows l + L*j, columns 0 .. L/2-1 (column 0 of row 0 mirrors itself)
+template <int NFFT, bool GRAD, bool EQ>
+SPL_DEVICE void stft_epilogue(float2* buf, int l, float eps4, float& s1, float& s2, float& s3) {
+  using G = FftGeom<NFFT>;
+  constexpr int L = G::L, R = G::R;
+#pragma unroll
+  for (int j = 0; j < R / L; ++j) {
+    const int row = l + L * j;
+    float2* pa = buf + row * (L + 1);
+    float2* pb = (row == 0) ? buf + L : buf + (R - row) * (L + 1) + (L - 1);      // mirror of column c is pb[-c]
+    stft_pair<GRAD, EQ>(pa, row == 0 ? pa : pb, row == 0, eps4, s1, s2, s3);
+#pragma unroll (EQ ? 1 : (L == 32 ? 5 : 7))
+    for (int c = 1; c < L / 2; ++c) stft_pair<GRAD, EQ>(pa + c, pb - c, false, eps4, s1, s2, s3);
+  }
+  if (l == 0) stft_pair<GRAD, EQ>(buf + L / 2, buf + L / 2, true, eps4, s1, s2, s3);   // bin N/2
+}
+
+// mel, pass 1 on one mirror pair: keep 2X[k] in the bin's own slot, park (Ax, Ay) in `amp_slot`.
+template <bool EQ>
+SPL_DEVICE void mel_pair_amp(float2* qa, float2* qb, float2* x_slot, float2* amp_slot, float eps4) {
+  const float2 a = *qa, bm = *qb;
+  const float2 x2 = __fadd2_rn(a, make_float2(bm.x, -bm.y));
+  const float2 y2 = EQ ? x2 : __fadd2_rn(make_float2(a.y, -a.x), make_float2(bm.y, bm.x));
+  const float pxc = fmaxf(fmaf(x2.x, x2.x, x2.y * x2.y), eps4);
+  const float pyc = EQ ? pxc : fmaxf(fmaf(y2.x, y2.x, y2.y * y2.y), eps4);
+  const float ax = 0.5f * pxc * spl_fast_rsqrt(pxc);                       // sqrt(max(|X|^2, eps))
+  const float ay = EQ ? ax : 0.5f * pyc * spl_fast_rsqrt(pyc);
+  *x_slot = x2;
+  *amp_slot = make_float2(ax, ay);
+}
+
+// mel, pass 3 on one mirror pair: gA[k] = gM[m0] W[k,m0] + gM[m0+1] W[k,m0+1];  H[k] = w gA gate / Ax * X
+SPL_DEVICE void mel_pair_grad(float2* qa, float2* qb, const float2* x_slot, bool self, int4 bt, const float2* msum,
+                              float eps4, bool active) {
+  const float2 x2 = *x_slot;
+  const float ga = fmaf(msum[bt.x].x, bits_to_float(bt.y), msum[bt.x + 1].x * bits_to_float(bt.z));
+  const float px = fmaf(x2.x, x2.x, x2.y * x2.y);                          // 4 |X|^2
+  // w gA / Ax * X = w gA * 2 rsqrt(px) * (2X) / 2
+  const float g = (active && px >= eps4) ? (self ? 1.f : 0.5f) * ga * spl_fast_rsqrt(px) : 0.f;
+  const float2 hk = __fmul2_rn(x2, make_float2(g, g));
+  *qa = hk;
+  if (!self) *qb = make_float2(hk.x, -hk.y);
+}
+
 // CTA prologue: every thread copies its share of the constant tables into shared memory.
 template <int NFFT, int KIND>
 SPL_DEVICE void cta_load_tables(const TransformParams& p, float* smem, int tid, int nthreads) {
@@ -269,22 +355,40 @@ SPL_DEVICE void transform_body(const TransformParams& p, float* smem, int block,
           const int s0 = t * p.hop - HALF;                         // sample index of tap n = 0
           const bool interior = (s0 + left >= 0) && (s0 + left + win <= p.T);
           bool same = true;
+          if (active && interior) {
+            // fast path: no reflection; every address is a compile-time offset from three pointers
+            const float* __restrict__ xp = xb + s0 + l;
+            const float* __restrict__ yp = yb + s0 + l;
+            const float* wp = wtab + (l - left);
 #pragma unroll
-          for (int n2 = 0; n2 < R; ++n2) {
-            const int lo = L * n2 - left;                          // tap index of lane 0
-            if (WIN_T > 0 && (lo + L - 1 < 0 || lo >= WIN_T)) { v[n2] = make_float2(0.f, 0.f); continue; }
-            const int tap = lo + l;
-            const bool all_lanes = WIN_T > 0 && lo >= 0 && lo + L - 1 < WIN_T;
-            float xv = 0.f, yv = 0.f;
-            if (active && (all_lanes || (tap >= 0 && tap < win))) {
-              int s = s0 + L * n2 + l;
-              if (!interior) s = reflect(s, p.T);
-              const float w = wtab[tap];
-              xv = __ldg(&xb[s]) * w;
-              yv = __ldg(&yb[s]) * w;
+            for (int n2 = 0; n2 < R; ++n2) {
+              const int lo = L * n2 - left;                        // tap index of lane 0
+              if (WIN_T > 0 && (lo + L - 1 < 0 || lo >= WIN_T)) { v[n2] = make_float2(0.f, 0.f); continue; }
+              const bool all_lanes = WIN_T > 0 && lo >= 0 && lo + L - 1 < WIN_T;
+              float2 xy = make_float2(0.f, 0.f);
+              if (all_lanes || (lo + l >= 0 && lo + l < win)) {
+                const float w = wp[L * n2];
+                xy = __fmul2_rn(make_float2(__ldg(xp + L * n2), __ldg(yp + L * n2)), make_float2(w, w));
+              }
+              same = same && (xy.x == xy.y);
+              v[n2] = xy;
             }
-            same = same && (xv == yv);
-            v[n2] = make_float2(xv, yv);
+          } else {
+#pragma unroll
+            for (int n2 = 0; n2 < R; ++n2) {
+              const int lo = L * n2 - left;
+              if (WIN_T > 0 && (lo + L - 1 < 0 || lo >= WIN_T)) { v[n2] = make_float2(0.f, 0.f); continue; }
+              const int tap = lo + l;
+              float xv = 0.f, yv = 0.f;
+              if (active && tap >= 0 && tap < win) {
+                const int sidx = reflect(s0 + L * n2 + l, p.T);
+                const float w = wtab[tap];
+                xv = __ldg(&xb[sidx]) * w;
+                yv = __ldg(&yb[sidx]) * w;
+              }
+              same = same && (xv == yv);
+              v[n2] = make_float2(xv, yv);
+            }
           }
           // A frame whose prediction and target taps are bit-identical must contribute exactly zero
           // (the reference returns sc = mag = mel = 0 and a zero gradient for x == y); the packed FFT
@@ -349,49 +453,11 @@ SPL_DEVICE void transform_body(const TransformParams& p, float* smem, int block,
         // Bin k = row + R*col sits at buf[row*(L+1) + col].  A lane owns rows l + L*j; for col < L/2 the
         // bin is k < N/2 and its mirror N-k is (R - row, L-1-col) -- or (0, L-col) inside row 0.  Bins 0
         // and N/2 (row 0, cols 0 and L/2) mirror themselves; lane 0 handles N/2 as the extra pair.
-        constexpr int NP = (R / L) * (L / 2);             // pairs per lane
         if (KIND == kKindStft) {
-          // Z = FFT(x + i y):  2X[k] = Z[k] + conj Z[N-k],  2Y[k] = -i (Z[k] - conj Z[N-k]).
-          // Everything below works on the doubled spectra (powers x4, magnitudes x2); the sums are
-          // rescaled once per chunk and the gradient factors absorb the scale.
           const float eps4 = 4.f * p.eps;
           if (active) {
-#pragma unroll 4
-            for (int i = 0; i <= NP; ++i) {
-              const bool extra = (i == NP);
-              if (extra && l != 0) break;
-              const int j = extra ? 0 : i / (L / 2), cidx = extra ? L / 2 : i % (L / 2);
-              const int row = l + L * j;
-              const bool self_mirror = extra || (row == 0 && cidx == 0);
-              float2* qa = buf + row * (L + 1) + cidx;
-              float2* qb = self_mirror ? qa : (row == 0 ? buf + (L - cidx) : buf + (R - row) * (L + 1) + (L - 1 - cidx));
-              const float2 a = *qa, bm = *qb;
-              const float2 x2 = __fadd2_rn(a, make_float2(bm.x, -bm.y));                                 // 2 X[k]
-              const float2 y2 = frame_equal ? x2 : __fadd2_rn(make_float2(a.y, -a.x), make_float2(bm.y, bm.x));  // 2 Y[k]
-              const float xr = x2.x, xi = x2.y, yr = y2.x, yi = y2.y;
-              const float px = fmaf(xr, xr, xi * xi), py = fmaf(yr, yr, yi * yi);  // 4 |X|^2, 4 |Y|^2
-              const float pxc = fmaxf(px, eps4), pyc = fmaxf(py, eps4);
-              const float rx = spl_fast_rsqrt(pxc), ry = spl_fast_rsqrt(pyc);
-              const float ax = __fmul_rn(pxc, rx), ay = __fmul_rn(pyc, ry);       // 2 Ax, 2 Ay
-              const float d = __fsub_rn(ay, ax);        // not contracted: exactly 0 when pxc == pyc
-              const float rx2 = rx * rx;
-              s1 = fmaf(d, d, s1);
-              s2 += pyc;
-              s3 += (pxc == pyc) ? 0.f : fabsf(spl_fast_log2(pyc * rx2));
-              if (GRAD) {
-                // gX = alpha X (spectral convergence) + i-slot beta X (log magnitude), both un-scaled:
-                //   alpha = gate (Ax - Ay)/Ax ,  beta = gate sign(Ax - Ay)/Ax^2 = 4 gate sign * rx2
-                // H[k] = w (alpha + i beta) X = w/2 (alpha + i beta) (2X), w = 1/2 (1 for self-mirror bins)
-                const bool gate = px >= eps4;
-                const float wgt = self_mirror ? 1.f : 0.5f;
-                const float gr = gate ? -0.5f * wgt * d * rx : 0.f;
-                const float bsel = (pxc > pyc) ? rx2 : ((pxc < pyc) ? -rx2 : 0.f);
-                const float gi = gate ? 2.f * wgt * bsel : 0.f;
-                const float2 g2 = make_float2(gi, gi), r2 = make_float2(gr, gr);
-                *qa = __ffma2_rn(make_float2(-xi, xr), g2, __fmul2_rn(x2, r2));                          // (gr + i gi) * (2X)
-                if (!self_mirror) *qb = __ffma2_rn(make_float2(xi, xr), g2, __fmul2_rn(make_float2(xr, -xi), r2));  // * conj(2X)
-              }
-            }
+            if (frame_equal) stft_epilogue<NFFT, GRAD, true>(buf, l, eps4, s1, s2, s3);
+            else             stft_epilogue<NFFT, GRAD, false>(buf, l, eps4, s1, s2, s3);
           } else if (GRAD) {
             for (int i = l; i < R * (L + 1); i += L) buf[i] = make_float2(0.f, 0.f);
           }
@@ -400,23 +466,25 @@ SPL_DEVICE void transform_body(const TransformParams& p, float* smem, int block,
           // pass 1: X stays in the bin's own slot; (Ax, Ay) are parked in the mirror slot; bin 0 parks
           // them in the pad slot of row 0, bin N/2 keeps them in place and moves X to the pad slot of row 1.
           constexpr int EX0 = L, EX1 = (L + 1) + L;
-#pragma unroll 4
-          for (int i = 0; i <= NP; ++i) {
-            const bool extra = (i == NP);
-            if (extra && l != 0) break;
-            const int j = extra ? 0 : i / (L / 2), cidx = extra ? L / 2 : i % (L / 2);
+          const float eps4 = 4.f * p.eps;
+#pragma unroll
+          for (int j = 0; j < R / L; ++j) {
             const int row = l + L * j;
-            const bool self_mirror = extra || (row == 0 && cidx == 0);
-            float2* qa = buf + row * (L + 1) + cidx;
-            float2* qb = self_mirror ? qa : (row == 0 ? buf + (L - cidx) : buf + (R - row) * (L + 1) + (L - 1 - cidx));
-            const float2 a = *qa, bm = *qb;
-            const float xr = 0.5f * (a.x + bm.x), xi = 0.5f * (a.y - bm.y);
-            const float yr = frame_equal ? xr : 0.5f * (a.y + bm.y);
-            const float yi = frame_equal ? xi : 0.5f * (bm.x - a.x);
-            const float pxc = fmaxf(fmaf(xr, xr, xi * xi), p.eps), pyc = fmaxf(fmaf(yr, yr, yi * yi), p.eps);
-            const float2 amp = make_float2(pxc * spl_fast_rsqrt(pxc), pyc * spl_fast_rsqrt(pyc));
-            if (extra) { buf[EX1] = make_float2(xr, xi); *qa = amp; }
-            else { *qa = make_float2(xr, xi); *(self_mirror ? buf + EX0 : qb) = amp; }
+            float2* pa = buf + row * (L + 1);
+            float2* pb = (row == 0) ? buf + L : buf + (R - row) * (L + 1) + (L - 1);    // mirror of column c is pb[-c]
+            if (frame_equal) {
+              mel_pair_amp<true>(pa, row == 0 ? pa : pb, pa, row == 0 ? buf + EX0 : pb, eps4);
+#pragma unroll 1
+              for (int c = 1; c < L / 2; ++c) mel_pair_amp<true>(pa + c, pb - c, pa + c, pb - c, eps4);
+            } else {
+              mel_pair_amp<false>(pa, row == 0 ? pa : pb, pa, row == 0 ? buf + EX0 : pb, eps4);
+#pragma unroll (L == 32 ? 5 : 7)
+              for (int c = 1; c < L / 2; ++c) mel_pair_amp<false>(pa + c, pb - c, pa + c, pb - c, eps4);
+            }
+          }
+          if (l == 0) {                                        // bin N/2: amplitudes stay, X moves to the pad slot
+            if (frame_equal) mel_pair_amp<true>(buf + L / 2, buf + L / 2, buf + EX1, buf + L / 2, eps4);
+            else             mel_pair_amp<false>(buf + L / 2, buf + L / 2, buf + EX1, buf + L / 2, eps4);
           }
           __syncwarp();
           // pass 2: balanced projection.  Every mel row is summed by a group of 1..L lanes walking a
@@ -455,23 +523,18 @@ SPL_DEVICE void transform_body(const TransformParams& p, float* smem, int block,
           __syncwarp();
           if (GRAD) {
             // pass 3: gA[k] = sum_m gM[m] W[k,m] (<= 2 adjacent rows), H[k] = w gA gate / Ax * X
-#pragma unroll 4
-            for (int i = 0; i <= NP; ++i) {
-              const bool extra = (i == NP);
-              if (extra && l != 0) break;
-              const int j = extra ? 0 : i / (L / 2), cidx = extra ? L / 2 : i % (L / 2);
+            const float eps4g = 4.f * p.eps;
+#pragma unroll
+            for (int j = 0; j < R / L; ++j) {
               const int row = l + L * j;
-              const bool self_mirror = extra || (row == 0 && cidx == 0);
-              float2* qa = buf + row * (L + 1) + cidx;
-              float2* qb = self_mirror ? qa : (row == 0 ? buf + (L - cidx) : buf + (R - row) * (L + 1) + (L - 1 - cidx));
-              const float2 xk = extra ? buf[EX1] : *qa;
-              const int4 bt = bin_tab[row + R * cidx];
-              const float ga = fmaf(msum[bt.x].x, bits_to_float(bt.y), msum[bt.x + 1].x * bits_to_float(bt.z));
-              const float px = fmaf(xk.x, xk.x, xk.y * xk.y);
-              const float g = (active && px >= p.eps) ? (self_mirror ? 1.f : 0.5f) * ga * spl_fast_rsqrt(px) : 0.f;
-              *qa = make_float2(g * xk.x, g * xk.y);
-              if (!self_mirror) *qb = make_float2(g * xk.x, -g * xk.y);
+              float2* pa = buf + row * (L + 1);
+              float2* pb = (row == 0) ? buf + L : buf + (R - row) * (L + 1) + (L - 1);
+              mel_pair_grad(pa, row == 0 ? pa : pb, pa, row == 0, bin_tab[row], msum, eps4g, active);
+#pragma unroll (L == 32 ? 5 : 7)
+              for (int c = 1; c < L / 2; ++c)
+                mel_pair_grad(pa + c, pb - c, pa + c, false, bin_tab[row + R * c], msum, eps4g, active);
             }
+            if (l == 0) mel_pair_grad(buf + L / 2, buf + L / 2, buf + EX1, true, bin_tab[NFFT / 2], msum, eps4g, active);
           }
         }
         __syncwarp();
