@@ -38,6 +38,10 @@ __device__ __forceinline__ float spl_fast_log2(float x) {
 }
 #endif
 
+#ifndef SPL_MAX_WARPS_SMALL
+#define SPL_MAX_WARPS_SMALL 16
+#endif
+
 namespace spl {
 
 constexpr int kKindStft = 0;
@@ -544,10 +548,13 @@ SPL_DEVICE void transform_body(const TransformParams& p, float* smem, int block,
         // ---- F. flush the ring entries no later frame of this chunk touches ----------------------
         const int done = min(m_c, (step + 1) * FPW);
         const int limit = (done == m_c) ? span_c : done * p.hop;
+        int idx = (flushed + lane) % p.ring_n;                  // one division per flush, then wrap by compare
+        const int wrap = 32 % p.ring_n;
         for (int q = flushed + lane; q < limit; q += 32) {
-          const int idx = q % p.ring_n;
           if (KIND == kKindStft) { out2[q] = ring2[idx]; ring2[idx] = make_float2(0.f, 0.f); }
           else                   { out1[q] = ring1[idx]; ring1[idx] = 0.f; }
+          idx += wrap;
+          idx -= (idx >= p.ring_n) ? p.ring_n : 0;
         }
         flushed = limit;
         __syncwarp();
@@ -567,6 +574,95 @@ SPL_DEVICE void transform_body(const TransformParams& p, float* smem, int block,
       }
     }
   }  // chunk
+}
+
+// ---------------------------------------------------------------------------------------------
+// Explicit magnitude spectrogram, forward only: out[b, t, k] = sqrt(max(|STFT(x)[b, t, k]|^2, eps)),
+// laid out (B, F, ld >= K) -- the tensor stft() returns (losses/stft_loss.py:19-35) and the A operand of
+// the mel projection GEMM.  Frames t and t+1 of the SAME signal share one complex FFT (real / imaginary
+// slot), so the work per frame is half of a naive real transform.
+// ---------------------------------------------------------------------------------------------
+struct SpecParams {
+  const float* x;        // (B, T)
+  int B, T;
+  int hop, win, left, n_frames;
+  int n_pairs;           // frame pairs per utterance = (n_frames + 1) / 2
+  float eps;
+  const float* window;
+  const float2* twiddle;
+  float* out;            // (B, n_frames, ld)
+  int ld;
+};
+
+template <int NFFT>
+SPL_DEVICE void spec_load_tables(const SpecParams& p, float* smem, int tid, int nthreads) {
+  constexpr int L = FftGeom<NFFT>::L;
+  const CtaTables ct = cta_tables(NFFT, p.win, kKindStft, L, 0, 0);
+  const float* tw = reinterpret_cast<const float*>(p.twiddle);
+  for (int i = tid; i < 2 * NFFT; i += nthreads) smem[ct.tw + i] = __ldg(&tw[i]);
+  for (int i = tid; i < p.win; i += nthreads) smem[ct.win + i] = __ldg(&p.window[i]);
+}
+
+template <int NFFT>
+SPL_DEVICE void spec_body(const SpecParams& p, float* smem, int block, int tid, int grid, int wpc) {
+  using G = FftGeom<NFFT>;
+  using SL = SmemLayout<NFFT, kKindStft, false>;
+  constexpr int L = G::L, R = G::R, FPW = SL::FPW, HALF = NFFT / 2;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int l = lane & (L - 1), h = lane / L;
+  const CtaTables ct = cta_tables(NFFT, p.win, kKindStft, L, 0, 0);
+  const float2* tw = reinterpret_cast<const float2*>(smem + ct.tw);
+  const float* wtab = smem + ct.win;
+  float2* buf = reinterpret_cast<float2*>(smem + ct.total + (size_t)warp * SL::words_per_warp(0, 0)) + h * SL::BUF_F2;
+  const int total = p.B * p.n_pairs;                 // work items: (utterance, frame pair)
+  const float eps4 = 4.f * p.eps;
+  const int steps = (total + grid * wpc * FPW - 1) / (grid * wpc * FPW);
+  for (int it = 0; it < steps; ++it) {
+    const int item = (it * grid * wpc + block * wpc + warp) * FPW + h;
+    const bool active = item < total;
+    const int b = active ? item / p.n_pairs : 0, pr = active ? item - b * p.n_pairs : 0;
+    const int t = 2 * pr;
+    const bool second = active && (t + 1 < p.n_frames);
+    const float* __restrict__ xb = p.x + (size_t)b * p.T;
+    float2 v[R];
+#pragma unroll
+    for (int n2 = 0; n2 < R; ++n2) {
+      const int tap = L * n2 - p.left + l;
+      float a0 = 0.f, a1 = 0.f;
+      if (active && tap >= 0 && tap < p.win) {
+        const float w = wtab[tap];
+        const int s = t * p.hop + L * n2 + l - HALF;
+        a0 = __ldg(&xb[reflect(s, p.T)]) * w;
+        if (second) a1 = __ldg(&xb[reflect(s + p.hop, p.T)]) * w;
+      }
+      v[n2] = make_float2(a0, a1);
+    }
+    fft_core<NFFT>(v, buf, tw, l);
+    if (active) {
+      float* o0 = p.out + ((size_t)b * p.n_frames + t) * p.ld;
+      float* o1 = o0 + p.ld;
+#pragma unroll
+      for (int j = 0; j < R / L; ++j) {
+        const int row = l + L * j;
+        const float2* pa = buf + row * (L + 1);
+        const float2* pb = (row == 0) ? buf + L : buf + (R - row) * (L + 1) + (L - 1);
+#pragma unroll 4
+        for (int c = 0; c <= L / 2; ++c) {
+          if (c == L / 2 && row != 0) break;                    // bin N/2 lives in row 0 only
+          const bool self = (row == 0) && (c == 0 || c == L / 2);
+          const float2 a = pa[c], bm = self ? a : pb[-c];
+          const float2 x2 = __fadd2_rn(a, make_float2(bm.x, -bm.y));                           // 2 X_t[k]
+          const float2 y2 = __fadd2_rn(make_float2(a.y, -a.x), make_float2(bm.y, bm.x));       // 2 X_{t+1}[k]
+          const float p0 = fmaxf(fmaf(x2.x, x2.x, x2.y * x2.y), eps4);
+          const float p1 = fmaxf(fmaf(y2.x, y2.x, y2.y * y2.y), eps4);
+          const int k = row + R * c;
+          o0[k] = 0.5f * p0 * spl_fast_rsqrt(p0);
+          if (second) o1[k] = 0.5f * p1 * spl_fast_rsqrt(p1);
+        }
+      }
+    }
+    __syncwarp();
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -767,7 +863,7 @@ struct ReduceFinalizeParams {
 #ifndef SPECLOSS_EMU
 // One persistent CTA per SM: up to 12 warps (168 registers) for the 64-point-per-lane kernels, 16 (128
 // registers) for the others; the host picks the actual warp count from the shared-memory budget.
-template <int NFFT> struct MaxWarps { static constexpr int value = NFFT == 2048 ? 12 : 16; };
+template <int NFFT> struct MaxWarps { static constexpr int value = NFFT == 2048 ? 12 : SPL_MAX_WARPS_SMALL; };
 
 template <int NFFT, int KIND, bool GRAD, int WIN_T>
 __global__ void __launch_bounds__(MaxWarps<NFFT>::value * 32, 1) transform_kernel(const TransformParams p) {
@@ -775,6 +871,13 @@ __global__ void __launch_bounds__(MaxWarps<NFFT>::value * 32, 1) transform_kerne
   cta_load_tables<NFFT, KIND>(p, smem_dyn, threadIdx.x, blockDim.x);
   __syncthreads();
   transform_body<NFFT, KIND, GRAD, WIN_T>(p, smem_dyn, blockIdx.x, threadIdx.x, gridDim.x, blockDim.x >> 5);
+}
+template <int NFFT>
+__global__ void __launch_bounds__(MaxWarps<NFFT>::value * 32, 1) spec_kernel(const SpecParams p) {
+  extern __shared__ __align__(16) float smem_dyn[];
+  spec_load_tables<NFFT>(p, smem_dyn, threadIdx.x, blockDim.x);
+  __syncthreads();
+  spec_body<NFFT>(p, smem_dyn, blockIdx.x, threadIdx.x, gridDim.x, blockDim.x >> 5);
 }
 __global__ void __launch_bounds__(256) reduce_kernel(const ReduceParams p) {
   __shared__ double sh[256];

@@ -8,6 +8,9 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import dl_speech_enhancement_b200 as pkg  # noqa: E402
+from dl_speech_enhancement_b200 import _abi  # noqa: E402
+if os.environ.get("PROF_LIB"):          # profiling only: time an alternative build of the library
+    _abi.LIB_PATH = os.path.abspath(os.environ["PROF_LIB"])
 from dl_speech_enhancement_b200.engine import cuda_engine  # noqa: E402
 
 B, T = int(os.environ.get("PROF_B", 16)), int(os.environ.get("PROF_T", 48000))
