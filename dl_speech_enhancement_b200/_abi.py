@@ -15,7 +15,7 @@ from ctypes import POINTER, c_char_p, c_double, c_float, c_int32, c_int64, c_voi
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libspecloss.so")
 CSRC = os.path.join(_HERE, "csrc")
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 SPL_KIND_STFT = 0
 SPL_KIND_MEL = 1
@@ -31,23 +31,23 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
 class SplTransform(ctypes.Structure):
     _fields_ = [
         ("kind", c_int32), ("n_fft", c_int32), ("hop", c_int32), ("win", c_int32),
-        ("frames_per_chunk", c_int32), ("eps", c_float),
+        ("eps", c_float),
         ("window", c_void_p), ("twiddle", c_void_p),
         ("n_mels", c_int32), ("inv_ln_base", c_float),
         ("mel_tasks", c_void_p), ("mel_entries", c_void_p), ("mel_rounds", c_int32), ("mel_entry_rows", c_int32), ("bin_tab", c_void_p),
-        ("partials", c_void_p), ("gchunks", c_void_p),
+        ("partials", c_void_p), ("gframes", c_void_p),
     ]
 
 
 class SplGeometry(ctypes.Structure):
     _fields_ = [
-        ("n_frames", c_int32), ("n_bins", c_int32), ("n_chunks", c_int32), ("span", c_int32),
-        ("n_sums", c_int32), ("partial_count", c_int64), ("gchunk_bytes", c_int64), ("smem_table_bytes", c_int64), ("smem_warp_bytes", c_int64),
+        ("n_frames", c_int32), ("n_bins", c_int32), ("n_sums", c_int32), ("reserved", c_int32),
+        ("partial_count", c_int64), ("gframe_bytes", c_int64), ("smem_table_bytes", c_int64), ("smem_warp_bytes", c_int64),
     ]
 
 
 EXPORTS = ("spl_abi_version", "spl_last_error", "spl_fill_twiddle", "spl_geometry_of", "spl_forward",
-           "spl_reduce", "spl_finalize", "spl_reduce_finalize", "spl_backward")
+           "spl_reduce", "spl_finalize", "spl_reduce_finalize", "spl_backward", "spl_spectrogram")
 
 
 class SpecLossError(RuntimeError):
@@ -77,6 +77,9 @@ def bind(lib: ctypes.CDLL) -> ctypes.CDLL:
     lib.spl_backward.restype = c_int32
     lib.spl_backward.argtypes = [POINTER(SplTransform), c_int32, c_int32, c_int32, c_void_p,
                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.spl_spectrogram.restype = c_int32
+    lib.spl_spectrogram.argtypes = [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p,
+                                    c_float, c_void_p, c_int32, c_void_p]
     ver = lib.spl_abi_version()
     if ver != ABI_VERSION:
         raise SpecLossError(f"libspecloss ABI version {ver}, expected {ABI_VERSION}")

@@ -28,38 +28,66 @@ int fail(int code, const char* fmt, ...) {
 
 constexpr size_t kMaxSmem = 227 * 1024;
 
-template <int NFFT, int KIND, bool GRAD, int WIN_T>
-int spl_launch_transform(const spl::TransformParams& p, int n_mels, void* stream) {
-  using SL = spl::SmemLayout<NFFT, KIND, GRAD>;
-  constexpr int L = spl::FftGeom<NFFT>::L;
-  const spl::CtaTables ct = spl::cta_tables(NFFT, p.win, KIND, L, p.mel_rounds, p.mel_entry_rows);
-  const size_t table_bytes = (size_t)ct.total * 4;
-  const size_t warp_bytes = (size_t)SL::words_per_warp(p.ring_n, n_mels) * 4;
+int device_sm_count(int* sms) {
+  static thread_local int cached[64] = {0};
+  int dev = 0;
+  SPL_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return fail(SPL_E_INVALID, "device ordinal %d out of range", dev);
+  if (!cached[dev]) SPL_CUDA(cudaDeviceGetAttribute(&cached[dev], cudaDevAttrMultiProcessorCount, dev));
+  *sms = cached[dev];
+  return SPL_OK;
+}
+
+// One persistent CTA per SM.  Warps per CTA: as many as registers (launch bounds) and shared memory allow, but
+// no more than needed to give every SM work; the warps then stride over the work items.
+int spl_launch_shape(int n_fft, size_t table_bytes, size_t warp_bytes, long long items, int* grid, int* wpc) {
   if (table_bytes + warp_bytes > kMaxSmem)
     return fail(SPL_E_INVALID, "shared memory %zu B (tables) + %zu B (one warp) exceeds 227 KB", table_bytes, warp_bytes);
-  auto kern = spl::transform_kernel<NFFT, KIND, GRAD, WIN_T>;
-  // per (instantiation, device): opt in to the full 227 KB of dynamic shared memory
-  static thread_local bool configured[64] = {false};
-  static thread_local int sm_count[64] = {0};
+  int sms = 0;
+  int rc = device_sm_count(&sms);
+  if (rc) return rc;
+  int w = n_fft == 2048 ? spl::MaxWarps<2048>::value : spl::MaxWarps<1024>::value;
+  const int by_smem = (int)((kMaxSmem - table_bytes) / warp_bytes);
+  if (by_smem < w) w = by_smem;
+  const long long spread = (items + sms - 1) / sms;
+  if (spread < w) w = (int)(spread < 1 ? 1 : spread);
+  const long long need = (items + w - 1) / w;
+  *grid = (int)(need < sms ? need : sms);
+  *wpc = w;
+  return SPL_OK;
+}
+
+// per (kernel instantiation, device): opt in to the full 227 KB of dynamic shared memory.  `configured` must be a
+// static of the calling launch template, i.e. one flag array per kernel.
+template <typename K>
+int opt_in_smem(K kern, bool* configured) {
   int dev = 0;
   SPL_CUDA(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64) return fail(SPL_E_INVALID, "device ordinal %d out of range", dev);
   if (!configured[dev]) {
     SPL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
-    SPL_CUDA(cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev));
     configured[dev] = true;
   }
-  // One persistent CTA per SM.  Warps per CTA: as many as registers (launch bounds) and shared memory
-  // allow, but no more than needed to give every SM work; warps then stride over the chunks.
-  const long long chunks = (long long)p.B * p.n_chunks;
-  int wpc = spl::MaxWarps<NFFT>::value;
-  const int by_smem = (int)((kMaxSmem - table_bytes) / warp_bytes);
-  if (by_smem < wpc) wpc = by_smem;
-  const long long spread = (chunks + sm_count[dev] - 1) / sm_count[dev];
-  if (spread < wpc) wpc = (int)(spread < 1 ? 1 : spread);
-  const long long need = (chunks + wpc - 1) / wpc;
-  const unsigned grid = (unsigned)(need < sm_count[dev] ? need : sm_count[dev]);
-  const size_t smem = table_bytes + warp_bytes * wpc;
+  return SPL_OK;
+}
+
+template <int NFFT, int KIND, bool GRAD, int WIN_T>
+int spl_launch_transform(const spl::TransformParams& p, int grid, int wpc, size_t smem, void* stream) {
+  auto kern = spl::transform_kernel<NFFT, KIND, GRAD, WIN_T>;
+  static thread_local bool configured[64] = {false};
+  int rc = opt_in_smem(kern, configured);
+  if (rc) return rc;
+  kern<<<grid, wpc * 32, smem, static_cast<cudaStream_t>(stream)>>>(p);
+  SPL_CUDA(cudaGetLastError());
+  return SPL_OK;
+}
+
+template <int NFFT>
+int spl_launch_spec(const spl::SpecParams& p, int grid, int wpc, size_t smem, void* stream) {
+  auto kern = spl::spec_kernel<NFFT>;
+  static thread_local bool configured[64] = {false};
+  int rc = opt_in_smem(kern, configured);
+  if (rc) return rc;
   kern<<<grid, wpc * 32, smem, static_cast<cudaStream_t>(stream)>>>(p);
   SPL_CUDA(cudaGetLastError());
   return SPL_OK;

@@ -2,23 +2,22 @@
 // the CUDA backend (specloss.cu) and by the CPU SIMT emulator used in the test-suite
 // (tests/emu/specloss_emu.cpp).  The includer provides, before including this file:
 //   int fail(int code, const char* fmt, ...);
-//   template <int NFFT, int KIND, bool GRAD, int WIN_T> int spl_launch_transform(const spl::TransformParams&, int n_mels, void* stream);
+//   int spl_launch_shape(int n_fft, size_t table_bytes, size_t warp_bytes, long long items, int* grid, int* wpc);
+//       -- CTAs and warps per CTA of a transform launch over `items` warp work items (the reduction needs the
+//          same numbers: one row of partial sums per warp)
+//   template <int NFFT, int KIND, bool GRAD, int WIN_T> int spl_launch_transform(const spl::TransformParams&, int grid, int wpc, size_t smem, void* stream);
+//   template <int NFFT> int spl_launch_spec(const spl::SpecParams&, int grid, int wpc, size_t smem, void* stream);
 //   int spl_launch_reduce(const spl::ReduceParams&, void* stream);
 //   int spl_launch_finalize(const spl::FinalizeParams&, void* stream);
 //   int spl_launch_reduce_finalize(const spl::ReduceFinalizeParams&, void* stream);
 //   int spl_launch_combine(const spl::CombineParams&, void* stream);
 namespace {
 
+constexpr long long kMaxPartialRows = 1024 * 32;      // upper bound on grid * warps per CTA on any device
+
 bool supported_nfft(int n) { return n == 512 || n == 1024 || n == 2048; }
 
 int frames_in_flight(int n_fft) { return n_fft == 512 ? 2 : 1; }
-
-// overlap-add ring per warp; none when every chunk is a single frame (the frame is its own slot)
-int ring_entries(const spl_transform* t) {
-  const int fpw = frames_in_flight(t->n_fft);
-  if (fpw == 1 && t->frames_per_chunk == 1) return 0;
-  return t->win + (fpw - 1) * t->hop;
-}
 
 int check_transform(const spl_transform* t, int B, int T) {
   if (!t) return fail(SPL_E_INVALID, "null transform");
@@ -26,52 +25,69 @@ int check_transform(const spl_transform* t, int B, int T) {
   if (!supported_nfft(t->n_fft)) return fail(SPL_E_INVALID, "n_fft %d not in {512,1024,2048}", t->n_fft);
   if (t->win < 1 || t->win > t->n_fft) return fail(SPL_E_INVALID, "win %d must be in [1, n_fft=%d]", t->win, t->n_fft);
   if (t->hop < 1 || t->hop > t->win) return fail(SPL_E_INVALID, "hop %d must be in [1, win=%d]", t->hop, t->win);
-  if (t->frames_per_chunk < 1) return fail(SPL_E_INVALID, "frames_per_chunk %d < 1", t->frames_per_chunk);
   if (B < 1) return fail(SPL_E_INVALID, "batch %d < 1", B);
   if (T <= t->n_fft / 2) return fail(SPL_E_INVALID, "reflect padding needs T > n_fft/2 (T=%d, n_fft=%d)", T, t->n_fft);
+  if ((long long)B * (1 + T / t->hop) > 0x7fffffffLL) return fail(SPL_E_INVALID, "B * frames exceeds 2^31");
   if (t->kind == SPL_KIND_MEL && (t->n_mels < 2 || t->n_mels > 512))
     return fail(SPL_E_INVALID, "n_mels %d must be in [2, 512]", t->n_mels);
   return SPL_OK;
 }
 
+int warp_words(int n_fft, int kind, int n_mels) {
+  if (kind == SPL_KIND_STFT)
+    return n_fft == 512 ? spl::SmemLayout<512, spl::kKindStft>::words_per_warp(0)
+         : n_fft == 1024 ? spl::SmemLayout<1024, spl::kKindStft>::words_per_warp(0)
+                         : spl::SmemLayout<2048, spl::kKindStft>::words_per_warp(0);
+  return n_fft == 512 ? spl::SmemLayout<512, spl::kKindMel>::words_per_warp(n_mels)
+       : n_fft == 1024 ? spl::SmemLayout<1024, spl::kKindMel>::words_per_warp(n_mels)
+                       : spl::SmemLayout<2048, spl::kKindMel>::words_per_warp(n_mels);
+}
+
+long long warp_items(const spl_transform* t, int B, int T) {       // frames / frames in flight per warp
+  const int fpw = frames_in_flight(t->n_fft);
+  return ((long long)B * (1 + T / t->hop) + fpw - 1) / fpw;
+}
+
 void geometry(const spl_transform* t, int B, int T, spl_geometry* g) {
+  std::memset(g, 0, sizeof(*g));
   g->n_frames = 1 + T / t->hop;
   g->n_bins = t->n_fft / 2 + 1;
-  g->n_chunks = (g->n_frames + t->frames_per_chunk - 1) / t->frames_per_chunk;
-  g->span = (t->frames_per_chunk - 1) * t->hop + t->win;
   g->n_sums = t->kind == SPL_KIND_STFT ? 3 : 1;
-  g->partial_count = (int64_t)B * g->n_chunks * g->n_sums;
-  g->gchunk_bytes = (int64_t)B * g->n_chunks * g->span * (t->kind == SPL_KIND_STFT ? 8 : 4);
-  const int ring_n = ring_entries(t);
-  int words = 0;
-#define SPL_WORDS(N)                                                                                        \
-  words = t->kind == SPL_KIND_STFT ? spl::SmemLayout<N, spl::kKindStft, true>::words_per_warp(ring_n, 0)    \
-                                   : spl::SmemLayout<N, spl::kKindMel, true>::words_per_warp(ring_n, t->n_mels)
-  if (t->n_fft == 512) { SPL_WORDS(512); } else if (t->n_fft == 1024) { SPL_WORDS(1024); } else { SPL_WORDS(2048); }
-#undef SPL_WORDS
-  const int lanes = t->n_fft == 512 ? 16 : 32;
-  const spl::CtaTables ct = spl::cta_tables(t->n_fft, t->win, t->kind, lanes, t->mel_rounds, t->mel_entry_rows);
+  const long long items = warp_items(t, B, T);
+  g->partial_count = (int64_t)(items < kMaxPartialRows ? items : kMaxPartialRows) * g->n_sums;
+  g->gframe_bytes = (int64_t)B * g->n_frames * t->win * (t->kind == SPL_KIND_STFT ? 8 : 4);
+  const spl::CtaTables ct = spl::cta_tables(t->n_fft, t->win, t->kind, t->mel_rounds, t->mel_entry_rows);
   g->smem_table_bytes = (int64_t)ct.total * 4;
-  g->smem_warp_bytes = (int64_t)words * 4;
+  g->smem_warp_bytes = (int64_t)warp_words(t->n_fft, t->kind, t->n_mels) * 4;
+}
+
+// CTAs x warps of the launch of transform t over (B, T)
+int shape_of(const spl_transform* t, int B, int T, int* grid, int* wpc) {
+  spl_geometry g;
+  geometry(t, B, T, &g);
+  int rc = spl_launch_shape(t->n_fft, (size_t)g.smem_table_bytes, (size_t)g.smem_warp_bytes, warp_items(t, B, T), grid, wpc);
+  if (rc) return rc;
+  if ((long long)*grid * *wpc > kMaxPartialRows) return fail(SPL_E_INVALID, "launch of %d x %d warps exceeds the partial-sum rows", *grid, *wpc);
+  return SPL_OK;
 }
 
 template <int NFFT, int WIN_T>
-int launch_win(const spl::TransformParams& p, int kind, bool grad, int n_mels, void* s) {
+int launch_win(const spl::TransformParams& p, int kind, bool grad, int grid, int wpc, size_t smem, void* s) {
   if (kind == SPL_KIND_STFT)
-    return grad ? spl_launch_transform<NFFT, spl::kKindStft, true, WIN_T>(p, n_mels, s)
-                : spl_launch_transform<NFFT, spl::kKindStft, false, WIN_T>(p, n_mels, s);
-  return grad ? spl_launch_transform<NFFT, spl::kKindMel, true, WIN_T>(p, n_mels, s)
-              : spl_launch_transform<NFFT, spl::kKindMel, false, WIN_T>(p, n_mels, s);
+    return grad ? spl_launch_transform<NFFT, spl::kKindStft, true, WIN_T>(p, grid, wpc, smem, s)
+                : spl_launch_transform<NFFT, spl::kKindStft, false, WIN_T>(p, grid, wpc, smem, s);
+  return grad ? spl_launch_transform<NFFT, spl::kKindMel, true, WIN_T>(p, grid, wpc, smem, s)
+              : spl_launch_transform<NFFT, spl::kKindMel, false, WIN_T>(p, grid, wpc, smem, s);
 }
 
 // Window lengths of the shipped configurations get kernels with the window support known at compile
 // time (zero taps pruned); every other (n_fft, win) pair runs the generic kernel of that n_fft.
-int launch_any(const spl::TransformParams& p, int n_fft, int kind, bool grad, int n_mels, void* s) {
-  if (n_fft == 1024) return p.win == 600 ? launch_win<1024, 600>(p, kind, grad, n_mels, s) : launch_win<1024, 0>(p, kind, grad, n_mels, s);
-  if (n_fft == 512) return p.win == 240 ? launch_win<512, 240>(p, kind, grad, n_mels, s) : launch_win<512, 0>(p, kind, grad, n_mels, s);
-  if (p.win == 1200) return launch_win<2048, 1200>(p, kind, grad, n_mels, s);
-  if (p.win == 2048) return launch_win<2048, 2048>(p, kind, grad, n_mels, s);
-  return launch_win<2048, 0>(p, kind, grad, n_mels, s);
+int launch_any(const spl::TransformParams& p, int n_fft, int kind, bool grad, int grid, int wpc, size_t smem, void* s) {
+  if (n_fft == 1024) return p.win == 600 ? launch_win<1024, 600>(p, kind, grad, grid, wpc, smem, s) : launch_win<1024, 0>(p, kind, grad, grid, wpc, smem, s);
+  if (n_fft == 512) return p.win == 240 ? launch_win<512, 240>(p, kind, grad, grid, wpc, smem, s) : launch_win<512, 0>(p, kind, grad, grid, wpc, smem, s);
+  if (p.win == 1200) return launch_win<2048, 1200>(p, kind, grad, grid, wpc, smem, s);
+  if (p.win == 2048) return launch_win<2048, 2048>(p, kind, grad, grid, wpc, smem, s);
+  return launch_win<2048, 0>(p, kind, grad, grid, wpc, smem, s);
 }
 
 }  // namespace
@@ -113,32 +129,62 @@ int32_t spl_forward(const spl_transform* ts, int32_t n, const float* x, const fl
     int rc = check_transform(t, B, T);
     if (rc) return rc;
     if (!t->window || !t->twiddle || !t->partials) return fail(SPL_E_INVALID, "transform %d: null window/twiddle/partials", r);
-    if (frames_in_flight(t->n_fft) == 2 && (t->frames_per_chunk & 1))
-      return fail(SPL_E_INVALID, "transform %d: frames_per_chunk must be even for n_fft=512", r);
     if (t->kind == SPL_KIND_MEL && (!t->mel_tasks || !t->mel_entries || t->mel_rounds < 1 || t->mel_entry_rows < 1 || !t->bin_tab))
       return fail(SPL_E_INVALID, "transform %d: null mel table", r);
     spl_geometry g;
     geometry(t, B, T, &g);
+    int grid = 0, wpc = 0;
+    rc = shape_of(t, B, T, &grid, &wpc);
+    if (rc) return rc;
     spl::TransformParams p;
     std::memset(&p, 0, sizeof(p));
     p.x = x; p.y = y; p.B = B; p.T = T;
     p.hop = t->hop; p.win = t->win; p.left = (t->n_fft - t->win) / 2;
-    p.n_frames = g.n_frames; p.m = t->frames_per_chunk; p.n_chunks = g.n_chunks; p.span = g.span;
-    p.ring_n = ring_entries(t);
+    p.n_frames = g.n_frames;
     p.eps = t->eps; p.window = t->window; p.twiddle = reinterpret_cast<const float2*>(t->twiddle);
-    p.partials = t->partials; p.gchunks = t->gchunks;
+    p.partials = t->partials; p.gframes = t->gframes;
     p.n_mels = t->kind == SPL_KIND_MEL ? t->n_mels : 0;
     p.inv_ln_base = t->inv_ln_base;
     p.mel_tasks = t->mel_tasks; p.mel_entries = t->mel_entries;
     p.mel_rounds = t->kind == SPL_KIND_MEL ? t->mel_rounds : 0;
     p.mel_entry_rows = t->kind == SPL_KIND_MEL ? t->mel_entry_rows : 0;
     p.bin_tab = t->bin_tab;
-    const bool grad = t->gchunks != nullptr;
-    void* s = stream;
-    rc = launch_any(p, t->n_fft, t->kind, grad, p.n_mels, s);
+    const size_t smem = (size_t)g.smem_table_bytes + (size_t)g.smem_warp_bytes * wpc;
+    rc = launch_any(p, t->n_fft, t->kind, t->gframes != nullptr, grid, wpc, smem, stream);
     if (rc) return rc;
   }
   return SPL_OK;
+}
+
+int32_t spl_spectrogram(const float* x, int32_t B, int32_t T, int32_t n_fft, int32_t hop, int32_t win,
+                        const float* window, const float* twiddle, float eps, float* out, int32_t ld, void* stream) {
+  spl_transform t;
+  std::memset(&t, 0, sizeof(t));
+  t.kind = SPL_KIND_STFT; t.n_fft = n_fft; t.hop = hop; t.win = win;
+  if (!supported_nfft(n_fft)) return fail(SPL_E_INVALID, "n_fft %d not in {512,1024,2048}", n_fft);
+  if (win < 1 || win > n_fft) return fail(SPL_E_INVALID, "win %d must be in [1, n_fft=%d]", win, n_fft);
+  if (hop < 1) return fail(SPL_E_INVALID, "hop %d < 1", hop);
+  if (B < 1) return fail(SPL_E_INVALID, "batch %d < 1", B);
+  if (T <= n_fft / 2) return fail(SPL_E_INVALID, "reflect padding needs T > n_fft/2 (T=%d, n_fft=%d)", T, n_fft);
+  if (!x || !window || !twiddle || !out) return fail(SPL_E_INVALID, "spl_spectrogram: null pointer");
+  if (ld < n_fft / 2 + 1) return fail(SPL_E_INVALID, "ld %d < n_fft/2+1", ld);
+  const int n_frames = 1 + T / hop, n_pairs = (n_frames + 1) / 2;
+  if ((long long)B * n_frames > 0x7fffffffLL) return fail(SPL_E_INVALID, "B * frames exceeds 2^31");
+  const spl::CtaTables ct = spl::cta_tables(n_fft, win, spl::kKindStft, 0, 0);
+  const size_t table_bytes = (size_t)ct.total * 4, warp_bytes = (size_t)warp_words(n_fft, SPL_KIND_STFT, 0) * 4;
+  const int fpw = frames_in_flight(n_fft);
+  int grid = 0, wpc = 0;
+  int rc = spl_launch_shape(n_fft, table_bytes, warp_bytes, ((long long)B * n_pairs + fpw - 1) / fpw, &grid, &wpc);
+  if (rc) return rc;
+  spl::SpecParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.x = x; p.B = B; p.T = T; p.hop = hop; p.win = win; p.left = (n_fft - win) / 2; p.n_frames = n_frames;
+  p.n_pairs = n_pairs; p.eps = eps; p.window = window; p.twiddle = reinterpret_cast<const float2*>(twiddle);
+  p.out = out; p.ld = ld;
+  const size_t smem = table_bytes + warp_bytes * wpc;
+  if (n_fft == 512) return spl_launch_spec<512>(p, grid, wpc, smem, stream);
+  if (n_fft == 1024) return spl_launch_spec<1024>(p, grid, wpc, smem, stream);
+  return spl_launch_spec<2048>(p, grid, wpc, smem, stream);
 }
 
 static int build_reduce(const spl_transform* ts, int n, int B, int T, double* sums, spl::ReduceParams* rp) {
@@ -148,13 +194,15 @@ static int build_reduce(const spl_transform* ts, int n, int B, int T, double* su
     int rc = check_transform(ts + r, B, T);
     if (rc) return rc;
     if (!ts[r].partials) return fail(SPL_E_INVALID, "transform %d: null partials", r);
-    spl_geometry g;
-    geometry(ts + r, B, T, &g);
-    for (int j = 0; j < g.n_sums; ++j) {
+    int grid = 0, wpc = 0;
+    rc = shape_of(ts + r, B, T, &grid, &wpc);
+    if (rc) return rc;
+    const int n_sums = ts[r].kind == SPL_KIND_STFT ? 3 : 1;
+    for (int j = 0; j < n_sums; ++j) {
       if (k >= 16) return fail(SPL_E_INVALID, "too many sums");
       rp->base[k] = ts[r].partials + j;
-      rp->stride[k] = g.n_sums;
-      rp->count[k] = (int)((int64_t)B * g.n_chunks);
+      rp->stride[k] = n_sums;
+      rp->count[k] = grid * wpc;
       ++k;
     }
   }
@@ -221,13 +269,10 @@ int32_t spl_backward(const spl_transform* ts, int32_t n, int32_t B, int32_t T, c
   for (int r = 0; r < n; ++r) {
     int rc = check_transform(ts + r, B, T);
     if (rc) return rc;
-    if (!ts[r].gchunks) return fail(SPL_E_INVALID, "transform %d: forward ran without gradient workspace", r);
-    spl_geometry g;
-    geometry(ts + r, B, T, &g);
+    if (!ts[r].gframes) return fail(SPL_E_INVALID, "transform %d: forward ran without gradient workspace", r);
     spl::CombineEntry& e = cp.e[r];
-    e.chunks = ts[r].gchunks; e.kind = ts[r].kind; e.half = ts[r].n_fft / 2; e.hop = ts[r].hop; e.win = ts[r].win;
-    e.left = (ts[r].n_fft - ts[r].win) / 2; e.m = ts[r].frames_per_chunk; e.n_chunks = g.n_chunks;
-    e.span = g.span; e.n_frames = g.n_frames;
+    e.frames = ts[r].gframes; e.kind = ts[r].kind; e.half = ts[r].n_fft / 2; e.hop = ts[r].hop; e.win = ts[r].win;
+    e.left = (ts[r].n_fft - ts[r].win) / 2; e.n_frames = 1 + T / ts[r].hop;
   }
   cp.coefs = coefs; cp.g_sc = g_sc; cp.g_mag = g_mag; cp.g_mel = g_mel; cp.dx = dx; cp.B = B; cp.T = T;
   return spl_launch_combine(cp, stream);

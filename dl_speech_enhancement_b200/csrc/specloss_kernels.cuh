@@ -49,14 +49,27 @@ constexpr int kKindMel = 1;
 
 // ---------------------------------------------------------------------------------------------
 // FFT geometry: N = L * R.  A group of L lanes owns one frame; every lane holds R complex points.
-//   pass A: in-lane R-point DFT over n2   (n = n1 + L*n2, n1 = lane in group)
-//   twiddle W_N^(n1*k2), transpose through shared memory
-//   pass B: in-lane L-point DFTs over n1  (R/L rows k2 per lane), output bin k = k2 + R*k1
+//   forward : in-lane R-point DFTs over n2 (n = n1 + L*n2, n1 = lane), twiddle W_N^(n1*k2), transpose through
+//             shared memory, in-lane L-point DFTs over n1 -> bin k = k2 + R*k1, row k2 owned by lane k2 % L,
+//             LEFT IN REGISTERS;
+//   inverse : the transposed algorithm on component-swapped data: L-point DFTs over k1 (registers), the same
+//             twiddle, transpose, R-point DFTs over k2 -> sample n = n1 + L*n2 back in lane n1.
+// The frame slot in shared memory is R rows of L (+1 pad) float2; its only uses are the two transposes and the
+// exchange of mirror halves (columns >= L/2 of every row) between the lanes that own rows k2 and R - k2.
 // ---------------------------------------------------------------------------------------------
 template <int NFFT> struct FftGeom;
 template <> struct FftGeom<512>  { static constexpr int L = 16, R = 32; };
 template <> struct FftGeom<1024> { static constexpr int L = 32, R = 32; };
 template <> struct FftGeom<2048> { static constexpr int L = 32, R = 64; };
+
+template <int NFFT> struct Geo {
+  static constexpr int L = FftGeom<NFFT>::L, R = FftGeom<NFFT>::R;
+  static constexpr int PITCH = L + 1;       // float2 per row: odd, so row-wise and column-wise accesses are conflict-free
+  static constexpr int RPL = R / L;         // rows per lane in the L-point passes
+  static constexpr int FPW = 32 / L;        // frames in flight per warp
+  static constexpr int HL = L / 2;          // columns kept in registers per row (bins below N/2)
+  static constexpr int SLOT_F2 = R * PITCH; // float2 per frame slot
+};
 
 template <int P> struct Dft;
 template <> struct Dft<16> { static SPL_DEVICE void run(float2 (&v)[16]) { fft16(v); } };
@@ -70,15 +83,11 @@ struct TransformParams {
   int B, T;
   int hop, win, left;    // left = (N - win) / 2 : first non-zero tap of the centred window
   int n_frames;          // 1 + T / hop
-  int m;                 // frames per chunk (one warp walks one chunk)
-  int n_chunks;          // chunks per utterance
-  int span;              // (m - 1) * hop + win : gradient slot length per chunk
-  int ring_n;            // ring buffer entries per warp: win + (32/L - 1) * hop
   float eps;
   const float* window;   // win taps
   const float2* twiddle; // [R][L] : W_N^(n1*k2) at [k2 * L + n1]
-  double* partials;      // [B * n_chunks][n_sums]
-  void* gchunks;         // [B * n_chunks][span] float2 (stft: u=sc part, v=log-mag part) | float (mel)
+  double* partials;      // [grid * warps per CTA][n_sums] : one row per warp
+  void* gframes;         // [B * n_frames][win] float2 (stft: u = sc part, v = log-mag part) | float (mel)
   // mel only
   int n_mels;
   float inv_ln_base;     // 1 / ln(log_base)  (1 for natural log)
@@ -95,24 +104,25 @@ SPL_DEVICE float2 cmul(float2 a, float2 w) {
   return __ffma2_rn(make_float2(-a.y, a.x), make_float2(w.y, w.y), __fmul2_rn(a, make_float2(w.x, w.x)));
 }
 
-SPL_DEVICE float warp_sum(float v) {
+SPL_DEVICE double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
 
-// Constant tables of a transform, staged once per CTA in shared memory (one persistent CTA per SM):
-// at 200+ KB of shared memory per SM the L1 keeps only ~28 KB, and twiddles + window + mel tables
-// (30-64 KB) would otherwise be re-fetched from L2 at every frame (r1c profile: long-scoreboard 3.7/issue).
+// Constant tables of a transform, staged once per CTA in shared memory (one persistent CTA per SM): at 200+ KB
+// of shared memory per SM the L1 keeps only ~28 KB, and twiddles + window + mel tables (30-64 KB) would
+// otherwise be re-fetched from L2 at every frame.  The twiddle rows are padded to PITCH so that the forward
+// pass (lane = n1, row fixed) and the inverse pass (lane = row, n1 fixed) both read without bank conflicts.
 struct CtaTables {
   int tw, win, tasks, entries, bintab, total;     // word offsets
 };
 SPL_DEVICE int align4(int n) { return (n + 3) & ~3; }
-static __host__ __device__ inline CtaTables cta_tables(int n_fft, int win, int kind, int lanes, int mel_rounds,
-                                                       int mel_entry_rows) {
+static __host__ __device__ inline CtaTables cta_tables(int n_fft, int win, int kind, int mel_rounds, int mel_entry_rows) {
+  const int lanes = n_fft == 512 ? 16 : 32, rows = n_fft / lanes;
   CtaTables t;
   int o = 0;
-  t.tw = o;      o += 2 * n_fft;
+  t.tw = o;      o += (2 * rows * (lanes + 1) + 3) & ~3;
   t.win = o;     o += (win + 3) & ~3;
   t.tasks = o;   o += kind == kKindMel ? 4 * mel_rounds * lanes : 0;
   t.entries = o; o += kind == kKindMel ? ((2 * mel_entry_rows * lanes + 3) & ~3) : 0;
@@ -121,60 +131,17 @@ static __host__ __device__ inline CtaTables cta_tables(int n_fft, int win, int k
   return t;
 }
 
-// shared memory carve-up per warp (in 4-byte words); the host side uses the same function
-template <int NFFT, int KIND, bool GRAD>
+// shared memory per warp (in 4-byte words); the host side uses the same function
+template <int NFFT, int KIND>
 struct SmemLayout {
-  using G = FftGeom<NFFT>;
-  static constexpr int FPW = 32 / G::L;                      // frames in flight per warp
-  static constexpr int BUF_F2 = G::R * (G::L + 1);           // float2 per frame slot: R rows of L (+1 pad)
-  static __host__ __device__ int words_per_warp(int ring_n, int n_mels) {
-    int w = FPW * BUF_F2 * 2;
-    if (GRAD) w += (KIND == kKindStft ? 2 : 1) * ((ring_n + 3) & ~3);
-    if (KIND == kKindMel) w += FPW * 2 * ((n_mels + 3) & ~3);
+  using G = Geo<NFFT>;
+  static __host__ __device__ int words_per_warp(int n_mels) {
+    int w = G::FPW * G::SLOT_F2 * 2;
+    if (KIND == kKindMel) w += G::FPW * 2 * ((n_mels + 3) & ~3);
     return (w + 3) & ~3;
   }
 };
 
-// Spectrum / time-sample layout inside a frame slot: element k = k2 + R*k1 lives in row k2, column k1.
-// Pass B works on whole rows in place (one owner lane per row, no hazards); lanes that walk
-// k = l + L*i (or N - k) touch a different bank each: the row pitch L+1 is odd in float2 units.
-template <int NFFT>
-SPL_DEVICE int pos(int k) {
-  using G = FftGeom<NFFT>;
-  return (k & (G::R - 1)) * (G::L + 1) + (k / G::R);
-}
-
-// ---------------------------------------------------------------------------------------------
-// The one FFT core of a kernel.  In: this lane's R points of the sequence, element n = l + L*n2 in
-// (re[n2], im[n2]).  Out: the forward DFT in the frame slot, element k at buf[pos(k)].
-// The inverse (un-normalised, e^{+i..}) is the same code on swapped components: feed (im, re),
-// read back (.y, .x).
-// ---------------------------------------------------------------------------------------------
-template <int NFFT>
-SPL_DEVICE void fft_core(float2 (&v)[FftGeom<NFFT>::R], float2* buf, const float2* tw, int l) {
-  using G = FftGeom<NFFT>;
-  constexpr int L = G::L, R = G::R, RPL = R / L;
-  // [region: fft_core pass A (in-lane R-point DFT)]
-  Dft<R>::run(v);
-  // [region: fft_core twiddle + transposed store]
-#pragma unroll
-  for (int k2 = 0; k2 < R; ++k2) buf[k2 * (L + 1) + l] = k2 > 0 ? cmul(v[k2], tw[k2 * L + l]) : v[0];
-  __syncwarp();
-  // [region: fft_core pass B (row load, L-point DFT, row store)]
-#pragma unroll 1
-  for (int j = 0; j < RPL; ++j) {
-    float2* row = buf + (j * L + l) * (L + 1);
-    float2 b[L];
-#pragma unroll
-    for (int n1 = 0; n1 < L; ++n1) b[n1] = row[n1];
-    Dft<L>::run(b);
-#pragma unroll
-    for (int k1 = 0; k1 < L; ++k1) row[k1] = b[k1];
-  }
-  __syncwarp();
-}
-
-// [region: misc helpers]
 // reflect index without edge repeat (torch.stft center=True, pad_mode="reflect")
 SPL_DEVICE int reflect(int s, int T) {
   s = s < 0 ? -s : s;
@@ -189,30 +156,179 @@ SPL_DEVICE float bits_to_float(int b) {
 #endif
 }
 
+// CTA prologue: every thread copies its share of the constant tables into shared memory.
+template <int NFFT>
+SPL_DEVICE void cta_load_fft_tables(const CtaTables& ct, const float2* twiddle, const float* window, int win,
+                                    float* smem, int tid, int nthreads) {
+  using G = Geo<NFFT>;
+  float2* tw = reinterpret_cast<float2*>(smem + ct.tw);
+  for (int i = tid; i < NFFT; i += nthreads) tw[(i / G::L) * G::PITCH + (i % G::L)] = __ldg(&twiddle[i]);
+  for (int i = tid; i < win; i += nthreads) smem[ct.win + i] = __ldg(&window[i]);
+}
+
+template <int NFFT, int KIND>
+SPL_DEVICE void cta_load_tables(const TransformParams& p, float* smem, int tid, int nthreads) {
+  constexpr int L = Geo<NFFT>::L;
+  const CtaTables ct = cta_tables(NFFT, p.win, KIND, p.mel_rounds, p.mel_entry_rows);
+  cta_load_fft_tables<NFFT>(ct, p.twiddle, p.window, p.win, smem, tid, nthreads);
+  if (KIND == kKindMel) {
+    int* ism = reinterpret_cast<int*>(smem);
+    const int* a = reinterpret_cast<const int*>(p.mel_tasks);
+    const int* b = reinterpret_cast<const int*>(p.mel_entries);
+    const int* c = reinterpret_cast<const int*>(p.bin_tab);
+    for (int i = tid; i < 4 * p.mel_rounds * L; i += nthreads) ism[ct.tasks + i] = __ldg(&a[i]);
+    for (int i = tid; i < 2 * p.mel_entry_rows * L; i += nthreads) ism[ct.entries + i] = __ldg(&b[i]);
+    for (int i = tid; i < 4 * (NFFT / 2 + 1); i += nthreads) ism[ct.bintab + i] = __ldg(&c[i]);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
-// The transform kernel body.  One warp walks chunks of `m` consecutive frames of one utterance
-// (grid-stride over chunks).  WIN_T > 0: window length known at compile time (shipped configs),
-// which prunes the zero taps out of the load, the first butterflies and the overlap-add.
+// FFT passes
 // ---------------------------------------------------------------------------------------------
-// One mirror pair (k, N-k) of the packed spectrum Z = FFT(x + i y) of an STFT-loss frame:
-//   2X[k] = Z[k] + conj Z[N-k],  2Y[k] = -i (Z[k] - conj Z[N-k]);
-// loss terms from the doubled spectra (powers x4, magnitudes x2; the chunk's sums are rescaled once), and --
-// GRAD -- the un-scaled gradient spectra written back in place:
+// [region: fwd pass A]
+// Forward, first half: this lane's R points (element n = l + L*n2 in v[n2]) -> R-point DFT, twiddle, column l of
+// the slot.  Ends with the warp barrier that makes the rows readable.
+template <int NFFT>
+SPL_DEVICE void fwd_pass_a(float2 (&v)[Geo<NFFT>::R], float2* S, const float2* tw, int l) {
+  using G = Geo<NFFT>;
+  Dft<G::R>::run(v);
+#pragma unroll
+  for (int k2 = 0; k2 < G::R; ++k2) S[k2 * G::PITCH + l] = k2 > 0 ? cmul(v[k2], tw[k2 * G::PITCH + l]) : v[0];
+  __syncwarp();
+}
+
+// [region: fwd pass B]
+// Forward, second half, for the rows l + L*j of this lane: L-point DFT of the row.  Columns < L/2 (bins below
+// N/2) stay in registers (A); columns >= L/2 go back to the row in place, where the lane owning the mirror row
+// R - row picks them up.  Ends with the warp barrier that publishes them.
+template <int NFFT>
+SPL_DEVICE void fwd_pass_b(float2 (&A)[Geo<NFFT>::RPL][Geo<NFFT>::HL], float2* S, int l) {
+  using G = Geo<NFFT>;
+#pragma unroll
+  for (int j = 0; j < G::RPL; ++j) {
+    float2* row = S + (l + G::L * j) * G::PITCH;
+    float2 b[G::L];
+#pragma unroll
+    for (int n1 = 0; n1 < G::L; ++n1) b[n1] = row[n1];
+    Dft<G::L>::run(b);
+#pragma unroll
+    for (int k1 = 0; k1 < G::HL; ++k1) A[j][k1] = b[k1];
+#pragma unroll
+    for (int k1 = G::HL; k1 < G::L; ++k1) row[k1] = b[k1];
+  }
+  __syncwarp();
+}
+
+// pointer to the mirror of column 0 of `row`: the mirror of (row, k1) is pb[-k1].  Row 0 mirrors into itself
+// ((0, k1) <-> (0, L - k1)); its column 0 (bin 0) has no partner: pb[0] is then the pad word of row 0.
+template <int NFFT>
+SPL_DEVICE float2* mirror_ptr(float2* S, int row) {
+  using G = Geo<NFFT>;
+  return row == 0 ? S + G::L : S + ((G::R - row) & (G::R - 1)) * G::PITCH + (G::L - 1);
+}
+
+// [region: inv pass B]
+// Inverse, first half: gradient spectrum rows (columns < L/2 in A, columns >= L/2 in the slot) -> swapped
+// components -> L-point DFT -> twiddle -> back to the row.  Ends with a warp barrier.
+template <int NFFT>
+SPL_DEVICE void inv_pass_b(float2 (&A)[Geo<NFFT>::RPL][Geo<NFFT>::HL], float2* S, const float2* tw, int l) {
+  using G = Geo<NFFT>;
+#pragma unroll
+  for (int j = 0; j < G::RPL; ++j) {
+    const int r = l + G::L * j;
+    float2* row = S + r * G::PITCH;
+    const float2* twr = tw + r * G::PITCH;
+    float2 b[G::L];
+#pragma unroll
+    for (int k1 = 0; k1 < G::HL; ++k1) b[k1] = make_float2(A[j][k1].y, A[j][k1].x);
+#pragma unroll
+    for (int k1 = G::HL; k1 < G::L; ++k1) { const float2 h = row[k1]; b[k1] = make_float2(h.y, h.x); }
+    Dft<G::L>::run(b);
+    row[0] = b[0];
+#pragma unroll
+    for (int n1 = 1; n1 < G::L; ++n1) row[n1] = cmul(b[n1], twr[n1]);
+  }
+  __syncwarp();
+}
+
+// [region: inv pass A]
+// Inverse, second half: column l of the slot -> R-point DFT.  v[n2] then holds sample n = l + L*n2 of the two real
+// sequences with swapped components: (.y, .x) = (Re, Im) of the un-normalised inverse transform.
+template <int NFFT>
+SPL_DEVICE void inv_pass_a(float2 (&v)[Geo<NFFT>::R], const float2* S, int l) {
+  using G = Geo<NFFT>;
+#pragma unroll
+  for (int m2 = 0; m2 < G::R; ++m2) v[m2] = S[m2 * G::PITCH + l];
+  Dft<G::R>::run(v);
+}
+
+// [region: tap load]
+// Taps of frame t of utterance rows xb / yb: reflect-pad, window, pack z = x*w + i*y*w into v[n2] (element
+// n = l + L*n2).  Returns whether every tap of this lane has x*w == y*w bit for bit.
+template <int NFFT, int WIN_T>
+SPL_DEVICE bool load_taps(float2 (&v)[Geo<NFFT>::R], const float* __restrict__ xb, const float* __restrict__ yb, int T,
+                          int s0, int win, int left, const float* wtab, int l, bool active) {
+  using G = Geo<NFFT>;
+  constexpr int L = G::L, R = G::R;
+  const bool interior = (s0 + left >= 0) && (s0 + left + win <= T);
+  bool same = true;
+  if (active && interior) {
+    // fast path: no reflection; every address is a compile-time offset from three pointers
+    const float* __restrict__ xp = xb + s0 + l;
+    const float* __restrict__ yp = yb + s0 + l;
+    const float* wp = wtab + (l - left);
+#pragma unroll
+    for (int n2 = 0; n2 < R; ++n2) {
+      const int lo = L * n2 - left;                        // tap index of lane 0
+      if (WIN_T > 0 && (lo + L - 1 < 0 || lo >= WIN_T)) { v[n2] = make_float2(0.f, 0.f); continue; }
+      const bool all_lanes = WIN_T > 0 && lo >= 0 && lo + L - 1 < WIN_T;
+      float2 xy = make_float2(0.f, 0.f);
+      if (all_lanes || (lo + l >= 0 && lo + l < win)) {
+        const float w = wp[L * n2];
+        xy = __fmul2_rn(make_float2(__ldg(xp + L * n2), __ldg(yp + L * n2)), make_float2(w, w));
+      }
+      same = same && (xy.x == xy.y);
+      v[n2] = xy;
+    }
+  } else {
+#pragma unroll
+    for (int n2 = 0; n2 < R; ++n2) {
+      const int lo = L * n2 - left;
+      if (WIN_T > 0 && (lo + L - 1 < 0 || lo >= WIN_T)) { v[n2] = make_float2(0.f, 0.f); continue; }
+      const int tap = lo + l;
+      float xv = 0.f, yv = 0.f;
+      if (active && tap >= 0 && tap < win) {
+        const int sidx = reflect(s0 + L * n2 + l, T);
+        const float w = wtab[tap];
+        xv = __ldg(&xb[sidx]) * w;
+        yv = __ldg(&yb[sidx]) * w;
+      }
+      same = same && (xv == yv);
+      v[n2] = make_float2(xv, yv);
+    }
+  }
+  return same;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Epilogues on mirror pairs (k, N-k) of the packed spectrum Z = FFT(x + i y):
+//   2X[k] = Z[k] + conj Z[N-k],  2Y[k] = -i (Z[k] - conj Z[N-k]).
+// ---------------------------------------------------------------------------------------------
+// [region: stft epilogue]
+// STFT loss terms from the doubled spectra (powers x4, magnitudes x2; the sums are rescaled once at the end), and --
+// GRAD -- the un-scaled gradient spectra:
 //   H[k] = w/2 (alpha + i beta) (2X),  H[N-k] = w/2 (alpha + i beta) conj(2X),  w = 1/2 (1 when k mirrors itself)
 //   alpha = gate (Ax - Ay)/Ax  (spectral convergence),  beta = gate sign(Ax - Ay)/Ax^2  (log magnitude).
 // EQ: prediction and target frames are bit-identical, Y := X, every difference term is exactly zero.
 template <bool GRAD, bool EQ>
-SPL_DEVICE void stft_pair(float2* qa, float2* qb, bool self, float eps4, float& s1, float& s2, float& s3) {
-  const float2 a = *qa, bm = *qb;
+SPL_DEVICE void stft_pair(float2 a, float2 bm, bool self, float eps4, float& s1, float& s2, float& s3, float2& ha,
+                          float2& hb) {
   const float2 x2 = __fadd2_rn(a, make_float2(bm.x, -bm.y));
   const float px = fmaf(x2.x, x2.x, x2.y * x2.y);
   const float pxc = fmaxf(px, eps4);
   if (EQ) {
     s2 += pxc;
-    if (GRAD) {
-      *qa = make_float2(0.f, 0.f);
-      if (!self) *qb = make_float2(0.f, 0.f);
-    }
+    ha = hb = make_float2(0.f, 0.f);
     return;
   }
   const float2 y2 = __fadd2_rn(make_float2(a.y, -a.x), make_float2(bm.y, bm.x));
@@ -231,356 +347,262 @@ SPL_DEVICE void stft_pair(float2* qa, float2* qb, bool self, float eps4, float& 
     const float gr = -wq * d * rxg;
     const float gi = 4.f * wq * sgn * rx * rxg;
     const float2 g2 = make_float2(gi, gi), r2 = make_float2(gr, gr);
-    *qa = __ffma2_rn(make_float2(-x2.y, x2.x), g2, __fmul2_rn(x2, r2));
-    if (!self) *qb = __ffma2_rn(make_float2(x2.y, x2.x), g2, __fmul2_rn(make_float2(x2.x, -x2.y), r2));
+    ha = __ffma2_rn(make_float2(-x2.y, x2.x), g2, __fmul2_rn(x2, r2));
+    hb = __ffma2_rn(make_float2(x2.y, x2.x), g2, __fmul2_rn(make_float2(x2.x, -x2.y), r2));
   }
 }
 
-// all pairs of one lane: rows l + L*j, columns 0 .. L/2-1 (column 0 of row 0 mirrors itself)
+// all pairs of one lane.  In: A = columns < L/2 of this lane's rows (registers), mirror halves in the slot.
+// Out (GRAD): H in A and in the mirror halves of the slot.
 template <int NFFT, bool GRAD, bool EQ>
-SPL_DEVICE void stft_epilogue(float2* buf, int l, float eps4, float& s1, float& s2, float& s3) {
-  using G = FftGeom<NFFT>;
-  constexpr int L = G::L, R = G::R;
+SPL_DEVICE void stft_epilogue(float2 (&A)[Geo<NFFT>::RPL][Geo<NFFT>::HL], float2* S, int l, float eps4, float& s1,
+                              float& s2, float& s3) {
+  using G = Geo<NFFT>;
 #pragma unroll
-  for (int j = 0; j < R / L; ++j) {
-    const int row = l + L * j;
-    float2* pa = buf + row * (L + 1);
-    float2* pb = (row == 0) ? buf + L : buf + (R - row) * (L + 1) + (L - 1);      // mirror of column c is pb[-c]
-    stft_pair<GRAD, EQ>(pa, row == 0 ? pa : pb, row == 0, eps4, s1, s2, s3);
-#pragma unroll (EQ ? 1 : (L == 32 ? 5 : 7))
-    for (int c = 1; c < L / 2; ++c) stft_pair<GRAD, EQ>(pa + c, pb - c, false, eps4, s1, s2, s3);
+  for (int j = 0; j < G::RPL; ++j) {
+    const int row = l + G::L * j;
+    float2* pb = mirror_ptr<NFFT>(S, row);
+#pragma unroll
+    for (int k1 = 0; k1 < G::HL; ++k1) {
+      const float2 a = A[j][k1];
+      float2 bm = pb[-k1];
+      bool self = false;
+      if (j == 0 && k1 == 0) {                       // bin 0 (row 0) mirrors itself
+        self = row == 0;
+        bm = self ? a : bm;
+      }
+      float2 ha, hb;
+      stft_pair<GRAD, EQ>(a, bm, self, eps4, s1, s2, s3, ha, hb);
+      if (GRAD) { A[j][k1] = ha; pb[-k1] = hb; }
+    }
   }
-  if (l == 0) stft_pair<GRAD, EQ>(buf + L / 2, buf + L / 2, true, eps4, s1, s2, s3);   // bin N/2
+  if (l == 0) {                                      // bin N/2 = (row 0, column L/2) mirrors itself
+    const float2 a = S[G::HL];
+    float2 ha, hb;
+    stft_pair<GRAD, EQ>(a, a, true, eps4, s1, s2, s3, ha, hb);
+    if (GRAD) S[G::HL] = ha;
+  }
 }
 
-// mel, pass 1 on one mirror pair: keep 2X[k] in the bin's own slot, park (Ax, Ay) in `amp_slot`.
+// [region: mel epilogue]
+// mel, pass 1 on one mirror pair: 2X[k] and the amplitudes (Ax, Ay) = sqrt(max(|.|^2, eps))
 template <bool EQ>
-SPL_DEVICE void mel_pair_amp(float2* qa, float2* qb, float2* x_slot, float2* amp_slot, float eps4) {
-  const float2 a = *qa, bm = *qb;
-  const float2 x2 = __fadd2_rn(a, make_float2(bm.x, -bm.y));
+SPL_DEVICE void mel_pair_amp(float2 a, float2 bm, float eps4, float2& x2, float2& amp) {
+  x2 = __fadd2_rn(a, make_float2(bm.x, -bm.y));
   const float2 y2 = EQ ? x2 : __fadd2_rn(make_float2(a.y, -a.x), make_float2(bm.y, bm.x));
   const float pxc = fmaxf(fmaf(x2.x, x2.x, x2.y * x2.y), eps4);
   const float pyc = EQ ? pxc : fmaxf(fmaf(y2.x, y2.x, y2.y * y2.y), eps4);
-  const float ax = 0.5f * pxc * spl_fast_rsqrt(pxc);                       // sqrt(max(|X|^2, eps))
+  const float ax = 0.5f * pxc * spl_fast_rsqrt(pxc);
   const float ay = EQ ? ax : 0.5f * pyc * spl_fast_rsqrt(pyc);
-  *x_slot = x2;
-  *amp_slot = make_float2(ax, ay);
+  amp = make_float2(ax, ay);
 }
 
-// mel, pass 3 on one mirror pair: gA[k] = gM[m0] W[k,m0] + gM[m0+1] W[k,m0+1];  H[k] = w gA gate / Ax * X
-SPL_DEVICE void mel_pair_grad(float2* qa, float2* qb, const float2* x_slot, bool self, int4 bt, const float2* msum,
-                              float eps4, bool active) {
-  const float2 x2 = *x_slot;
+// mel, pass 3 on one bin: gA[k] = gM[m0] W[k,m0] + gM[m0+1] W[k,m0+1];  H[k] = w gA gate / Ax * X
+SPL_DEVICE float2 mel_bin_grad(float2 x2, bool self, int4 bt, const float2* msum, float eps4, bool active) {
   const float ga = fmaf(msum[bt.x].x, bits_to_float(bt.y), msum[bt.x + 1].x * bits_to_float(bt.z));
   const float px = fmaf(x2.x, x2.x, x2.y * x2.y);                          // 4 |X|^2
   // w gA / Ax * X = w gA * 2 rsqrt(px) * (2X) / 2
   const float g = (active && px >= eps4) ? (self ? 1.f : 0.5f) * ga * spl_fast_rsqrt(px) : 0.f;
-  const float2 hk = __fmul2_rn(x2, make_float2(g, g));
-  *qa = hk;
-  if (!self) *qb = make_float2(hk.x, -hk.y);
+  return __fmul2_rn(x2, make_float2(g, g));
 }
 
-// CTA prologue: every thread copies its share of the constant tables into shared memory.
-template <int NFFT, int KIND>
-SPL_DEVICE void cta_load_tables(const TransformParams& p, float* smem, int tid, int nthreads) {
-  constexpr int L = FftGeom<NFFT>::L;
-  const CtaTables ct = cta_tables(NFFT, p.win, KIND, L, p.mel_rounds, p.mel_entry_rows);
-  const float* tw = reinterpret_cast<const float*>(p.twiddle);
-  for (int i = tid; i < 2 * NFFT; i += nthreads) smem[ct.tw + i] = __ldg(&tw[i]);
-  for (int i = tid; i < p.win; i += nthreads) smem[ct.win + i] = __ldg(&p.window[i]);
-  if (KIND == kKindMel) {
-    int* ism = reinterpret_cast<int*>(smem);
-    const int* a = reinterpret_cast<const int*>(p.mel_tasks);
-    const int* b = reinterpret_cast<const int*>(p.mel_entries);
-    const int* c = reinterpret_cast<const int*>(p.bin_tab);
-    for (int i = tid; i < 4 * p.mel_rounds * L; i += nthreads) ism[ct.tasks + i] = __ldg(&a[i]);
-    for (int i = tid; i < 2 * p.mel_entry_rows * L; i += nthreads) ism[ct.entries + i] = __ldg(&b[i]);
-    for (int i = tid; i < 4 * (NFFT / 2 + 1); i += nthreads) ism[ct.bintab + i] = __ldg(&c[i]);
+// mel epilogue of one frame: amplitudes -> banded projection -> log-mel L1 -> (GRAD) gradient spectrum.
+// In: A = Z columns < L/2 (registers), mirror halves in the slot.  Out (GRAD): H in A / mirror halves.
+// The amplitudes of bin k <= N/2 are parked at the bin's own slot position (columns <= L/2 are free: they live in A).
+template <int NFFT, bool GRAD>
+SPL_DEVICE void mel_epilogue(float2 (&A)[Geo<NFFT>::RPL][Geo<NFFT>::HL], float2* S, float2* msum, int l, bool frame_equal,
+                             bool active, const TransformParams& p, const int4* mel_tasks, const int2* mel_entries,
+                             const int4* bin_tab, float& s1) {
+  using G = Geo<NFFT>;
+  constexpr int L = G::L, R = G::R;
+  const float eps4 = 4.f * p.eps;
+  float2 xh = make_float2(0.f, 0.f);                   // 2X[N/2], lane 0
+  // pass 1
+#pragma unroll
+  for (int j = 0; j < G::RPL; ++j) {
+    const int row = l + L * j;
+    const float2* pb = mirror_ptr<NFFT>(S, row);
+    float2* arow = S + row * G::PITCH;
+#pragma unroll
+    for (int k1 = 0; k1 < G::HL; ++k1) {
+      const float2 a = A[j][k1];
+      float2 bm = pb[-k1];
+      if (j == 0 && k1 == 0) bm = (row == 0) ? a : bm;
+      float2 x2, amp;
+      if (frame_equal) mel_pair_amp<true>(a, bm, eps4, x2, amp);
+      else             mel_pair_amp<false>(a, bm, eps4, x2, amp);
+      A[j][k1] = x2;
+      arow[k1] = amp;
+    }
+  }
+  if (l == 0) {
+    const float2 a = S[G::HL];
+    float2 amp;
+    if (frame_equal) mel_pair_amp<true>(a, a, eps4, xh, amp);
+    else             mel_pair_amp<false>(a, a, eps4, xh, amp);
+    S[G::HL] = amp;
+  }
+  __syncwarp();
+  // pass 2: balanced projection.  Every mel row is summed by a group of 1..L lanes walking a host-built table
+  // of (amplitude slot, weight) entries, then reduced with shuffles.
+  for (int r = 0; r < p.mel_rounds; ++r) {
+    const int4 tk = mel_tasks[r * L + l];
+    const int row = tk.x & 0xfff, grp = (tk.x >> 12) & 0xff, iters = tk.x >> 20;
+    const int2* en = mel_entries + tk.y * L + l;
+    float mx = 0.f, my = 0.f;
+#pragma unroll 4
+    for (int s = 0; s < iters; ++s) {
+      const int2 e = en[s * L];
+      const float2 amp = S[e.x];
+      const float w = bits_to_float(e.y);
+      mx = fmaf(amp.x, w, mx);
+      my = fmaf(amp.y, w, my);
+    }
+#pragma unroll
+    for (int o = 1; o < L; o <<= 1) {
+      const float tx = __shfl_xor_sync(0xffffffffu, mx, o), ty = __shfl_xor_sync(0xffffffffu, my, o);
+      if (o < grp) { mx += tx; my += ty; }
+    }
+    if (row != 0xfff && (l & (grp - 1)) == 0) msum[row] = make_float2(mx, my);
+  }
+  __syncwarp();
+  for (int row = l; row < p.n_mels; row += L) {
+    const float2 mm = msum[row];
+    const float mxc = fmaxf(mm.x, p.eps), myc = fmaxf(mm.y, p.eps);
+    const float dl = (mxc == myc) ? 0.f : (logf(mxc) - logf(myc)) * p.inv_ln_base;
+    if (active) s1 += fabsf(dl);
+    if (GRAD) {
+      const float sgn = (dl > 0.f) ? 1.f : ((dl < 0.f) ? -1.f : 0.f);
+      msum[row].x = (mm.x >= p.eps) ? sgn * p.inv_ln_base / mxc : 0.f;     // gM[row]
+    }
+  }
+  __syncwarp();
+  if (GRAD) {
+    // pass 3: gA[k] = sum_m gM[m] W[k,m] (<= 2 adjacent rows), H[k] = w gA gate / Ax * X, H[N-k] = conj H[k]
+#pragma unroll
+    for (int j = 0; j < G::RPL; ++j) {
+      const int row = l + L * j;
+      float2* pb = mirror_ptr<NFFT>(S, row);
+#pragma unroll
+      for (int k1 = 0; k1 < G::HL; ++k1) {
+        const bool self = (j == 0 && k1 == 0) && row == 0;
+        const float2 hk = mel_bin_grad(A[j][k1], self, bin_tab[row + R * k1], msum, eps4, active);
+        A[j][k1] = hk;
+        pb[-k1] = make_float2(hk.x, -hk.y);
+      }
+    }
+    if (l == 0) S[G::HL] = mel_bin_grad(xh, true, bin_tab[NFFT / 2], msum, eps4, active);
+    __syncwarp();
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// The transform kernel body.  A group of L lanes takes one frame at a time (warps stride over the frames of the
+// whole batch); everything between the waveform loads and the per-frame gradient store stays on chip.
+// WIN_T > 0: window length known at compile time (shipped configs), which prunes the zero taps out of the
+// load, the first butterflies of the forward transform and the last ones of the inverse.
+// ---------------------------------------------------------------------------------------------
 template <int NFFT, int KIND, bool GRAD, int WIN_T>
 SPL_DEVICE void transform_body(const TransformParams& p, float* smem, int block, int tid, int grid, int wpc) {
-  using G = FftGeom<NFFT>;
-  using SL = SmemLayout<NFFT, KIND, GRAD>;
-  constexpr int L = G::L, R = G::R, FPW = SL::FPW, HALF = NFFT / 2;
+  using G = Geo<NFFT>;
+  using SL = SmemLayout<NFFT, KIND>;
+  constexpr int L = G::L, R = G::R, FPW = G::FPW, HALF = NFFT / 2;
   const int warp = tid >> 5, lane = tid & 31;
   const int l = lane & (L - 1), h = lane / L;
   const int win = WIN_T > 0 ? WIN_T : p.win;
   const int left = WIN_T > 0 ? (NFFT - WIN_T) / 2 : p.left;
 
-  const CtaTables ct = cta_tables(NFFT, p.win, KIND, L, p.mel_rounds, p.mel_entry_rows);
+  const CtaTables ct = cta_tables(NFFT, p.win, KIND, p.mel_rounds, p.mel_entry_rows);
   const float2* tw = reinterpret_cast<const float2*>(smem + ct.tw);
   const float* wtab = smem + ct.win;
   const int4* mel_tasks = reinterpret_cast<const int4*>(smem + ct.tasks);
   const int2* mel_entries = reinterpret_cast<const int2*>(smem + ct.entries);
   const int4* bin_tab = reinterpret_cast<const int4*>(smem + ct.bintab);
 
-  float* wsm = smem + ct.total + (size_t)warp * SL::words_per_warp(p.ring_n, p.n_mels);
-  float2* buf = reinterpret_cast<float2*>(wsm) + h * SL::BUF_F2;     // this frame slot
-  float* ring_base = wsm + FPW * SL::BUF_F2 * 2;
-  float2* ring2 = reinterpret_cast<float2*>(ring_base);              // stft: (u, v)
-  float* ring1 = ring_base;                                          // mel : u
-  float2* msum = reinterpret_cast<float2*>(ring_base + (GRAD ? (KIND == kKindStft ? 2 : 1) * align4(p.ring_n) : 0)) +
-                 h * align4(p.n_mels);              // mel: per-row (Mx, My), then (gM, -)
-  const bool no_ring = (FPW == 1) && (p.m == 1);    // one frame per chunk: windowed frame goes straight to its slot
-  const int total_chunks = p.B * p.n_chunks;
+  float* wsm = smem + ct.total + (size_t)warp * SL::words_per_warp(p.n_mels);
+  float2* S = reinterpret_cast<float2*>(wsm) + h * G::SLOT_F2;                       // this group's frame slot
+  float2* msum = reinterpret_cast<float2*>(wsm + FPW * G::SLOT_F2 * 2) + h * align4(p.n_mels);   // mel: (Mx, My), then (gM, -)
 
-  // [region: chunk loop setup]
-  for (int chunk_id = block * wpc + warp; chunk_id < total_chunks; chunk_id += grid * wpc) {
-    const int b = chunk_id / p.n_chunks, c = chunk_id - b * p.n_chunks;
-    const int t0 = c * p.m;
-    const int m_c = min(p.m, p.n_frames - t0);
+  const int total = p.B * p.n_frames;
+  const unsigned grp_mask = (L == 32) ? 0xffffffffu : (((1u << (L & 31)) - 1u) << (h * L));
+  double d1 = 0.0, d2 = 0.0, d3 = 0.0;      // this lane's share of the sums (stft: 4*S1, 4*S2, S3/(0.5 ln 2); mel: S4)
+
+  // [region: frame loop]
+  for (int base = (block * wpc + warp) * FPW; base < total; base += grid * wpc * FPW) {
+    const int item = base + h;
+    const bool active = item < total;
+    const int b = active ? item / p.n_frames : 0;
+    const int t = active ? item - b * p.n_frames : 0;
     const float* __restrict__ xb = p.x + (size_t)b * p.T;
     const float* __restrict__ yb = p.y + (size_t)b * p.T;
-
-    if (GRAD && !no_ring) {
-      if (KIND == kKindStft) for (int i = lane; i < p.ring_n; i += 32) ring2[i] = make_float2(0.f, 0.f);
-      else                   for (int i = lane; i < p.ring_n; i += 32) ring1[i] = 0.f;
-      __syncwarp();
+    float s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    float2 A[G::RPL][G::HL];
+    bool frame_equal;
+    {
+      float2 v[R];
+      const bool same = load_taps<NFFT, WIN_T>(v, xb, yb, p.T, t * p.hop - HALF, win, left, wtab, l, active);
+      // A frame whose prediction and target taps are bit-identical must contribute exactly zero (the reference
+      // returns sc = mag = mel = 0 and a zero gradient for x == y); the packed FFT would leave ~1e-7 of rounding
+      // asymmetry between X and Y, so such frames reuse X for Y.
+      const unsigned eq_bits = __ballot_sync(0xffffffffu, same);
+      frame_equal = (eq_bits & grp_mask) == grp_mask;
+      fwd_pass_a<NFFT>(v, S, tw, l);
     }
-    float2* out2 = reinterpret_cast<float2*>(p.gchunks) + (size_t)chunk_id * p.span;
-    float* out1 = reinterpret_cast<float*>(p.gchunks) + (size_t)chunk_id * p.span;
-    const int span_c = (m_c - 1) * p.hop + win;
-    int flushed = 0;
-    float s1 = 0.f, s2 = 0.f, s3 = 0.f;   // stft: 4*S1, 4*S2, S3/(0.5 ln 2) ; mel: s1 = S4
-
-    for (int step = 0; step * FPW < m_c; ++step) {
-      const int jc = step * FPW + h;          // frame index inside the chunk
-      const bool active = jc < m_c;
-      const int t = t0 + jc;
-      bool frame_equal = false;
-#pragma unroll 1
-      for (int job = 0; job < (GRAD ? 2 : 1); ++job) {
-        float2 v[R];
-        if (job == 0) {
-          // [region: A load taps + window + equality vote]
-          // ---- A. taps of frame t: reflect-pad, window, pack z = x*w + i*y*w ---------------------
-          const int s0 = t * p.hop - HALF;                         // sample index of tap n = 0
-          const bool interior = (s0 + left >= 0) && (s0 + left + win <= p.T);
-          bool same = true;
-          if (active && interior) {
-            // fast path: no reflection; every address is a compile-time offset from three pointers
-            const float* __restrict__ xp = xb + s0 + l;
-            const float* __restrict__ yp = yb + s0 + l;
-            const float* wp = wtab + (l - left);
+    fwd_pass_b<NFFT>(A, S, l);
+    if (KIND == kKindStft) {
+      const float eps4 = 4.f * p.eps;
+      if (frame_equal) stft_epilogue<NFFT, GRAD, true>(A, S, l, eps4, s1, s2, s3);
+      else             stft_epilogue<NFFT, GRAD, false>(A, S, l, eps4, s1, s2, s3);
+      __syncwarp();      // mirror halves: all reads (and the H written back over them) done before the slot is reused
+    } else {
+      mel_epilogue<NFFT, GRAD>(A, S, msum, l, frame_equal, active, p, mel_tasks, mel_entries, bin_tab, s1);
+    }
+    if (active) { d1 += (double)s1; d2 += (double)s2; d3 += (double)s3; }
+    if (GRAD) {
+      inv_pass_b<NFFT>(A, S, tw, l);
+      float2 v[R];
+      inv_pass_a<NFFT>(v, S, l);
+      // [region: window + store]
+      // windowed frame gradient -> this frame's slot in HBM (coalesced; one writer per element)
+      if (active) {
+        float2* out2 = reinterpret_cast<float2*>(p.gframes) + (size_t)item * win;
+        float* out1 = reinterpret_cast<float*>(p.gframes) + (size_t)item * win;
+        const float* wp = wtab + (l - left);
 #pragma unroll
-            for (int n2 = 0; n2 < R; ++n2) {
-              const int lo = L * n2 - left;                        // tap index of lane 0
-              if (WIN_T > 0 && (lo + L - 1 < 0 || lo >= WIN_T)) { v[n2] = make_float2(0.f, 0.f); continue; }
-              const bool all_lanes = WIN_T > 0 && lo >= 0 && lo + L - 1 < WIN_T;
-              float2 xy = make_float2(0.f, 0.f);
-              if (all_lanes || (lo + l >= 0 && lo + l < win)) {
-                const float w = wp[L * n2];
-                xy = __fmul2_rn(make_float2(__ldg(xp + L * n2), __ldg(yp + L * n2)), make_float2(w, w));
-              }
-              same = same && (xy.x == xy.y);
-              v[n2] = xy;
-            }
-          } else {
-#pragma unroll
-            for (int n2 = 0; n2 < R; ++n2) {
-              const int lo = L * n2 - left;
-              if (WIN_T > 0 && (lo + L - 1 < 0 || lo >= WIN_T)) { v[n2] = make_float2(0.f, 0.f); continue; }
-              const int tap = lo + l;
-              float xv = 0.f, yv = 0.f;
-              if (active && tap >= 0 && tap < win) {
-                const int sidx = reflect(s0 + L * n2 + l, p.T);
-                const float w = wtab[tap];
-                xv = __ldg(&xb[sidx]) * w;
-                yv = __ldg(&yb[sidx]) * w;
-              }
-              same = same && (xv == yv);
-              v[n2] = make_float2(xv, yv);
-            }
-          }
-          // A frame whose prediction and target taps are bit-identical must contribute exactly zero
-          // (the reference returns sc = mag = mel = 0 and a zero gradient for x == y); the packed FFT
-          // would leave ~1e-7 of rounding asymmetry between X and Y, so such frames reuse X for Y.
-          const unsigned eq_bits = __ballot_sync(0xffffffffu, same);
-          const unsigned grp_mask = (L == 32) ? 0xffffffffu : (((1u << (L & 31)) - 1u) << (h * L));
-          frame_equal = (eq_bits & grp_mask) == grp_mask;
-        } else {
-          // [region: D job-1 load of H]
-          // ---- D. gradient spectrum H (slot layout) -> inverse DFT via swapped components ------
-#pragma unroll
-          for (int n2 = 0; n2 < R; ++n2) {
-            const float2 hk = buf[(l + L * (n2 % (R / L))) * (L + 1) + n2 / (R / L)];   // element n = l + L*n2
-            v[n2] = make_float2(hk.y, hk.x);
-          }
-          __syncwarp();
-        }
-        fft_core<NFFT>(v, buf, tw, l);
-        if (job == 1) {
-          // [region: E window + overlap-add]
-          // ---- E. window, overlap-add into the ring (slot holds (imag, real) = (v, u) swapped) --
-          const int n2_lo = left / L, n2_hi = (left + win - 1) / L;      // register slots with live taps
-          if (no_ring) {
-            if (active) {
-#pragma unroll 4
-              for (int n2 = n2_lo; n2 <= n2_hi; ++n2) {
-                const int tap = L * n2 - left + l;
-                if (tap >= 0 && tap < win) {
-                  const float w = wtab[tap];
-                  const float2 g = buf[(l + L * (n2 % (R / L))) * (L + 1) + n2 / (R / L)];
-                  if (KIND == kKindStft) out2[tap] = __fmul2_rn(make_float2(g.y, g.x), make_float2(w, w));
-                  else                   out1[tap] = g.y * w;
-                }
-              }
-            }
-            __syncwarp();
-            continue;
-          }
-#pragma unroll 1
-          for (int hh = 0; hh < FPW; ++hh) {
-            if (h == hh && active) {
-              const int base = (jc * p.hop) % p.ring_n;
-#pragma unroll 4
-              for (int n2 = n2_lo; n2 <= n2_hi; ++n2) {
-                const int tap = L * n2 - left + l;
-                if (tap >= 0 && tap < win) {
-                  const float w = wtab[tap];
-                  const float2 g = buf[(l + L * (n2 % (R / L))) * (L + 1) + n2 / (R / L)];
-                  int idx = base + tap;
-                  idx -= (idx >= p.ring_n) ? p.ring_n : 0;
-                  if (KIND == kKindStft) ring2[idx] = __ffma2_rn(make_float2(g.y, g.x), make_float2(w, w), ring2[idx]);
-                  else                   ring1[idx] = fmaf(g.y, w, ring1[idx]);
-                }
-              }
-            }
-            __syncwarp();
-          }
-          continue;
-        }
-        // [region: C epilogue]
-        // ---- C. job 0 epilogue ------------------------------------------------------------------
-        // Bin k = row + R*col sits at buf[row*(L+1) + col].  A lane owns rows l + L*j; for col < L/2 the
-        // bin is k < N/2 and its mirror N-k is (R - row, L-1-col) -- or (0, L-col) inside row 0.  Bins 0
-        // and N/2 (row 0, cols 0 and L/2) mirror themselves; lane 0 handles N/2 as the extra pair.
-        if (KIND == kKindStft) {
-          const float eps4 = 4.f * p.eps;
-          if (active) {
-            if (frame_equal) stft_epilogue<NFFT, GRAD, true>(buf, l, eps4, s1, s2, s3);
-            else             stft_epilogue<NFFT, GRAD, false>(buf, l, eps4, s1, s2, s3);
-          } else if (GRAD) {
-            for (int i = l; i < R * (L + 1); i += L) buf[i] = make_float2(0.f, 0.f);
-          }
-        } else {
-          // ---- mel: amplitudes -> banded projection -> log-mel L1 -> gradient spectrum ------------
-          // pass 1: X stays in the bin's own slot; (Ax, Ay) are parked in the mirror slot; bin 0 parks
-          // them in the pad slot of row 0, bin N/2 keeps them in place and moves X to the pad slot of row 1.
-          constexpr int EX0 = L, EX1 = (L + 1) + L;
-          const float eps4 = 4.f * p.eps;
-#pragma unroll
-          for (int j = 0; j < R / L; ++j) {
-            const int row = l + L * j;
-            float2* pa = buf + row * (L + 1);
-            float2* pb = (row == 0) ? buf + L : buf + (R - row) * (L + 1) + (L - 1);    // mirror of column c is pb[-c]
-            if (frame_equal) {
-              mel_pair_amp<true>(pa, row == 0 ? pa : pb, pa, row == 0 ? buf + EX0 : pb, eps4);
-#pragma unroll 1
-              for (int c = 1; c < L / 2; ++c) mel_pair_amp<true>(pa + c, pb - c, pa + c, pb - c, eps4);
-            } else {
-              mel_pair_amp<false>(pa, row == 0 ? pa : pb, pa, row == 0 ? buf + EX0 : pb, eps4);
-#pragma unroll (L == 32 ? 5 : 7)
-              for (int c = 1; c < L / 2; ++c) mel_pair_amp<false>(pa + c, pb - c, pa + c, pb - c, eps4);
-            }
-          }
-          if (l == 0) {                                        // bin N/2: amplitudes stay, X moves to the pad slot
-            if (frame_equal) mel_pair_amp<true>(buf + L / 2, buf + L / 2, buf + EX1, buf + L / 2, eps4);
-            else             mel_pair_amp<false>(buf + L / 2, buf + L / 2, buf + EX1, buf + L / 2, eps4);
-          }
-          __syncwarp();
-          // pass 2: balanced projection.  Every mel row is summed by a group of 1..L lanes walking a
-          // host-built table of (amplitude slot, weight) entries, then reduced with shuffles.
-          for (int r = 0; r < p.mel_rounds; ++r) {
-            const int4 tk = mel_tasks[r * L + l];
-            const int row = tk.x & 0xfff, grp = (tk.x >> 12) & 0xff, iters = tk.x >> 20;
-            const int2* en = mel_entries + tk.y * L + l;
-            float mx = 0.f, my = 0.f;
-#pragma unroll 4
-            for (int s = 0; s < iters; ++s) {
-              const int2 e = en[s * L];
-              const float2 amp = buf[e.x];
-              const float w = bits_to_float(e.y);
-              mx = fmaf(amp.x, w, mx);
-              my = fmaf(amp.y, w, my);
-            }
-#pragma unroll
-            for (int o = 1; o < L; o <<= 1) {
-              const float tx = __shfl_xor_sync(0xffffffffu, mx, o), ty = __shfl_xor_sync(0xffffffffu, my, o);
-              if (o < grp) { mx += tx; my += ty; }
-            }
-            if (row != 0xfff && (l & (grp - 1)) == 0) msum[row] = make_float2(mx, my);
-          }
-          __syncwarp();
-          for (int row = l; row < p.n_mels; row += L) {
-            const float2 mm = msum[row];
-            const float mxc = fmaxf(mm.x, p.eps), myc = fmaxf(mm.y, p.eps);
-            const float dl = (mxc == myc) ? 0.f : (logf(mxc) - logf(myc)) * p.inv_ln_base;
-            if (active) s1 += fabsf(dl);
-            if (GRAD) {
-              const float sgn = (dl > 0.f) ? 1.f : ((dl < 0.f) ? -1.f : 0.f);
-              msum[row].x = (mm.x >= p.eps) ? sgn * p.inv_ln_base / mxc : 0.f;     // gM[row]
-            }
-          }
-          __syncwarp();
-          if (GRAD) {
-            // pass 3: gA[k] = sum_m gM[m] W[k,m] (<= 2 adjacent rows), H[k] = w gA gate / Ax * X
-            const float eps4g = 4.f * p.eps;
-#pragma unroll
-            for (int j = 0; j < R / L; ++j) {
-              const int row = l + L * j;
-              float2* pa = buf + row * (L + 1);
-              float2* pb = (row == 0) ? buf + L : buf + (R - row) * (L + 1) + (L - 1);
-              mel_pair_grad(pa, row == 0 ? pa : pb, pa, row == 0, bin_tab[row], msum, eps4g, active);
-#pragma unroll (L == 32 ? 5 : 7)
-              for (int c = 1; c < L / 2; ++c)
-                mel_pair_grad(pa + c, pb - c, pa + c, false, bin_tab[row + R * c], msum, eps4g, active);
-            }
-            if (l == 0) mel_pair_grad(buf + L / 2, buf + L / 2, buf + EX1, true, bin_tab[NFFT / 2], msum, eps4g, active);
+        for (int n2 = 0; n2 < R; ++n2) {
+          const int lo = L * n2 - left;
+          if (WIN_T > 0 && (lo + L - 1 < 0 || lo >= WIN_T)) continue;
+          const bool all_lanes = WIN_T > 0 && lo >= 0 && lo + L - 1 < WIN_T;
+          if (all_lanes || (lo + l >= 0 && lo + l < win)) {
+            const float w = wp[L * n2];
+            if (KIND == kKindStft) out2[lo + l] = __fmul2_rn(make_float2(v[n2].y, v[n2].x), make_float2(w, w));
+            else                   out1[lo + l] = v[n2].y * w;
           }
         }
-        __syncwarp();
-      }  // job
-      if (GRAD && !no_ring) {
-        // [region: F ring flush]
-        // ---- F. flush the ring entries no later frame of this chunk touches ----------------------
-        const int done = min(m_c, (step + 1) * FPW);
-        const int limit = (done == m_c) ? span_c : done * p.hop;
-        int idx = (flushed + lane) % p.ring_n;                  // one division per flush, then wrap by compare
-        const int wrap = 32 % p.ring_n;
-        for (int q = flushed + lane; q < limit; q += 32) {
-          if (KIND == kKindStft) { out2[q] = ring2[idx]; ring2[idx] = make_float2(0.f, 0.f); }
-          else                   { out1[q] = ring1[idx]; ring1[idx] = 0.f; }
-          idx += wrap;
-          idx -= (idx >= p.ring_n) ? p.ring_n : 0;
-        }
-        flushed = limit;
-        __syncwarp();
-      }
-    }  // step
-
-    // [region: partial sums]
-    // ---- partial sums of this chunk (one writer per slot: deterministic) ------------------------
-    s1 = warp_sum(s1);
-    if (KIND == kKindStft) { s2 = warp_sum(s2); s3 = warp_sum(s3); }
-    if (lane == 0) {
-      if (KIND == kKindStft) {
-        double* o = p.partials + (size_t)chunk_id * 3;
-        o[0] = 0.25 * (double)s1; o[1] = 0.25 * (double)s2; o[2] = 0.34657359027997264 * (double)s3;  // 0.5 ln 2
-      } else {
-        p.partials[chunk_id] = (double)s1;
       }
     }
-  }  // chunk
+  }
+
+  // [region: partial sums]
+  // one row of partial sums per warp (fixed frame -> warp assignment and fixed order: deterministic)
+  d1 = warp_sum(d1);
+  if (KIND == kKindStft) { d2 = warp_sum(d2); d3 = warp_sum(d3); }
+  if (lane == 0) {
+    const int prow = block * wpc + warp;
+    if (KIND == kKindStft) {
+      double* o = p.partials + (size_t)prow * 3;
+      o[0] = 0.25 * d1; o[1] = 0.25 * d2; o[2] = 0.34657359027997264 * d3;     // 0.5 ln 2
+    } else {
+      p.partials[prow] = d1;
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
 // Explicit magnitude spectrogram, forward only: out[b, t, k] = sqrt(max(|STFT(x)[b, t, k]|^2, eps)),
 // laid out (B, F, ld >= K) -- the tensor stft() returns (losses/stft_loss.py:19-35) and the A operand of
-// the mel projection GEMM.  Frames t and t+1 of the SAME signal share one complex FFT (real / imaginary
-// slot), so the work per frame is half of a naive real transform.
+// the mel projection GEMM (mel_loss.py:88-91).  Frames t and t+1 of the SAME signal share one complex FFT (real /
+// imaginary part), so the work per frame is half of a naive real transform.
 // ---------------------------------------------------------------------------------------------
 struct SpecParams {
   const float* x;        // (B, T)
@@ -594,79 +616,77 @@ struct SpecParams {
   int ld;
 };
 
-template <int NFFT>
-SPL_DEVICE void spec_load_tables(const SpecParams& p, float* smem, int tid, int nthreads) {
-  constexpr int L = FftGeom<NFFT>::L;
-  const CtaTables ct = cta_tables(NFFT, p.win, kKindStft, L, 0, 0);
-  const float* tw = reinterpret_cast<const float*>(p.twiddle);
-  for (int i = tid; i < 2 * NFFT; i += nthreads) smem[ct.tw + i] = __ldg(&tw[i]);
-  for (int i = tid; i < p.win; i += nthreads) smem[ct.win + i] = __ldg(&p.window[i]);
-}
-
+// [region: spectrogram]
 template <int NFFT>
 SPL_DEVICE void spec_body(const SpecParams& p, float* smem, int block, int tid, int grid, int wpc) {
-  using G = FftGeom<NFFT>;
-  using SL = SmemLayout<NFFT, kKindStft, false>;
-  constexpr int L = G::L, R = G::R, FPW = SL::FPW, HALF = NFFT / 2;
+  using G = Geo<NFFT>;
+  using SL = SmemLayout<NFFT, kKindStft>;
+  constexpr int L = G::L, R = G::R, FPW = G::FPW, HALF = NFFT / 2;
   const int warp = tid >> 5, lane = tid & 31;
   const int l = lane & (L - 1), h = lane / L;
-  const CtaTables ct = cta_tables(NFFT, p.win, kKindStft, L, 0, 0);
+  const CtaTables ct = cta_tables(NFFT, p.win, kKindStft, 0, 0);
   const float2* tw = reinterpret_cast<const float2*>(smem + ct.tw);
   const float* wtab = smem + ct.win;
-  float2* buf = reinterpret_cast<float2*>(smem + ct.total + (size_t)warp * SL::words_per_warp(0, 0)) + h * SL::BUF_F2;
+  float2* S = reinterpret_cast<float2*>(smem + ct.total + (size_t)warp * SL::words_per_warp(0)) + h * G::SLOT_F2;
   const int total = p.B * p.n_pairs;                 // work items: (utterance, frame pair)
   const float eps4 = 4.f * p.eps;
-  const int steps = (total + grid * wpc * FPW - 1) / (grid * wpc * FPW);
-  for (int it = 0; it < steps; ++it) {
-    const int item = (it * grid * wpc + block * wpc + warp) * FPW + h;
+  for (int base = (block * wpc + warp) * FPW; base < total; base += grid * wpc * FPW) {
+    const int item = base + h;
     const bool active = item < total;
     const int b = active ? item / p.n_pairs : 0, pr = active ? item - b * p.n_pairs : 0;
     const int t = 2 * pr;
     const bool second = active && (t + 1 < p.n_frames);
     const float* __restrict__ xb = p.x + (size_t)b * p.T;
-    float2 v[R];
+    float2 A[G::RPL][G::HL];
+    {
+      float2 v[R];
 #pragma unroll
-    for (int n2 = 0; n2 < R; ++n2) {
-      const int tap = L * n2 - p.left + l;
-      float a0 = 0.f, a1 = 0.f;
-      if (active && tap >= 0 && tap < p.win) {
-        const float w = wtab[tap];
-        const int s = t * p.hop + L * n2 + l - HALF;
-        a0 = __ldg(&xb[reflect(s, p.T)]) * w;
-        if (second) a1 = __ldg(&xb[reflect(s + p.hop, p.T)]) * w;
-      }
-      v[n2] = make_float2(a0, a1);
-    }
-    fft_core<NFFT>(v, buf, tw, l);
-    if (active) {
-      float* o0 = p.out + ((size_t)b * p.n_frames + t) * p.ld;
-      float* o1 = o0 + p.ld;
-#pragma unroll
-      for (int j = 0; j < R / L; ++j) {
-        const int row = l + L * j;
-        const float2* pa = buf + row * (L + 1);
-        const float2* pb = (row == 0) ? buf + L : buf + (R - row) * (L + 1) + (L - 1);
-#pragma unroll 4
-        for (int c = 0; c <= L / 2; ++c) {
-          if (c == L / 2 && row != 0) break;                    // bin N/2 lives in row 0 only
-          const bool self = (row == 0) && (c == 0 || c == L / 2);
-          const float2 a = pa[c], bm = self ? a : pb[-c];
-          const float2 x2 = __fadd2_rn(a, make_float2(bm.x, -bm.y));                           // 2 X_t[k]
-          const float2 y2 = __fadd2_rn(make_float2(a.y, -a.x), make_float2(bm.y, bm.x));       // 2 X_{t+1}[k]
-          const float p0 = fmaxf(fmaf(x2.x, x2.x, x2.y * x2.y), eps4);
-          const float p1 = fmaxf(fmaf(y2.x, y2.x, y2.y * y2.y), eps4);
-          const int k = row + R * c;
-          o0[k] = 0.5f * p0 * spl_fast_rsqrt(p0);
-          if (second) o1[k] = 0.5f * p1 * spl_fast_rsqrt(p1);
+      for (int n2 = 0; n2 < R; ++n2) {
+        const int tap = L * n2 - p.left + l;
+        float a0 = 0.f, a1 = 0.f;
+        if (active && tap >= 0 && tap < p.win) {
+          const float w = wtab[tap];
+          const int s = t * p.hop + L * n2 + l - HALF;
+          a0 = __ldg(&xb[reflect(s, p.T)]) * w;
+          if (second) a1 = __ldg(&xb[reflect(s + p.hop, p.T)]) * w;
         }
+        v[n2] = make_float2(a0, a1);
+      }
+      fwd_pass_a<NFFT>(v, S, tw, l);
+    }
+    fwd_pass_b<NFFT>(A, S, l);
+    float* o0 = p.out + ((size_t)b * p.n_frames + t) * p.ld;
+    float* o1 = o0 + p.ld;
+#pragma unroll
+    for (int j = 0; j < G::RPL; ++j) {
+      const int row = l + L * j;
+      const float2* pb = mirror_ptr<NFFT>(S, row);
+#pragma unroll
+      for (int k1 = 0; k1 < G::HL; ++k1) {
+        const float2 a = A[j][k1];
+        float2 bm = pb[-k1];
+        if (j == 0 && k1 == 0) bm = (row == 0) ? a : bm;
+        const float2 x2 = __fadd2_rn(a, make_float2(bm.x, -bm.y));                           // 2 X_t[k]
+        const float2 y2 = __fadd2_rn(make_float2(a.y, -a.x), make_float2(bm.y, bm.x));       // 2 X_{t+1}[k]
+        const float p0 = fmaxf(fmaf(x2.x, x2.x, x2.y * x2.y), eps4);
+        const float p1 = fmaxf(fmaf(y2.x, y2.x, y2.y * y2.y), eps4);
+        const int k = row + R * k1;
+        if (active) o0[k] = 0.5f * p0 * spl_fast_rsqrt(p0);
+        if (second) o1[k] = 0.5f * p1 * spl_fast_rsqrt(p1);
       }
     }
-    __syncwarp();
+    if (l == 0) {                                                    // bin N/2
+      const float2 a = S[G::HL];
+      const float p0 = fmaxf(4.f * a.x * a.x, eps4), p1 = fmaxf(4.f * a.y * a.y, eps4);
+      if (active) o0[NFFT / 2] = 0.5f * p0 * spl_fast_rsqrt(p0);
+      if (second) o1[NFFT / 2] = 0.5f * p1 * spl_fast_rsqrt(p1);
+    }
+    __syncwarp();       // the slot's mirror halves are read above; the next pass-A store must wait for every lane
   }
 }
 
 // ---------------------------------------------------------------------------------------------
-// deterministic reduction of the per-chunk partial sums: one CTA per output sum
+// deterministic reduction of the per-warp partial sums: one CTA per output sum
 // ---------------------------------------------------------------------------------------------
 struct ReduceParams {
   int n_sums;
@@ -730,12 +750,12 @@ SPL_DEVICE void finalize_body(const FinalizeParams& p) {
 
 // ---------------------------------------------------------------------------------------------
 // backward: dx[b, i] = sum over transforms of coef * (overlap-added frame gradients), gathered
-// from the per-chunk slots (no atomics: every slot has one writer, every dx sample one reader)
+// from the per-frame slots (no atomics: every slot has one writer, every dx sample one reader)
 // and folded over the reflect-padding margins.
 // ---------------------------------------------------------------------------------------------
 struct CombineEntry {
-  const void* chunks;
-  int kind, half, hop, win, left, m, n_chunks, span, n_frames;
+  const void* frames;    // [B * n_frames][win] float2 (stft) | float (mel)
+  int kind, half, hop, win, left, n_frames;
 };
 struct CombineParams {
   int n;
@@ -748,46 +768,38 @@ struct CombineParams {
   int B, T;
 };
 
-// overlap-added value at one padded position (used for the reflect-fold margins)
+// overlap-added value at one padded position (used for the reflect-fold margins): frames t with
+// 0 <= q - t*hop < win, q = position relative to the first live tap of frame 0
 SPL_DEVICE float gather_padded(const CombineEntry& e, int b, int ppos, float cu, float cv) {
-  const int q_abs = ppos - e.left;
-  if (q_abs < 0 || q_abs >= (e.n_frames - 1) * e.hop + e.win) return 0.f;
-  const int mh = e.m * e.hop;
-  int c = min(q_abs / mh, e.n_chunks - 1);
+  const int q = ppos - e.left;
+  if (q < 0) return 0.f;
   float acc = 0.f;
-  for (; c >= 0; --c) {
-    const int q = q_abs - c * mh;
-    if (q >= e.span) break;
-    const int m_c = min(e.m, e.n_frames - c * e.m);
-    if (q < (m_c - 1) * e.hop + e.win) {
-      const size_t o = ((size_t)b * e.n_chunks + c) * e.span + q;
-      if (e.kind == kKindStft) {
-        const float2 v = __ldg(reinterpret_cast<const float2*>(e.chunks) + o);
-        acc = fmaf(cu, v.x, fmaf(cv, v.y, acc));
-      } else {
-        acc = fmaf(cu, __ldg(reinterpret_cast<const float*>(e.chunks) + o), acc);
-      }
+  for (int t = min(q / e.hop, e.n_frames - 1); t >= 0; --t) {
+    const int tap = q - t * e.hop;
+    if (tap >= e.win) break;
+    const size_t o = ((size_t)b * e.n_frames + t) * e.win + tap;
+    if (e.kind == kKindStft) {
+      const float2 v = __ldg(reinterpret_cast<const float2*>(e.frames) + o);
+      acc = fmaf(cu, v.x, fmaf(cv, v.y, acc));
+    } else {
+      acc = fmaf(cu, __ldg(reinterpret_cast<const float*>(e.frames) + o), acc);
     }
   }
   return acc;
 }
 
-// same for four consecutive padded positions ppos0 .. ppos0+3: one chunk walk, 16-byte loads when the
-// four samples sit inside one slot and the address is aligned (always the case for the shipped configs)
+// same for four consecutive padded positions ppos0 .. ppos0+3: one walk over the covering frames, 16-byte loads
+// when the four taps sit inside the frame and the address is aligned
 SPL_DEVICE void gather_padded4(const CombineEntry& e, int b, int ppos0, float cu, float cv, float (&acc)[4]) {
   const int q0 = ppos0 - e.left;
-  if (q0 + 3 < 0 || q0 >= (e.n_frames - 1) * e.hop + e.win) return;
-  const int mh = e.m * e.hop;
-  int c = min((q0 + 3) / mh, e.n_chunks - 1);
-  for (; c >= 0; --c) {
-    const int q = q0 - c * mh;
-    if (q >= e.span) break;
-    const int m_c = min(e.m, e.n_frames - c * e.m);
-    const int lim = (m_c - 1) * e.hop + e.win;
-    const size_t o = ((size_t)b * e.n_chunks + c) * e.span + q;     // meaningful for q >= 0 only
+  if (q0 + 3 < 0) return;
+  for (int t = min((q0 + 3) / e.hop, e.n_frames - 1); t >= 0; --t) {
+    const int tap = q0 - t * e.hop;                 // tap of the first of the four positions (may be negative)
+    if (tap >= e.win) break;
+    const size_t o = ((size_t)b * e.n_frames + t) * e.win + tap;     // meaningful for tap >= 0 only
     if (e.kind == kKindStft) {
-      const float2* src = reinterpret_cast<const float2*>(e.chunks);
-      if (q >= 0 && q + 3 < lim && (o & 1) == 0) {
+      const float2* src = reinterpret_cast<const float2*>(e.frames);
+      if (tap >= 0 && tap + 3 < e.win && (o & 1) == 0) {
         const float4 v0 = __ldg(reinterpret_cast<const float4*>(src + o));
         const float4 v1 = __ldg(reinterpret_cast<const float4*>(src + o + 2));
         acc[0] = fmaf(cu, v0.x, fmaf(cv, v0.y, acc[0]));
@@ -797,21 +809,21 @@ SPL_DEVICE void gather_padded4(const CombineEntry& e, int b, int ppos0, float cu
       } else {
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          if (q + j >= 0 && q + j < lim) {
+          if (tap + j >= 0 && tap + j < e.win) {
             const float2 v = __ldg(src + (o + j));
             acc[j] = fmaf(cu, v.x, fmaf(cv, v.y, acc[j]));
           }
       }
     } else {
-      const float* src = reinterpret_cast<const float*>(e.chunks);
-      if (q >= 0 && q + 3 < lim && (o & 3) == 0) {
+      const float* src = reinterpret_cast<const float*>(e.frames);
+      if (tap >= 0 && tap + 3 < e.win && (o & 3) == 0) {
         const float4 v = __ldg(reinterpret_cast<const float4*>(src + o));
         acc[0] = fmaf(cu, v.x, acc[0]); acc[1] = fmaf(cu, v.y, acc[1]);
         acc[2] = fmaf(cu, v.z, acc[2]); acc[3] = fmaf(cu, v.w, acc[3]);
       } else {
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          if (q + j >= 0 && q + j < lim) acc[j] = fmaf(cu, __ldg(src + (o + j)), acc[j]);
+          if (tap + j >= 0 && tap + j < e.win) acc[j] = fmaf(cu, __ldg(src + (o + j)), acc[j]);
       }
     }
   }
@@ -875,7 +887,8 @@ __global__ void __launch_bounds__(MaxWarps<NFFT>::value * 32, 1) transform_kerne
 template <int NFFT>
 __global__ void __launch_bounds__(MaxWarps<NFFT>::value * 32, 1) spec_kernel(const SpecParams p) {
   extern __shared__ __align__(16) float smem_dyn[];
-  spec_load_tables<NFFT>(p, smem_dyn, threadIdx.x, blockDim.x);
+  cta_load_fft_tables<NFFT>(cta_tables(NFFT, p.win, kKindStft, 0, 0), p.twiddle, p.window, p.win, smem_dyn, threadIdx.x,
+                            blockDim.x);
   __syncthreads();
   spec_body<NFFT>(p, smem_dyn, blockIdx.x, threadIdx.x, gridDim.x, blockDim.x >> 5);
 }

@@ -58,8 +58,8 @@ def mel_tables(melmat: np.ndarray, n_fft: int):
     group is reduced with shuffles.  Groups are packed into rounds of L lanes, largest first, which
     keeps them aligned to their size.  Each lane walks a dense list of (amplitude slot, weight)
     entries, so the inner loop has no index arithmetic; padding entries carry weight 0.
-    The amplitudes of bin k are parked by the kernel in the slot of the mirror bin n_fft - k (bin 0: the
-    pad slot of row 0), see specloss_kernels.cuh.
+    The amplitudes of bin k <= n_fft/2 are parked by the kernel at the bin's own position in the frame slot
+    (those columns are free: the spectrum lives in registers), see specloss_kernels.cuh.
     Backward projection: every bin feeds at most two adjacent rows m0, m0+1.
     Slaney/HTK triangles always satisfy both; anything else raises (there is no dense fallback)."""
     lanes, _ = fft_geometry(n_fft)
@@ -90,7 +90,7 @@ def mel_tables(melmat: np.ndarray, n_fft: int):
         rounds.append(cur)
     tasks = np.zeros((len(rounds), lanes, 4), np.int32)
     entries = []
-    amp_slot = lambda k: lanes if k == 0 else slot_offset(n_fft, n_fft - k)      # noqa: E731
+    amp_slot = lambda k: slot_offset(n_fft, k)      # noqa: E731
     for r, grp_list in enumerate(rounds):
         iters = max((-(-ln // g) for g, _, _, ln in grp_list), default=0)
         ent = np.zeros((iters, lanes, 2), np.int32)
@@ -152,37 +152,6 @@ class TransformPlan:
             raise RuntimeError("window buffer must be float32 with win_length taps (fp32-only implementation)")
 
 
-def choose_frames_per_chunk(batch: int, n_frames: int, n_fft: int) -> int:
-    """Frames walked by one warp.  Small problems want many short chunks (parallelism: the whole
-    config-2 batch is 27.6k frames for ~2.4k resident warps), big ones longer chunks (less seam
-    traffic in the gradient slots).  SPECLOSS_FRAMES_PER_CHUNK overrides: "4" or "1024:2,2048:1,512:4"."""
-    env = os.environ.get("SPECLOSS_FRAMES_PER_CHUNK")
-    m = None
-    if env:
-        if ":" in env:
-            spec = dict(item.split(":") for item in env.split(","))
-            if str(n_fft) in spec:
-                m = max(1, int(spec[str(n_fft)]))
-        else:
-            m = max(1, int(env))
-    if m is None:
-        warps = _SM_COUNT * (12 if n_fft == 2048 else 16)
-        per_warp = batch * n_frames / float(warps)
-        if n_fft == 2048:
-            # one frame per chunk: no overlap-add ring in shared memory, 12 instead of 8 warps per SM
-            # (measured on B200, config 2: mel 154 -> 84 us, stft-2048 93 -> 60 us)
-            m = 1
-        elif per_warp < 8.0:
-            # small problem: the finest granularity keeps the warps evenly loaded (config 2 has 2.7 frames
-            # of the 1024-point transform per resident warp; m = 2 would round that up to 4)
-            m = 1 if n_fft == 1024 else 2
-        else:
-            m = max(2, min(16, int(round(per_warp / 4.0))))
-    if n_fft == 512 and (m & 1):        # two frames in flight per warp
-        m += 1
-    return m
-
-
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
@@ -210,7 +179,7 @@ def _align(n: int, a: int = 256) -> int:
 class _Recipe:
     """Everything about a (plan list, batch shape, grad mode) that does not change from call to call:
     the filled ctypes transform array and the carve-up of the single per-call workspace buffer."""
-    __slots__ = ("template", "nbytes", "n", "off_partials", "off_gchunks", "off_sums", "off_coefs", "ws_bytes",
+    __slots__ = ("template", "nbytes", "n", "off_partials", "off_gframes", "off_sums", "off_coefs", "ws_bytes",
                  "n_sums", "has_stft", "has_mel", "keep")
 
 
@@ -240,7 +209,7 @@ class Engine:
     def _recipe(self, plans: Sequence[TransformPlan], batch: int, t_len: int, need_grad: bool, dev) -> _Recipe:
         key = (tuple((p.kind, p.n_fft, p.hop, p.win, p.eps, p.n_mels, p.inv_ln_base, p.window.data_ptr(),
                       p.twiddle.data_ptr()) + tuple(t.data_ptr() for t in p.tables.values()) for p in plans),
-               batch, t_len, need_grad, str(dev), os.environ.get("SPECLOSS_FRAMES_PER_CHUNK"))
+               batch, t_len, need_grad, str(dev))
         rec = self._recipes.get(key)
         if rec is not None:
             return rec
@@ -249,7 +218,7 @@ class Engine:
         n = len(plans)
         arr = (SplTransform * n)()
         rec = _Recipe()
-        rec.n, rec.off_partials, rec.off_gchunks, rec.keep = n, [], [], []
+        rec.n, rec.off_partials, rec.off_gframes, rec.keep = n, [], [], []
         off = 0
         n_sums = 0
         for i, pl in enumerate(plans):
@@ -262,7 +231,6 @@ class Engine:
             tr = arr[i]
             tr.kind, tr.n_fft, tr.hop, tr.win = pl.kind, pl.n_fft, pl.hop, pl.win
             tr.eps = pl.eps
-            tr.frames_per_chunk = choose_frames_per_chunk(batch, 1 + t_len // pl.hop, pl.n_fft)
             tr.window, tr.twiddle = _ptr(pl.window), _ptr(pl.twiddle)
             tr.n_mels, tr.inv_ln_base = pl.n_mels, pl.inv_ln_base
             if pl.kind == SPL_KIND_MEL:
@@ -277,8 +245,8 @@ class Engine:
             rec.off_partials.append(off)
             off = _align(off + 8 * g.partial_count)
             if need_grad:
-                rec.off_gchunks.append(off)
-                off = _align(off + g.gchunk_bytes)
+                rec.off_gframes.append(off)
+                off = _align(off + g.gframe_bytes)
             n_sums += g.n_sums
             rec.keep.extend([pl.window, pl.twiddle] + list(pl.tables.values()))
         rec.off_sums = off
@@ -309,7 +277,7 @@ class Engine:
         ctypes.memmove(arr, rec.template, rec.nbytes)
         for i in range(n):
             arr[i].partials = base + rec.off_partials[i]
-            arr[i].gchunks = base + rec.off_gchunks[i] if need_grad else None
+            arr[i].gframes = base + rec.off_gframes[i] if need_grad else None
         st = ForwardState()
         st.batch, st.t_len, st.has_grad, st.n, st.transforms = batch, t_len, need_grad, n, arr
         st.keep = (ws, rec.keep)
@@ -339,6 +307,21 @@ class Engine:
             st.n_launches = n + 2
         self.launches += st.n_launches
         return st
+
+    # -- explicit spectrogram ----------------------------------------------------------------------
+    def spectrogram(self, x: torch.Tensor, n_fft: int, hop: int, win: int, window: torch.Tensor,
+                    twiddle: torch.Tensor, eps: float, ld: Optional[int] = None) -> torch.Tensor:
+        """(B, T) fp32 -> magnitude spectrogram (B, 1 + T // hop, n_fft // 2 + 1), the tensor the reference's
+        stft() returns (stft_loss.py:19-35).  With `ld` the rows are padded to ld floats (a view is returned)."""
+        fft_geometry(n_fft)
+        batch, t_len = x.shape
+        n_bins = n_fft // 2 + 1
+        ld = n_bins if ld is None else int(ld)
+        out = torch.empty(batch, 1 + t_len // hop, ld, dtype=torch.float32, device=x.device)
+        _abi.check(self.lib, self.lib.spl_spectrogram(x.data_ptr(), batch, t_len, n_fft, hop, win, window.data_ptr(),
+                                                      twiddle.data_ptr(), eps, out.data_ptr(), ld, self._stream(x)))
+        self.launches += 1
+        return out if ld == n_bins else out[:, :, :n_bins]
 
     # -- backward --------------------------------------------------------------------------------
     def backward(self, st: ForwardState, g_sc: Optional[torch.Tensor], g_mag: Optional[torch.Tensor],

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SPL_ABI_VERSION 5
+#define SPL_ABI_VERSION 6
 
 #define SPL_OK 0
 #define SPL_E_INVALID (-1)   /* bad argument / outside the supported envelope */
@@ -38,8 +38,6 @@ extern "C" {
 typedef struct spl_transform {
   int32_t kind;              /* SPL_KIND_* */
   int32_t n_fft, hop, win;   /* torch.stft(x, n_fft, hop, win, window), center=True, reflect pad */
-  int32_t frames_per_chunk;  /* consecutive frames walked by one warp (>= 1; even if n_fft==512); 1 = no
-                                shared-memory overlap-add, every windowed frame goes straight to its slot */
   float eps;                 /* clamp on |X|^2: 1e-7 (stft_loss.py:19) / 1e-10 (mel_loss.py:35); mel reuses it on the mel energies */
   const float* window;       /* device, `win` taps (the module's registered buffer) */
   const float* twiddle;      /* device, 2*n_fft floats written by spl_fill_twiddle() */
@@ -54,20 +52,20 @@ typedef struct spl_transform {
   int32_t mel_entry_rows;       /* sum of iters over the rounds */
   const int32_t* bin_tab;       /* device [(n_fft/2+1) * 4]: {m0, bits(melmat[k,m0]), bits(melmat[k,m0+1]), 0} */
   /* --- per-call workspace, sized by spl_geometry() --- */
-  double* partials;          /* device [partial_count] */
-  void* gchunks;             /* device [gchunk_bytes]; NULL = forward only (torch.no_grad) */
+  double* partials;          /* device [partial_count]: one row of n_sums per warp of the launch */
+  void* gframes;             /* device [gframe_bytes]: the windowed, un-scaled gradient of every frame
+                                ([B * n_frames][win] float2 for STFT, float for mel); NULL = forward only (torch.no_grad) */
 } spl_transform;
 
 typedef struct spl_geometry {
   int32_t n_frames;          /* 1 + T / hop */
   int32_t n_bins;            /* n_fft / 2 + 1 */
-  int32_t n_chunks;          /* per utterance */
-  int32_t span;              /* gradient slot length per chunk, in elements */
   int32_t n_sums;            /* 3 (S1, S2, S3) for STFT, 1 (S4) for mel */
-  int64_t partial_count;     /* doubles in `partials` */
-  int64_t gchunk_bytes;      /* bytes in `gchunks` */
+  int32_t reserved;
+  int64_t partial_count;     /* doubles in `partials` (upper bound over devices) */
+  int64_t gframe_bytes;      /* bytes in `gframes` */
   int64_t smem_table_bytes;  /* shared memory per CTA for the constant tables (twiddle, window, mel tables) */
-  int64_t smem_warp_bytes;   /* shared memory per warp (frame slot(s), overlap-add ring, mel scratch) */
+  int64_t smem_warp_bytes;   /* shared memory per warp (frame slot(s), mel scratch) */
 } spl_geometry;
 
 int32_t spl_abi_version(void);
@@ -81,7 +79,7 @@ int32_t spl_geometry_of(const spl_transform* t, int32_t B, int32_t T, spl_geomet
 
 /* Forward of every transform in ts[0..n): replaces stft()/STFTLoss.forward (stft_loss.py:19-35,
  * 100-117) and MelSpectrogram.forward (mel_loss.py:74-94) for x and y at once.  Writes per-chunk
- * partial sums and, when gchunks != NULL, the un-scaled waveform-gradient pieces of dL/dx. */
+ * partial sums and, when gframes != NULL, the un-scaled waveform-gradient pieces of dL/dx. */
 int32_t spl_forward(const spl_transform* ts, int32_t n, const float* x, const float* y,
                     int32_t B, int32_t T, void* stream);
 
@@ -106,6 +104,13 @@ int32_t spl_reduce_finalize(const spl_transform* ts, int32_t n, int32_t B, int32
  * the reference modules.  g_* are device scalars (NULL = 0). */
 int32_t spl_backward(const spl_transform* ts, int32_t n, int32_t B, int32_t T, const float* coefs,
                      const float* g_sc, const float* g_mag, const float* g_mel, float* dx, void* stream);
+
+/* Explicit magnitude spectrogram out[b, t, k] = sqrt(max(|STFT(x)[b, t, k]|^2, eps)), (B, 1 + T/hop, ld) with
+ * ld >= n_fft/2 + 1 floats per frame: the tensor stft() returns (stft_loss.py:19-35) and the operand of the mel
+ * projection in MelSpectrogram.forward (mel_loss.py:88-91).  Forward only.  window: device, `win` taps; twiddle:
+ * device, 2*n_fft floats from spl_fill_twiddle(). */
+int32_t spl_spectrogram(const float* x, int32_t B, int32_t T, int32_t n_fft, int32_t hop, int32_t win,
+                        const float* window, const float* twiddle, float eps, float* out, int32_t ld, void* stream);
 
 #ifdef __cplusplus
 }

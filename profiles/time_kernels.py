@@ -29,17 +29,27 @@ cases = [("stft1024", [stft.stft_losses[0].plan()]), ("stft2048", [stft.stft_los
          ("all4", stft.plans() + mel.plans())]
 
 
-def timeit(fn, reps=30):
-    for _ in range(5):
-        fn()
+def timeit(fn, inner=10, reps=10):
+    """Device time per call, free of host launch overhead: `inner` calls captured in one CUDA graph, replayed."""
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            fn()
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        for _ in range(inner):
+            fn()
+    graph.replay()
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     for _ in range(reps):
-        fn()
+        graph.replay()
     b.record()
     torch.cuda.synchronize()
-    return a.elapsed_time(b) / reps * 1e3
+    return a.elapsed_time(b) / (reps * inner) * 1e3
 
 
 for spec in (sys.argv[1:] or [""]):

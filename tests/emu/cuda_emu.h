@@ -29,6 +29,7 @@ static inline float2 make_float2(float x, float y) { return float2{x, y}; }
 struct EmuWarp {
   std::barrier<> bar{32};
   float slots[32];
+  double dslots[32];
   unsigned votes[32];
 };
 extern thread_local EmuWarp* emu_warp;
@@ -40,6 +41,13 @@ static inline float __shfl_xor_sync(unsigned, float v, int lane_mask) {
   emu_warp->slots[emu_lane] = v;
   emu_warp->bar.arrive_and_wait();
   const float r = emu_warp->slots[emu_lane ^ lane_mask];
+  emu_warp->bar.arrive_and_wait();
+  return r;
+}
+static inline double __shfl_xor_sync(unsigned, double v, int lane_mask) {
+  emu_warp->dslots[emu_lane] = v;
+  emu_warp->bar.arrive_and_wait();
+  const double r = emu_warp->dslots[emu_lane ^ lane_mask];
   emu_warp->bar.arrive_and_wait();
   return r;
 }

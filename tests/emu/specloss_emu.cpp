@@ -42,16 +42,18 @@ void run_warp(F&& body) {     // body(lane), 32 lanes in lock step
   for (auto& t : th) t.join();
 }
 
-template <int NFFT, int KIND, bool GRAD, int WIN_T>
-int spl_launch_transform(const spl::TransformParams& p, int n_mels, void*) {
-  using SL = spl::SmemLayout<NFFT, KIND, GRAD>;
-  constexpr int L = spl::FftGeom<NFFT>::L;
-  const spl::CtaTables ct = spl::cta_tables(NFFT, p.win, KIND, L, p.mel_rounds, p.mel_entry_rows);
-  const int wpc = 3;                       // odd on purpose; fewer warps than chunks exercises the stride loop
-  const size_t words = (size_t)ct.total + (size_t)SL::words_per_warp(p.ring_n, n_mels) * wpc;
-  const long long chunks = (long long)p.B * p.n_chunks;
-  const int need = (int)((chunks + wpc - 1) / wpc);
-  const int grid = std::min(need, 5);
+// emulated device: 5 "SMs", 3 warps per CTA (odd on purpose; fewer warps than frames exercises the stride loop)
+int spl_launch_shape(int, size_t, size_t, long long items, int* grid, int* wpc) {
+  const int w = 3;
+  const long long need = (items + w - 1) / w;
+  *grid = (int)std::min<long long>(need, 5);
+  *wpc = w;
+  return SPL_OK;
+}
+
+template <typename Load, typename Body>
+void run_grid(int grid, int wpc, size_t smem_bytes, Load&& load, Body&& body) {
+  const size_t words = smem_bytes / 4;
   std::vector<std::thread> blocks;
   const int par = std::max(1u, std::thread::hardware_concurrency());
   for (int b0 = 0; b0 < grid; b0 += par) {
@@ -59,14 +61,28 @@ int spl_launch_transform(const spl::TransformParams& p, int n_mels, void*) {
     for (int block = b0; block < std::min(grid, b0 + par); ++block)
       blocks.emplace_back([&, block] {
         std::vector<float> smem(words, -12345.0f);   // poison: uninitialised reads show up as garbage
-        for (int tid = 0; tid < wpc * 32; ++tid) spl::cta_load_tables<NFFT, KIND>(p, smem.data(), tid, wpc * 32);
+        for (int tid = 0; tid < wpc * 32; ++tid) load(smem.data(), tid);
         for (int warp = 0; warp < wpc; ++warp)
-          run_warp([&](int lane) {
-            spl::transform_body<NFFT, KIND, GRAD, WIN_T>(p, smem.data(), block, warp * 32 + lane, grid, wpc);
-          });
+          run_warp([&](int lane) { body(smem.data(), block, warp * 32 + lane); });
       });
     for (auto& t : blocks) t.join();
   }
+}
+
+template <int NFFT, int KIND, bool GRAD, int WIN_T>
+int spl_launch_transform(const spl::TransformParams& p, int grid, int wpc, size_t smem, void*) {
+  run_grid(grid, wpc, smem,
+           [&](float* sm, int tid) { spl::cta_load_tables<NFFT, KIND>(p, sm, tid, wpc * 32); },
+           [&](float* sm, int block, int tid) { spl::transform_body<NFFT, KIND, GRAD, WIN_T>(p, sm, block, tid, grid, wpc); });
+  return SPL_OK;
+}
+
+template <int NFFT>
+int spl_launch_spec(const spl::SpecParams& p, int grid, int wpc, size_t smem, void*) {
+  const spl::CtaTables ct = spl::cta_tables(NFFT, p.win, spl::kKindStft, 0, 0);
+  run_grid(grid, wpc, smem,
+           [&](float* sm, int tid) { spl::cta_load_fft_tables<NFFT>(ct, p.twiddle, p.window, p.win, sm, tid, wpc * 32); },
+           [&](float* sm, int block, int tid) { spl::spec_body<NFFT>(p, sm, block, tid, grid, wpc); });
   return SPL_OK;
 }
 

@@ -53,7 +53,7 @@ def test_twiddle_table_matches_native(lib):
 
 def _tr(**kw):
     t = _abi.SplTransform()
-    t.kind, t.n_fft, t.hop, t.win, t.frames_per_chunk, t.eps = 0, 1024, 120, 600, 4, 1e-7
+    t.kind, t.n_fft, t.hop, t.win, t.eps = 0, 1024, 120, 600, 1e-7
     for k, v in kw.items():
         setattr(t, k, v)
     return t
@@ -62,14 +62,16 @@ def _tr(**kw):
 def test_geometry(lib):
     g = _abi.SplGeometry()
     assert lib.spl_geometry_of(ctypes.byref(_tr()), 16, 48000, ctypes.byref(g)) == 0
-    assert (g.n_frames, g.n_bins, g.n_chunks, g.span, g.n_sums) == (401, 513, 101, 3 * 120 + 600, 3)
-    assert g.partial_count == 16 * 101 * 3 and g.gchunk_bytes == 16 * 101 * 960 * 8
-    assert g.smem_table_bytes == (2 * 1024 + 600) * 4 and 0 < g.smem_warp_bytes <= 32 * 1024
+    assert (g.n_frames, g.n_bins, g.n_sums) == (401, 513, 3)
+    assert g.partial_count == 16 * 401 * 3 and g.gframe_bytes == 16 * 401 * 600 * 8
+    assert g.smem_table_bytes == (2 * 32 * 33 + 600) * 4 and 0 < g.smem_warp_bytes <= 32 * 1024
+    assert lib.spl_geometry_of(ctypes.byref(_tr()), 256, 192000, ctypes.byref(g)) == 0
+    assert g.partial_count == 32768 * 3            # capped: one row per warp of the launch
 
 
 @pytest.mark.parametrize("kw,frag", [
     (dict(n_fft=768), "n_fft"), (dict(win=2000), "win"), (dict(hop=700), "hop"),
-    (dict(frames_per_chunk=0), "frames_per_chunk"), (dict(kind=7), "kind"),
+    (dict(kind=7), "kind"),
 ])
 def test_invalid_arguments_are_reported(lib, kw, frag):
     g = _abi.SplGeometry()
