@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 namespace {
@@ -67,6 +68,65 @@ int opt_in_smem(K kern, bool* configured) {
   if (!configured[dev]) {
     SPL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
     configured[dev] = true;
+  }
+  return SPL_OK;
+}
+
+// Side streams for the concurrent transforms of one spl_forward() call: created once per (thread, device), never
+// destroyed.  Fork/join is event based, so it is also legal while `stream` is being captured into a CUDA graph.
+// SPECLOSS_SERIAL=1 keeps everything on the caller's stream.
+struct SideStreams {
+  cudaStream_t s[SPL_MAX_TRANSFORMS];
+  cudaEvent_t fork, join[SPL_MAX_TRANSFORMS];
+  bool ready;
+};
+
+int side_streams(SideStreams** out) {
+  static thread_local SideStreams per_dev[64];
+  int dev = 0;
+  SPL_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return fail(SPL_E_INVALID, "device ordinal %d out of range", dev);
+  SideStreams& ss = per_dev[dev];
+  if (!ss.ready) {
+    SPL_CUDA(cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming));
+    for (int i = 1; i < SPL_MAX_TRANSFORMS; ++i) {
+      SPL_CUDA(cudaStreamCreateWithFlags(&ss.s[i], cudaStreamNonBlocking));
+      SPL_CUDA(cudaEventCreateWithFlags(&ss.join[i], cudaEventDisableTiming));
+    }
+    ss.ready = true;
+  }
+  *out = &ss;
+  return SPL_OK;
+}
+
+bool serial_mode() {
+  static const bool v = [] { const char* e = std::getenv("SPECLOSS_SERIAL"); return e && e[0] == '1'; }();
+  return v;
+}
+
+int spl_fork(void* stream, int n, void** streams) {
+  for (int i = 0; i < n; ++i) streams[i] = stream;
+  if (n < 2 || serial_mode()) return SPL_OK;
+  SideStreams* ss = nullptr;
+  int rc = side_streams(&ss);
+  if (rc) return rc;
+  SPL_CUDA(cudaEventRecord(ss->fork, static_cast<cudaStream_t>(stream)));
+  for (int i = 1; i < n; ++i) {
+    SPL_CUDA(cudaStreamWaitEvent(ss->s[i], ss->fork, 0));
+    streams[i] = ss->s[i];
+  }
+  return SPL_OK;
+}
+
+int spl_join(void* stream, int n, void** streams) {
+  if (n < 2 || serial_mode()) return SPL_OK;
+  SideStreams* ss = nullptr;
+  int rc = side_streams(&ss);
+  if (rc) return rc;
+  for (int i = 1; i < n; ++i) {
+    if (streams[i] == stream) continue;
+    SPL_CUDA(cudaEventRecord(ss->join[i], static_cast<cudaStream_t>(streams[i])));
+    SPL_CUDA(cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), ss->join[i], 0));
   }
   return SPL_OK;
 }

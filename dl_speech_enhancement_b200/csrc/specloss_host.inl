@@ -7,6 +7,8 @@
 //          same numbers: one row of partial sums per warp)
 //   template <int NFFT, int KIND, bool GRAD, int WIN_T> int spl_launch_transform(const spl::TransformParams&, int grid, int wpc, size_t smem, void* stream);
 //   template <int NFFT> int spl_launch_spec(const spl::SpecParams&, int grid, int wpc, size_t smem, void* stream);
+//   int spl_fork(void* stream, int n, void** streams);   -- streams[0] = stream, streams[1..n) run concurrently after
+//   int spl_join(void* stream, int n, void** streams);      everything queued on `stream` so far; join = stream waits for all
 //   int spl_launch_reduce(const spl::ReduceParams&, void* stream);
 //   int spl_launch_finalize(const spl::FinalizeParams&, void* stream);
 //   int spl_launch_reduce_finalize(const spl::ReduceFinalizeParams&, void* stream);
@@ -131,11 +133,28 @@ int32_t spl_forward(const spl_transform* ts, int32_t n, const float* x, const fl
     if (!t->window || !t->twiddle || !t->partials) return fail(SPL_E_INVALID, "transform %d: null window/twiddle/partials", r);
     if (t->kind == SPL_KIND_MEL && (!t->mel_tasks || !t->mel_entries || t->mel_rounds < 1 || t->mel_entry_rows < 1 || !t->bin_tab))
       return fail(SPL_E_INVALID, "transform %d: null mel table", r);
+  }
+  // The transforms are independent: each runs on its own stream, most expensive first, so that the CTAs of the
+  // next kernel take over the SMs one by one as the CTAs of the previous one retire (every kernel is one
+  // persistent CTA per SM; back to back on ONE stream each of them would drain completely before the next starts).
+  int order[SPL_MAX_TRANSFORMS];
+  double cost[SPL_MAX_TRANSFORMS];
+  for (int r = 0; r < n; ++r) {
+    order[r] = r;
+    cost[r] = (double)(1 + T / ts[r].hop) * ts[r].n_fft * (ts[r].kind == SPL_KIND_MEL ? 1.4 : 1.0);
+  }
+  for (int i = 1; i < n; ++i)
+    for (int j = i; j > 0 && cost[order[j]] > cost[order[j - 1]]; --j) { const int tmp = order[j]; order[j] = order[j - 1]; order[j - 1] = tmp; }
+  void* streams[SPL_MAX_TRANSFORMS];
+  int rc = spl_fork(stream, n, streams);
+  if (rc) return rc;
+  for (int i = 0; i < n; ++i) {
+    const spl_transform* t = ts + order[i];
     spl_geometry g;
     geometry(t, B, T, &g);
     int grid = 0, wpc = 0;
     rc = shape_of(t, B, T, &grid, &wpc);
-    if (rc) return rc;
+    if (rc) break;
     spl::TransformParams p;
     std::memset(&p, 0, sizeof(p));
     p.x = x; p.y = y; p.B = B; p.T = T;
@@ -150,10 +169,11 @@ int32_t spl_forward(const spl_transform* ts, int32_t n, const float* x, const fl
     p.mel_entry_rows = t->kind == SPL_KIND_MEL ? t->mel_entry_rows : 0;
     p.bin_tab = t->bin_tab;
     const size_t smem = (size_t)g.smem_table_bytes + (size_t)g.smem_warp_bytes * wpc;
-    rc = launch_any(p, t->n_fft, t->kind, t->gframes != nullptr, grid, wpc, smem, stream);
-    if (rc) return rc;
+    rc = launch_any(p, t->n_fft, t->kind, t->gframes != nullptr, grid, wpc, smem, streams[i]);
+    if (rc) break;
   }
-  return SPL_OK;
+  const int rc_join = spl_join(stream, n, streams);      // always re-join, also after a failed launch
+  return rc ? rc : rc_join;
 }
 
 int32_t spl_spectrogram(const float* x, int32_t B, int32_t T, int32_t n_fft, int32_t hop, int32_t win,

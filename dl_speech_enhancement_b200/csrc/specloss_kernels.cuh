@@ -41,11 +41,27 @@ __device__ __forceinline__ float spl_fast_log2(float x) {
 #ifndef SPL_MAX_WARPS_SMALL
 #define SPL_MAX_WARPS_SMALL 16
 #endif
+// Code-size experiments, all measured slower on B200 (gpurun_out/r1k_variants.txt) because ptxas starts spilling
+// the tap registers: 2048-point kernels with rolled row loops (rows parked in the slot), and the two R-point
+// codelet sites merged into a 2-iteration loop.
+#ifndef SPL_PARK_2048
+#define SPL_PARK_2048 0
+#endif
+#ifndef SPL_PHASE_LOOP
+#define SPL_PHASE_LOOP 0
+#endif
+// Third experiment, also slower (gpurun_out/r1k_sync.txt: stft-2048 206 -> 232 us at 32 x 4 s): a CTA barrier once
+// per frame round in the 2048-point kernels, meant to keep the warps of a CTA in the same region of the ~100 KB
+// instruction stream (shared instruction-cache lines); lock-stepped warps contend for the same pipe instead.
+#ifndef SPL_SYNC_2048
+#define SPL_SYNC_2048 0
+#endif
 
 namespace spl {
 
 constexpr int kKindStft = 0;
 constexpr int kKindMel = 1;
+constexpr int kPhaseUnroll = SPL_PHASE_LOOP ? 1 : 2;   // 1: the two phases of a frame share one copy of the R-point codelet
 
 // ---------------------------------------------------------------------------------------------
 // FFT geometry: N = L * R.  A group of L lanes owns one frame; every lane holds R complex points.
@@ -69,6 +85,12 @@ template <int NFFT> struct Geo {
   static constexpr int FPW = 32 / L;        // frames in flight per warp
   static constexpr int HL = L / 2;          // columns kept in registers per row (bins below N/2)
   static constexpr int SLOT_F2 = R * PITCH; // float2 per frame slot
+  // Rows per lane held in registers between the passes.  2048-point transforms (two 32-column rows per lane) keep
+  // ONE row at a time and park the other in its own slot positions: their row loops stay rolled, which halves the
+  // code (an unrolled kernel is ~100 KB of SASS against a 32 KB instruction cache: no_instruction stalls 1.2-2.0
+  // per issue, profiles r1j).
+  static constexpr bool PARK = SPL_PARK_2048 && NFFT == 2048;
+  static constexpr int AROWS = PARK ? 1 : RPL;
 };
 
 template <int P> struct Dft;
@@ -185,26 +207,25 @@ SPL_DEVICE void cta_load_tables(const TransformParams& p, float* smem, int tid, 
 // ---------------------------------------------------------------------------------------------
 // FFT passes
 // ---------------------------------------------------------------------------------------------
-// [region: fwd pass A]
-// Forward, first half: this lane's R points (element n = l + L*n2 in v[n2]) -> R-point DFT, twiddle, column l of
-// the slot.  Ends with the warp barrier that makes the rows readable.
+// [region: fwd twiddle + store]
+// Forward, after the in-lane R-point DFT of this lane's points (element n = l + L*n2 in v[n2]): twiddle, column l
+// of the slot.  Ends with the warp barrier that makes the rows readable.
 template <int NFFT>
-SPL_DEVICE void fwd_pass_a(float2 (&v)[Geo<NFFT>::R], float2* S, const float2* tw, int l) {
+SPL_DEVICE void fwd_store_cols(const float2 (&v)[Geo<NFFT>::R], float2* S, const float2* tw, int l) {
   using G = Geo<NFFT>;
-  Dft<G::R>::run(v);
 #pragma unroll
   for (int k2 = 0; k2 < G::R; ++k2) S[k2 * G::PITCH + l] = k2 > 0 ? cmul(v[k2], tw[k2 * G::PITCH + l]) : v[0];
   __syncwarp();
 }
 
 // [region: fwd pass B]
-// Forward, second half, for the rows l + L*j of this lane: L-point DFT of the row.  Columns < L/2 (bins below
-// N/2) stay in registers (A); columns >= L/2 go back to the row in place, where the lane owning the mirror row
-// R - row picks them up.  Ends with the warp barrier that publishes them.
+// Forward, second half, for the rows l + L*j of this lane: L-point DFT of the row.  Columns >= L/2 go back to the
+// row in place, where the lane owning the mirror row R - row picks them up; columns < L/2 (bins below N/2) stay in
+// registers (A) -- or, PARK, go back to the row as well.  Ends with the warp barrier that publishes them.
 template <int NFFT>
-SPL_DEVICE void fwd_pass_b(float2 (&A)[Geo<NFFT>::RPL][Geo<NFFT>::HL], float2* S, int l) {
+SPL_DEVICE void fwd_pass_b(float2 (&A)[Geo<NFFT>::AROWS][Geo<NFFT>::HL], float2* S, int l) {
   using G = Geo<NFFT>;
-#pragma unroll
+#pragma unroll(G::PARK ? 1 : G::RPL)
   for (int j = 0; j < G::RPL; ++j) {
     float2* row = S + (l + G::L * j) * G::PITCH;
     float2 b[G::L];
@@ -212,7 +233,10 @@ SPL_DEVICE void fwd_pass_b(float2 (&A)[Geo<NFFT>::RPL][Geo<NFFT>::HL], float2* S
     for (int n1 = 0; n1 < G::L; ++n1) b[n1] = row[n1];
     Dft<G::L>::run(b);
 #pragma unroll
-    for (int k1 = 0; k1 < G::HL; ++k1) A[j][k1] = b[k1];
+    for (int k1 = 0; k1 < G::HL; ++k1) {
+      if (G::PARK) row[k1] = b[k1];
+      else         A[j][k1] = b[k1];
+    }
 #pragma unroll
     for (int k1 = G::HL; k1 < G::L; ++k1) row[k1] = b[k1];
   }
@@ -228,19 +252,22 @@ SPL_DEVICE float2* mirror_ptr(float2* S, int row) {
 }
 
 // [region: inv pass B]
-// Inverse, first half: gradient spectrum rows (columns < L/2 in A, columns >= L/2 in the slot) -> swapped
-// components -> L-point DFT -> twiddle -> back to the row.  Ends with a warp barrier.
+// Inverse, first half: gradient spectrum rows (columns < L/2 in A -- PARK: in the slot --, columns >= L/2 in the
+// slot) -> swapped components -> L-point DFT -> twiddle -> back to the row.  Ends with a warp barrier.
 template <int NFFT>
-SPL_DEVICE void inv_pass_b(float2 (&A)[Geo<NFFT>::RPL][Geo<NFFT>::HL], float2* S, const float2* tw, int l) {
+SPL_DEVICE void inv_pass_b(float2 (&A)[Geo<NFFT>::AROWS][Geo<NFFT>::HL], float2* S, const float2* tw, int l) {
   using G = Geo<NFFT>;
-#pragma unroll
+#pragma unroll(G::PARK ? 1 : G::RPL)
   for (int j = 0; j < G::RPL; ++j) {
     const int r = l + G::L * j;
     float2* row = S + r * G::PITCH;
     const float2* twr = tw + r * G::PITCH;
     float2 b[G::L];
 #pragma unroll
-    for (int k1 = 0; k1 < G::HL; ++k1) b[k1] = make_float2(A[j][k1].y, A[j][k1].x);
+    for (int k1 = 0; k1 < G::HL; ++k1) {
+      const float2 h = G::PARK ? row[k1] : A[G::PARK ? 0 : j][k1];
+      b[k1] = make_float2(h.y, h.x);
+    }
 #pragma unroll
     for (int k1 = G::HL; k1 < G::L; ++k1) { const float2 h = row[k1]; b[k1] = make_float2(h.y, h.x); }
     Dft<G::L>::run(b);
@@ -249,17 +276,6 @@ SPL_DEVICE void inv_pass_b(float2 (&A)[Geo<NFFT>::RPL][Geo<NFFT>::HL], float2* S
     for (int n1 = 1; n1 < G::L; ++n1) row[n1] = cmul(b[n1], twr[n1]);
   }
   __syncwarp();
-}
-
-// [region: inv pass A]
-// Inverse, second half: column l of the slot -> R-point DFT.  v[n2] then holds sample n = l + L*n2 of the two real
-// sequences with swapped components: (.y, .x) = (Re, Im) of the un-normalised inverse transform.
-template <int NFFT>
-SPL_DEVICE void inv_pass_a(float2 (&v)[Geo<NFFT>::R], const float2* S, int l) {
-  using G = Geo<NFFT>;
-#pragma unroll
-  for (int m2 = 0; m2 < G::R; ++m2) v[m2] = S[m2 * G::PITCH + l];
-  Dft<G::R>::run(v);
 }
 
 // [region: tap load]
@@ -319,27 +335,23 @@ SPL_DEVICE bool load_taps(float2 (&v)[Geo<NFFT>::R], const float* __restrict__ x
 // GRAD -- the un-scaled gradient spectra:
 //   H[k] = w/2 (alpha + i beta) (2X),  H[N-k] = w/2 (alpha + i beta) conj(2X),  w = 1/2 (1 when k mirrors itself)
 //   alpha = gate (Ax - Ay)/Ax  (spectral convergence),  beta = gate sign(Ax - Ay)/Ax^2  (log magnitude).
-// EQ: prediction and target frames are bit-identical, Y := X, every difference term is exactly zero.
-template <bool GRAD, bool EQ>
-SPL_DEVICE void stft_pair(float2 a, float2 bm, bool self, float eps4, float& s1, float& s2, float& s3, float2& ha,
-                          float2& hb) {
+// eq: prediction and target frames are bit-identical; Y := X then makes every difference term exactly zero
+// (d = 0, lg2(p) - lg2(p) = 0, sign(0) = 0).
+template <bool GRAD>
+SPL_DEVICE void stft_pair(float2 a, float2 bm, bool self, bool eq, float eps4, float& s1, float& s2, float& s3,
+                          float2& ha, float2& hb) {
   const float2 x2 = __fadd2_rn(a, make_float2(bm.x, -bm.y));
+  float2 y2 = __fadd2_rn(make_float2(a.y, -a.x), make_float2(bm.y, bm.x));
+  y2 = eq ? x2 : y2;
   const float px = fmaf(x2.x, x2.x, x2.y * x2.y);
-  const float pxc = fmaxf(px, eps4);
-  if (EQ) {
-    s2 += pxc;
-    ha = hb = make_float2(0.f, 0.f);
-    return;
-  }
-  const float2 y2 = __fadd2_rn(make_float2(a.y, -a.x), make_float2(bm.y, bm.x));
   const float py = fmaf(y2.x, y2.x, y2.y * y2.y);
-  const float pyc = fmaxf(py, eps4);
+  const float pxc = fmaxf(px, eps4), pyc = fmaxf(py, eps4);
   const float rx = spl_fast_rsqrt(pxc), ry = spl_fast_rsqrt(pyc);
   const float ax = __fmul_rn(pxc, rx), ay = __fmul_rn(pyc, ry);       // 2 Ax, 2 Ay
   const float d = __fsub_rn(ay, ax);                                  // never contracted: 0 when pxc == pyc
   s1 = fmaf(d, d, s1);
   s2 += pyc;
-  s3 += fabsf(spl_fast_log2(pyc * rx * rx));
+  s3 += fabsf(__fsub_rn(spl_fast_log2(pyc), spl_fast_log2(pxc)));
   if (GRAD) {
     const float wq = self ? 0.5f : 0.25f;
     const float rxg = px >= eps4 ? rx : 0.f;                          // clamp gate of the reference
@@ -352,49 +364,52 @@ SPL_DEVICE void stft_pair(float2 a, float2 bm, bool self, float eps4, float& s1,
   }
 }
 
-// all pairs of one lane.  In: A = columns < L/2 of this lane's rows (registers), mirror halves in the slot.
-// Out (GRAD): H in A and in the mirror halves of the slot.
-template <int NFFT, bool GRAD, bool EQ>
-SPL_DEVICE void stft_epilogue(float2 (&A)[Geo<NFFT>::RPL][Geo<NFFT>::HL], float2* S, int l, float eps4, float& s1,
-                              float& s2, float& s3) {
+// all pairs of one lane.  In: columns < L/2 of this lane's rows in A (PARK: in the slot), mirror halves in the slot.
+// Out (GRAD): H in the same places.
+template <int NFFT, bool GRAD>
+SPL_DEVICE void stft_epilogue(float2 (&A)[Geo<NFFT>::AROWS][Geo<NFFT>::HL], float2* S, int l, bool eq, float eps4,
+                              float& s1, float& s2, float& s3) {
   using G = Geo<NFFT>;
-#pragma unroll
+#pragma unroll(G::PARK ? 1 : G::RPL)
   for (int j = 0; j < G::RPL; ++j) {
     const int row = l + G::L * j;
     float2* pb = mirror_ptr<NFFT>(S, row);
+    float2* arow = S + row * G::PITCH;
 #pragma unroll
     for (int k1 = 0; k1 < G::HL; ++k1) {
-      const float2 a = A[j][k1];
+      const float2 a = G::PARK ? arow[k1] : A[G::PARK ? 0 : j][k1];
       float2 bm = pb[-k1];
       bool self = false;
-      if (j == 0 && k1 == 0) {                       // bin 0 (row 0) mirrors itself
+      if (k1 == 0) {                                 // bin 0 (row 0) mirrors itself
         self = row == 0;
         bm = self ? a : bm;
       }
       float2 ha, hb;
-      stft_pair<GRAD, EQ>(a, bm, self, eps4, s1, s2, s3, ha, hb);
-      if (GRAD) { A[j][k1] = ha; pb[-k1] = hb; }
+      stft_pair<GRAD>(a, bm, self, eq, eps4, s1, s2, s3, ha, hb);
+      if (GRAD) {
+        if (G::PARK) arow[k1] = ha;
+        else         A[G::PARK ? 0 : j][k1] = ha;
+        pb[-k1] = hb;
+      }
     }
   }
   if (l == 0) {                                      // bin N/2 = (row 0, column L/2) mirrors itself
     const float2 a = S[G::HL];
     float2 ha, hb;
-    stft_pair<GRAD, EQ>(a, a, true, eps4, s1, s2, s3, ha, hb);
+    stft_pair<GRAD>(a, a, true, eq, eps4, s1, s2, s3, ha, hb);
     if (GRAD) S[G::HL] = ha;
   }
 }
 
 // [region: mel epilogue]
-// mel, pass 1 on one mirror pair: 2X[k] and the amplitudes (Ax, Ay) = sqrt(max(|.|^2, eps))
-template <bool EQ>
-SPL_DEVICE void mel_pair_amp(float2 a, float2 bm, float eps4, float2& x2, float2& amp) {
+// mel, pass 1 on one mirror pair: 2X[k] and the amplitudes (Ax, Ay) = sqrt(max(|.|^2, eps)); eq: Y := X
+SPL_DEVICE void mel_pair_amp(float2 a, float2 bm, bool eq, float eps4, float2& x2, float2& amp) {
   x2 = __fadd2_rn(a, make_float2(bm.x, -bm.y));
-  const float2 y2 = EQ ? x2 : __fadd2_rn(make_float2(a.y, -a.x), make_float2(bm.y, bm.x));
+  float2 y2 = __fadd2_rn(make_float2(a.y, -a.x), make_float2(bm.y, bm.x));
+  y2 = eq ? x2 : y2;
   const float pxc = fmaxf(fmaf(x2.x, x2.x, x2.y * x2.y), eps4);
-  const float pyc = EQ ? pxc : fmaxf(fmaf(y2.x, y2.x, y2.y * y2.y), eps4);
-  const float ax = 0.5f * pxc * spl_fast_rsqrt(pxc);
-  const float ay = EQ ? ax : 0.5f * pyc * spl_fast_rsqrt(pyc);
-  amp = make_float2(ax, ay);
+  const float pyc = fmaxf(fmaf(y2.x, y2.x, y2.y * y2.y), eps4);
+  amp = __fmul2_rn(make_float2(0.5f * pxc, 0.5f * pyc), make_float2(spl_fast_rsqrt(pxc), spl_fast_rsqrt(pyc)));
 }
 
 // mel, pass 3 on one bin: gA[k] = gM[m0] W[k,m0] + gM[m0+1] W[k,m0+1];  H[k] = w gA gate / Ax * X
@@ -407,10 +422,11 @@ SPL_DEVICE float2 mel_bin_grad(float2 x2, bool self, int4 bt, const float2* msum
 }
 
 // mel epilogue of one frame: amplitudes -> banded projection -> log-mel L1 -> (GRAD) gradient spectrum.
-// In: A = Z columns < L/2 (registers), mirror halves in the slot.  Out (GRAD): H in A / mirror halves.
-// The amplitudes of bin k <= N/2 are parked at the bin's own slot position (columns <= L/2 are free: they live in A).
+// In: Z columns < L/2 in A (PARK: in the slot), mirror halves in the slot.  Out (GRAD): H in the same places.
+// The amplitudes of bin k <= N/2 are parked at the bin's own slot position; 2X[k] waits for pass 3 in A (PARK: in
+// the mirror position, whose Z[N-k] is consumed by then).
 template <int NFFT, bool GRAD>
-SPL_DEVICE void mel_epilogue(float2 (&A)[Geo<NFFT>::RPL][Geo<NFFT>::HL], float2* S, float2* msum, int l, bool frame_equal,
+SPL_DEVICE void mel_epilogue(float2 (&A)[Geo<NFFT>::AROWS][Geo<NFFT>::HL], float2* S, float2* msum, int l, bool eq,
                              bool active, const TransformParams& p, const int4* mel_tasks, const int2* mel_entries,
                              const int4* bin_tab, float& s1) {
   using G = Geo<NFFT>;
@@ -418,28 +434,27 @@ SPL_DEVICE void mel_epilogue(float2 (&A)[Geo<NFFT>::RPL][Geo<NFFT>::HL], float2*
   const float eps4 = 4.f * p.eps;
   float2 xh = make_float2(0.f, 0.f);                   // 2X[N/2], lane 0
   // pass 1
-#pragma unroll
+#pragma unroll(G::PARK ? 1 : G::RPL)
   for (int j = 0; j < G::RPL; ++j) {
     const int row = l + L * j;
-    const float2* pb = mirror_ptr<NFFT>(S, row);
+    float2* pb = mirror_ptr<NFFT>(S, row);
     float2* arow = S + row * G::PITCH;
 #pragma unroll
     for (int k1 = 0; k1 < G::HL; ++k1) {
-      const float2 a = A[j][k1];
+      const float2 a = G::PARK ? arow[k1] : A[G::PARK ? 0 : j][k1];
       float2 bm = pb[-k1];
-      if (j == 0 && k1 == 0) bm = (row == 0) ? a : bm;
+      if (k1 == 0) bm = (row == 0) ? a : bm;
       float2 x2, amp;
-      if (frame_equal) mel_pair_amp<true>(a, bm, eps4, x2, amp);
-      else             mel_pair_amp<false>(a, bm, eps4, x2, amp);
-      A[j][k1] = x2;
+      mel_pair_amp(a, bm, eq, eps4, x2, amp);
+      if (G::PARK) pb[-k1] = x2;
+      else         A[G::PARK ? 0 : j][k1] = x2;
       arow[k1] = amp;
     }
   }
   if (l == 0) {
     const float2 a = S[G::HL];
     float2 amp;
-    if (frame_equal) mel_pair_amp<true>(a, a, eps4, xh, amp);
-    else             mel_pair_amp<false>(a, a, eps4, xh, amp);
+    mel_pair_amp(a, a, eq, eps4, xh, amp);
     S[G::HL] = amp;
   }
   __syncwarp();
@@ -479,15 +494,19 @@ SPL_DEVICE void mel_epilogue(float2 (&A)[Geo<NFFT>::RPL][Geo<NFFT>::HL], float2*
   __syncwarp();
   if (GRAD) {
     // pass 3: gA[k] = sum_m gM[m] W[k,m] (<= 2 adjacent rows), H[k] = w gA gate / Ax * X, H[N-k] = conj H[k]
-#pragma unroll
+#pragma unroll(G::PARK ? 1 : G::RPL)
     for (int j = 0; j < G::RPL; ++j) {
       const int row = l + L * j;
       float2* pb = mirror_ptr<NFFT>(S, row);
+      float2* arow = S + row * G::PITCH;
+      const int4* bt = bin_tab + row;
 #pragma unroll
       for (int k1 = 0; k1 < G::HL; ++k1) {
-        const bool self = (j == 0 && k1 == 0) && row == 0;
-        const float2 hk = mel_bin_grad(A[j][k1], self, bin_tab[row + R * k1], msum, eps4, active);
-        A[j][k1] = hk;
+        const bool self = k1 == 0 && row == 0;
+        const float2 x2 = G::PARK ? pb[-k1] : A[G::PARK ? 0 : j][k1];
+        const float2 hk = mel_bin_grad(x2, self, bt[R * k1], msum, eps4, active);
+        if (G::PARK) arow[k1] = hk;
+        else         A[G::PARK ? 0 : j][k1] = hk;
         pb[-k1] = make_float2(hk.x, -hk.y);
       }
     }
@@ -528,43 +547,54 @@ SPL_DEVICE void transform_body(const TransformParams& p, float* smem, int block,
   double d1 = 0.0, d2 = 0.0, d3 = 0.0;      // this lane's share of the sums (stft: 4*S1, 4*S2, S3/(0.5 ln 2); mel: S4)
 
   // [region: frame loop]
-  for (int base = (block * wpc + warp) * FPW; base < total; base += grid * wpc * FPW) {
+  constexpr bool CTA_SYNC = SPL_SYNC_2048 && NFFT == 2048;
+  const int stride = grid * wpc * FPW;
+  const int rounds = (total + stride - 1) / stride;
+  for (int round = 0; round < rounds; ++round) {
+    const int base = round * stride + (block * wpc + warp) * FPW;
+    if (CTA_SYNC) __syncthreads();
+    if (base >= total) continue;
     const int item = base + h;
     const bool active = item < total;
     const int b = active ? item / p.n_frames : 0;
     const int t = active ? item - b * p.n_frames : 0;
-    const float* __restrict__ xb = p.x + (size_t)b * p.T;
-    const float* __restrict__ yb = p.y + (size_t)b * p.T;
     float s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    float2 A[G::RPL][G::HL];
-    bool frame_equal;
-    {
-      float2 v[R];
-      const bool same = load_taps<NFFT, WIN_T>(v, xb, yb, p.T, t * p.hop - HALF, win, left, wtab, l, active);
-      // A frame whose prediction and target taps are bit-identical must contribute exactly zero (the reference
-      // returns sc = mag = mel = 0 and a zero gradient for x == y); the packed FFT would leave ~1e-7 of rounding
-      // asymmetry between X and Y, so such frames reuse X for Y.
-      const unsigned eq_bits = __ballot_sync(0xffffffffu, same);
-      frame_equal = (eq_bits & grp_mask) == grp_mask;
-      fwd_pass_a<NFFT>(v, S, tw, l);
-    }
-    fwd_pass_b<NFFT>(A, S, l);
-    if (KIND == kKindStft) {
-      const float eps4 = 4.f * p.eps;
-      if (frame_equal) stft_epilogue<NFFT, GRAD, true>(A, S, l, eps4, s1, s2, s3);
-      else             stft_epilogue<NFFT, GRAD, false>(A, S, l, eps4, s1, s2, s3);
-      __syncwarp();      // mirror halves: all reads (and the H written back over them) done before the slot is reused
-    } else {
-      mel_epilogue<NFFT, GRAD>(A, S, msum, l, frame_equal, active, p, mel_tasks, mel_entries, bin_tab, s1);
-    }
-    if (active) { d1 += (double)s1; d2 += (double)s2; d3 += (double)s3; }
-    if (GRAD) {
-      inv_pass_b<NFFT>(A, S, tw, l);
-      float2 v[R];
-      inv_pass_a<NFFT>(v, S, l);
-      // [region: window + store]
-      // windowed frame gradient -> this frame's slot in HBM (coalesced; one writer per element)
-      if (active) {
+    // Two phases share ONE copy of the R-point codelet: 0 = forward transform + epilogue (+ first half of the
+    // inverse), 1 = second half of the inverse + windowed store.
+#pragma unroll(kPhaseUnroll)
+    for (int phase = 0; phase < (GRAD ? 2 : 1); ++phase) {
+      float2 v[R];              // defined afresh by each phase: nothing is carried around the loop in registers
+      bool frame_equal = false;
+      if (phase == 0) {
+        const bool same = load_taps<NFFT, WIN_T>(v, p.x + (size_t)b * p.T, p.y + (size_t)b * p.T, p.T,
+                                                 t * p.hop - HALF, win, left, wtab, l, active);
+        // A frame whose prediction and target taps are bit-identical must contribute exactly zero (the reference
+        // returns sc = mag = mel = 0 and a zero gradient for x == y); the packed FFT would leave ~1e-7 of rounding
+        // asymmetry between X and Y, so such frames reuse X for Y.
+        const unsigned eq_bits = __ballot_sync(0xffffffffu, same);
+        frame_equal = (eq_bits & grp_mask) == grp_mask;
+      } else {
+        // [region: inv column load]
+#pragma unroll
+        for (int m2 = 0; m2 < R; ++m2) v[m2] = S[m2 * G::PITCH + l];
+      }
+      Dft<R>::run(v);
+      if (phase == 0) {
+        fwd_store_cols<NFFT>(v, S, tw, l);
+        float2 A[G::AROWS][G::HL];
+        fwd_pass_b<NFFT>(A, S, l);
+        if (KIND == kKindStft) {
+          stft_epilogue<NFFT, GRAD>(A, S, l, frame_equal, 4.f * p.eps, s1, s2, s3);
+          __syncwarp();    // mirror halves: all reads (and the H written back over them) done before the slot is reused
+        } else {
+          mel_epilogue<NFFT, GRAD>(A, S, msum, l, frame_equal, active, p, mel_tasks, mel_entries, bin_tab, s1);
+        }
+        if (active) { d1 += (double)s1; d2 += (double)s2; d3 += (double)s3; }
+        if (GRAD) inv_pass_b<NFFT>(A, S, tw, l);
+      } else if (active) {
+        // [region: window + store]
+        // v[n2] = sample n = l + L*n2 of the two real gradient sequences with swapped components: (.y, .x) = (u, v).
+        // Windowed frame gradient -> this frame's slot in HBM (coalesced; one writer per element).
         float2* out2 = reinterpret_cast<float2*>(p.gframes) + (size_t)item * win;
         float* out1 = reinterpret_cast<float*>(p.gframes) + (size_t)item * win;
         const float* wp = wtab + (l - left);
@@ -637,7 +667,7 @@ SPL_DEVICE void spec_body(const SpecParams& p, float* smem, int block, int tid, 
     const int t = 2 * pr;
     const bool second = active && (t + 1 < p.n_frames);
     const float* __restrict__ xb = p.x + (size_t)b * p.T;
-    float2 A[G::RPL][G::HL];
+    float2 A[G::AROWS][G::HL];
     {
       float2 v[R];
 #pragma unroll
@@ -652,20 +682,22 @@ SPL_DEVICE void spec_body(const SpecParams& p, float* smem, int block, int tid, 
         }
         v[n2] = make_float2(a0, a1);
       }
-      fwd_pass_a<NFFT>(v, S, tw, l);
+      Dft<R>::run(v);
+      fwd_store_cols<NFFT>(v, S, tw, l);
     }
     fwd_pass_b<NFFT>(A, S, l);
     float* o0 = p.out + ((size_t)b * p.n_frames + t) * p.ld;
     float* o1 = o0 + p.ld;
-#pragma unroll
+#pragma unroll(G::PARK ? 1 : G::RPL)
     for (int j = 0; j < G::RPL; ++j) {
       const int row = l + L * j;
       const float2* pb = mirror_ptr<NFFT>(S, row);
+      const float2* arow = S + row * G::PITCH;
 #pragma unroll
       for (int k1 = 0; k1 < G::HL; ++k1) {
-        const float2 a = A[j][k1];
+        const float2 a = G::PARK ? arow[k1] : A[G::PARK ? 0 : j][k1];
         float2 bm = pb[-k1];
-        if (j == 0 && k1 == 0) bm = (row == 0) ? a : bm;
+        if (k1 == 0) bm = (row == 0) ? a : bm;
         const float2 x2 = __fadd2_rn(a, make_float2(bm.x, -bm.y));                           // 2 X_t[k]
         const float2 y2 = __fadd2_rn(make_float2(a.y, -a.x), make_float2(bm.y, bm.x));       // 2 X_{t+1}[k]
         const float p0 = fmaxf(fmaf(x2.x, x2.x, x2.y * x2.y), eps4);

@@ -51,6 +51,12 @@ int spl_launch_shape(int, size_t, size_t, long long items, int* grid, int* wpc) 
   return SPL_OK;
 }
 
+int spl_fork(void* stream, int n, void** streams) {
+  for (int i = 0; i < n; ++i) streams[i] = stream;
+  return SPL_OK;
+}
+int spl_join(void*, int, void**) { return SPL_OK; }
+
 template <typename Load, typename Body>
 void run_grid(int grid, int wpc, size_t smem_bytes, Load&& load, Body&& body) {
   const size_t words = smem_bytes / 4;
