@@ -31,7 +31,7 @@ def test_band_tables_reproduce_matrix(sr, n_fft, n_mels, fmin, fmax):
     t = {k: v.numpy() for k, v in mel_tables(w, n_fft).items()}
     tasks = t["mel_tasks"].reshape(-1, lanes, 4)
     entries = t["mel_entries"].reshape(-1, lanes, 2)
-    slot_to_bin = {(lanes if k == 0 else slot_offset(n_fft, n_fft - k)): k for k in range(w.shape[0])}
+    slot_to_bin = {slot_offset(n_fft, k): k for k in range(w.shape[0])}    # natural position of bin k in the frame slot
     assert len(slot_to_bin) == w.shape[0]           # amplitude slots are distinct
     rebuilt = np.zeros_like(w)
     seen = set()
