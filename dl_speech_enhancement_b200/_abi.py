@@ -15,7 +15,7 @@ from ctypes import POINTER, c_char_p, c_double, c_float, c_int32, c_int64, c_voi
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libspecloss.so")
 CSRC = os.path.join(_HERE, "csrc")
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 SPL_KIND_STFT = 0
 SPL_KIND_MEL = 1
@@ -47,7 +47,7 @@ class SplGeometry(ctypes.Structure):
 
 
 EXPORTS = ("spl_abi_version", "spl_last_error", "spl_fill_twiddle", "spl_geometry_of", "spl_forward",
-           "spl_reduce", "spl_finalize", "spl_reduce_finalize", "spl_backward", "spl_spectrogram")
+           "spl_reduce", "spl_finalize", "spl_reduce_finalize", "spl_backward", "spl_spectrogram", "spl_mel_project")
 
 
 class SpecLossError(RuntimeError):
@@ -79,7 +79,10 @@ def bind(lib: ctypes.CDLL) -> ctypes.CDLL:
                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.spl_spectrogram.restype = c_int32
     lib.spl_spectrogram.argtypes = [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p,
-                                    c_float, c_void_p, c_int32, c_void_p]
+                                    c_float, c_void_p, c_void_p, c_int32, c_void_p]
+    lib.spl_mel_project.restype = c_int32
+    lib.spl_mel_project.argtypes = [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_int32, c_int32, c_int32,
+                                    c_float, c_float, c_void_p, c_void_p]
     ver = lib.spl_abi_version()
     if ver != ABI_VERSION:
         raise SpecLossError(f"libspecloss ABI version {ver}, expected {ABI_VERSION}")
@@ -102,7 +105,7 @@ def build_library(verbose: bool = False) -> str:
     if not os.path.exists(nvcc):
         raise SpecLossError("nvcc not found; libspecloss.so cannot be built")
     srcs = [os.path.join(CSRC, f) for f in ("specloss.cu", "specloss_kernels.cuh", "specloss_host.inl",
-                                            "fft_codelets.cuh")]
+                                            "fft_codelets.cuh", "melgemm.cuh")]
     hdr = os.path.join(os.path.dirname(_HERE), "include", "specloss.h")
     newest = max(os.path.getmtime(p) for p in srcs + [hdr])
     if os.path.exists(LIB_PATH) and os.path.getmtime(LIB_PATH) >= newest:

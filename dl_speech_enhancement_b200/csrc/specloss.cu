@@ -2,6 +2,7 @@
 // Kernels: specloss_kernels.cuh.  Argument checking / parameter assembly: specloss_host.inl.
 #include "../../include/specloss.h"
 #include "specloss_kernels.cuh"
+#include "melgemm.cuh"
 
 #include <cmath>
 #include <cstdarg>
@@ -149,6 +150,64 @@ int spl_launch_spec(const spl::SpecParams& p, int grid, int wpc, size_t smem, vo
   int rc = opt_in_smem(kern, configured);
   if (rc) return rc;
   kern<<<grid, wpc * 32, smem, static_cast<cudaStream_t>(stream)>>>(p);
+  SPL_CUDA(cudaGetLastError());
+  return SPL_OK;
+}
+
+// ---- tensor-core mel projection: TMA descriptors through the driver entry point (no link-time libcuda dependency) ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int encode_tiled_fn(EncodeTiledFn* out) {
+  static EncodeTiledFn cached = nullptr;
+  if (!cached) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    SPL_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+    if (q != cudaDriverEntryPointSuccess || !fn) return fail(SPL_E_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+    cached = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+  *out = cached;
+  return SPL_OK;
+}
+
+// (rows, ld) fp32 row-major, boxes of box_rows x 32 elements, 128-byte swizzle, zero fill outside
+int make_map(EncodeTiledFn enc, CUtensorMap* map, const float* base, long long rows, int ld, int box_rows) {
+  const cuuint64_t gdim[2] = {(cuuint64_t)ld, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)ld * 4};
+  const cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1u, 1u};
+  const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(SPL_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return SPL_OK;
+}
+
+int spl_launch_mel_gemm(const float* amp_hi, const float* amp_lo, const float* w_hi, const float* w_lo, int ld,
+                        const spl::MelGemmParams& p, void* stream) {
+  EncodeTiledFn enc = nullptr;
+  int rc = encode_tiled_fn(&enc);
+  if (rc) return rc;
+  CUtensorMap m_ah, m_al, m_wh, m_wl;
+  if ((rc = make_map(enc, &m_ah, amp_hi, p.rows, ld, spl::kGemmBM))) return rc;
+  if ((rc = make_map(enc, &m_al, amp_lo, p.rows, ld, spl::kGemmBM))) return rc;
+  if ((rc = make_map(enc, &m_wh, w_hi, p.n_pad, ld, p.n_pad))) return rc;
+  if ((rc = make_map(enc, &m_wl, w_lo, p.n_pad, ld, p.n_pad))) return rc;
+  const size_t smem = spl::mel_gemm_smem_bytes(p.n_pad);
+  // this kernel also has static shared memory (barriers): opt in to exactly what the largest tile set needs
+  static thread_local bool configured[64] = {false};
+  int dev = 0;
+  SPL_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return fail(SPL_E_INVALID, "device ordinal %d out of range", dev);
+  if (!configured[dev]) {
+    SPL_CUDA(cudaFuncSetAttribute(spl::mel_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)spl::mel_gemm_smem_bytes(spl::kGemmMaxN)));
+    configured[dev] = true;
+  }
+  const unsigned grid = (unsigned)((p.rows + spl::kGemmBM - 1) / spl::kGemmBM);
+  spl::mel_gemm_kernel<<<grid, 128, smem, static_cast<cudaStream_t>(stream)>>>(m_ah, m_al, m_wh, m_wl, p);
   SPL_CUDA(cudaGetLastError());
   return SPL_OK;
 }

@@ -9,6 +9,8 @@
 //   template <int NFFT> int spl_launch_spec(const spl::SpecParams&, int grid, int wpc, size_t smem, void* stream);
 //   int spl_fork(void* stream, int n, void** streams);   -- streams[0] = stream, streams[1..n) run concurrently after
 //   int spl_join(void* stream, int n, void** streams);      everything queued on `stream` so far; join = stream waits for all
+//   int spl_launch_mel_gemm(const float* amp_hi, const float* amp_lo, const float* w_hi, const float* w_lo, int ld,
+//                           const spl::MelGemmParams&, void* stream);
 //   int spl_launch_reduce(const spl::ReduceParams&, void* stream);
 //   int spl_launch_finalize(const spl::FinalizeParams&, void* stream);
 //   int spl_launch_reduce_finalize(const spl::ReduceFinalizeParams&, void* stream);
@@ -177,7 +179,8 @@ int32_t spl_forward(const spl_transform* ts, int32_t n, const float* x, const fl
 }
 
 int32_t spl_spectrogram(const float* x, int32_t B, int32_t T, int32_t n_fft, int32_t hop, int32_t win,
-                        const float* window, const float* twiddle, float eps, float* out, int32_t ld, void* stream) {
+                        const float* window, const float* twiddle, float eps, float* out, float* out_lo, int32_t ld,
+                        void* stream) {
   spl_transform t;
   std::memset(&t, 0, sizeof(t));
   t.kind = SPL_KIND_STFT; t.n_fft = n_fft; t.hop = hop; t.win = win;
@@ -200,11 +203,29 @@ int32_t spl_spectrogram(const float* x, int32_t B, int32_t T, int32_t n_fft, int
   std::memset(&p, 0, sizeof(p));
   p.x = x; p.B = B; p.T = T; p.hop = hop; p.win = win; p.left = (n_fft - win) / 2; p.n_frames = n_frames;
   p.n_pairs = n_pairs; p.eps = eps; p.window = window; p.twiddle = reinterpret_cast<const float2*>(twiddle);
-  p.out = out; p.ld = ld;
+  p.out = out; p.out_lo = out_lo; p.ld = ld;
   const size_t smem = table_bytes + warp_bytes * wpc;
   if (n_fft == 512) return spl_launch_spec<512>(p, grid, wpc, smem, stream);
   if (n_fft == 1024) return spl_launch_spec<1024>(p, grid, wpc, smem, stream);
   return spl_launch_spec<2048>(p, grid, wpc, smem, stream);
+}
+
+int32_t spl_mel_project(const float* amp_hi, const float* amp_lo, int64_t rows, int32_t ld,
+                        const float* w_hi, const float* w_lo, int32_t n_mels, int32_t n_pad, int32_t frames,
+                        float eps, float log_scale, float* out, void* stream) {
+  if (!amp_hi || !amp_lo || !w_hi || !w_lo || !out) return fail(SPL_E_INVALID, "spl_mel_project: null pointer");
+  if (rows < 1 || rows > 0x7fffff00LL) return fail(SPL_E_INVALID, "rows %lld out of range", (long long)rows);
+  if (frames < 1 || rows % frames) return fail(SPL_E_INVALID, "rows %lld is not a multiple of frames %d", (long long)rows, frames);
+  if (ld < 32 || ld % 32) return fail(SPL_E_INVALID, "ld %d must be a positive multiple of 32", ld);
+  if (n_mels < 1 || n_pad < n_mels || n_pad % 16 || n_pad > spl::kGemmMaxN)
+    return fail(SPL_E_INVALID, "n_mels %d / n_pad %d: n_pad must be a multiple of 16 in [n_mels, %d]", n_mels, n_pad, spl::kGemmMaxN);
+  if (((uintptr_t)amp_hi | (uintptr_t)amp_lo | (uintptr_t)w_hi | (uintptr_t)w_lo) & 15)
+    return fail(SPL_E_INVALID, "spl_mel_project: operands must be 16-byte aligned");
+  spl::MelGemmParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.rows = rows; p.n_mels = n_mels; p.n_pad = n_pad; p.frames = frames; p.kblocks = ld / 32;
+  p.eps = eps; p.log_scale = log_scale; p.out = out;
+  return spl_launch_mel_gemm(amp_hi, amp_lo, w_hi, w_lo, ld, p, stream);
 }
 
 static int build_reduce(const spl_transform* ts, int n, int B, int T, double* sums, spl::ReduceParams* rp) {

@@ -642,9 +642,25 @@ struct SpecParams {
   float eps;
   const float* window;
   const float2* twiddle;
-  float* out;            // (B, n_frames, ld)
+  float* out;            // (B, n_frames, ld); pad columns [n_fft/2+1, ld) are written as zeros
+  float* out_lo;         // null, or the second half of the TF32 split: out = tf32(A) exactly, out_lo = A - out
   int ld;
 };
+
+// A = hi + lo with hi exactly representable in TF32 (low 13 mantissa bits cleared); lo = A - hi is exact in fp32
+SPL_DEVICE void spec_store(float* o, float* o_lo, int k, float a) {
+  if (o_lo) {
+    int bits;
+    memcpy(&bits, &a, 4);
+    bits &= ~0x1fff;
+    float hi;
+    memcpy(&hi, &bits, 4);
+    o[k] = hi;
+    o_lo[k] = a - hi;
+  } else {
+    o[k] = a;
+  }
+}
 
 // [region: spectrogram]
 template <int NFFT>
@@ -686,8 +702,11 @@ SPL_DEVICE void spec_body(const SpecParams& p, float* smem, int block, int tid, 
       fwd_store_cols<NFFT>(v, S, tw, l);
     }
     fwd_pass_b<NFFT>(A, S, l);
-    float* o0 = p.out + ((size_t)b * p.n_frames + t) * p.ld;
+    const size_t orow = ((size_t)b * p.n_frames + t) * p.ld;
+    float* o0 = p.out + orow;
     float* o1 = o0 + p.ld;
+    float* l0 = p.out_lo ? p.out_lo + orow : nullptr;
+    float* l1 = p.out_lo ? l0 + p.ld : nullptr;
 #pragma unroll(G::PARK ? 1 : G::RPL)
     for (int j = 0; j < G::RPL; ++j) {
       const int row = l + L * j;
@@ -703,15 +722,19 @@ SPL_DEVICE void spec_body(const SpecParams& p, float* smem, int block, int tid, 
         const float p0 = fmaxf(fmaf(x2.x, x2.x, x2.y * x2.y), eps4);
         const float p1 = fmaxf(fmaf(y2.x, y2.x, y2.y * y2.y), eps4);
         const int k = row + R * k1;
-        if (active) o0[k] = 0.5f * p0 * spl_fast_rsqrt(p0);
-        if (second) o1[k] = 0.5f * p1 * spl_fast_rsqrt(p1);
+        if (active) spec_store(o0, l0, k, 0.5f * p0 * spl_fast_rsqrt(p0));
+        if (second) spec_store(o1, l1, k, 0.5f * p1 * spl_fast_rsqrt(p1));
       }
+    }
+    for (int k = NFFT / 2 + 1 + l; k < p.ld; k += L) {               // pad columns of the GEMM operand
+      if (active) { o0[k] = 0.f; if (l0) l0[k] = 0.f; }
+      if (second) { o1[k] = 0.f; if (l1) l1[k] = 0.f; }
     }
     if (l == 0) {                                                    // bin N/2
       const float2 a = S[G::HL];
       const float p0 = fmaxf(4.f * a.x * a.x, eps4), p1 = fmaxf(4.f * a.y * a.y, eps4);
-      if (active) o0[NFFT / 2] = 0.5f * p0 * spl_fast_rsqrt(p0);
-      if (second) o1[NFFT / 2] = 0.5f * p1 * spl_fast_rsqrt(p1);
+      if (active) spec_store(o0, l0, NFFT / 2, 0.5f * p0 * spl_fast_rsqrt(p0));
+      if (second) spec_store(o1, l1, NFFT / 2, 0.5f * p1 * spl_fast_rsqrt(p1));
     }
     __syncwarp();       // the slot's mirror halves are read above; the next pass-A store must wait for every lane
   }

@@ -152,6 +152,30 @@ class TransformPlan:
             raise RuntimeError("window buffer must be float32 with win_length taps (fp32-only implementation)")
 
 
+def gemm_ld(n_fft: int) -> int:
+    """Row pitch (floats) of the amplitude operand of the mel GEMM: n_fft/2+1 bins padded to whole 32-float k-blocks."""
+    return ((n_fft // 2 + 1) + 31) // 32 * 32
+
+
+def split_tf32(w: np.ndarray):
+    """w = hi + lo with hi exactly representable in TF32 (low 13 mantissa bits cleared) -- the 3xTF32 operand split."""
+    w = np.ascontiguousarray(w, dtype=np.float32)
+    hi = (w.view(np.uint32) & np.uint32(0xffffe000)).view(np.float32)
+    return hi, (w - hi).astype(np.float32)
+
+
+def mel_gemm_weights(melmat: np.ndarray, n_fft: int):
+    """(K, n_mels) filterbank -> (w_hi, w_lo): melmat^T zero-padded to (n_pad, ld), K-major like the amplitudes."""
+    k_bins, n_mels = melmat.shape
+    n_pad = (n_mels + 15) // 16 * 16
+    if n_pad > 128:
+        raise NotImplementedError("the tensor-core mel projection supports num_mels <= 128")
+    w = np.zeros((n_pad, gemm_ld(n_fft)), np.float32)
+    w[:n_mels, :k_bins] = melmat.T
+    hi, lo = split_tf32(w)
+    return torch.from_numpy(hi.copy()), torch.from_numpy(lo.copy())
+
+
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
@@ -308,20 +332,38 @@ class Engine:
         self.launches += st.n_launches
         return st
 
-    # -- explicit spectrogram ----------------------------------------------------------------------
+    # -- explicit spectrogram / log-mel spectrogram -----------------------------------------------------
     def spectrogram(self, x: torch.Tensor, n_fft: int, hop: int, win: int, window: torch.Tensor,
-                    twiddle: torch.Tensor, eps: float, ld: Optional[int] = None) -> torch.Tensor:
+                    twiddle: torch.Tensor, eps: float, ld: Optional[int] = None, split: bool = False):
         """(B, T) fp32 -> magnitude spectrogram (B, 1 + T // hop, n_fft // 2 + 1), the tensor the reference's
-        stft() returns (stft_loss.py:19-35).  With `ld` the rows are padded to ld floats (a view is returned)."""
+        stft() returns (stft_loss.py:19-35).  With `ld` the rows are padded to ld floats (zeros) and a view is
+        returned.  split=True returns (hi, lo) with hi = tf32(A) and lo = A - hi, full (B, F, ld) buffers: the
+        operands of mel_project()."""
         fft_geometry(n_fft)
         batch, t_len = x.shape
         n_bins = n_fft // 2 + 1
         ld = n_bins if ld is None else int(ld)
         out = torch.empty(batch, 1 + t_len // hop, ld, dtype=torch.float32, device=x.device)
+        lo = torch.empty_like(out) if split else None
         _abi.check(self.lib, self.lib.spl_spectrogram(x.data_ptr(), batch, t_len, n_fft, hop, win, window.data_ptr(),
-                                                      twiddle.data_ptr(), eps, out.data_ptr(), ld, self._stream(x)))
+                                                      twiddle.data_ptr(), eps, out.data_ptr(), _ptr(lo), ld,
+                                                      self._stream(x)))
         self.launches += 1
+        if split:
+            return out, lo
         return out if ld == n_bins else out[:, :, :n_bins]
+
+    def mel_project(self, amp_hi: torch.Tensor, amp_lo: torch.Tensor, w_hi: torch.Tensor, w_lo: torch.Tensor,
+                    n_mels: int, eps: float, log_scale: float) -> torch.Tensor:
+        """(B, F, ld) split amplitudes x (n_pad, ld) split melmat^T -> log-mel (B, n_mels, F) on the tensor cores:
+        log_b(clamp(matmul(x_amp, melmat), eps)).transpose(1, 2) of MelSpectrogram.forward (mel_loss.py:91-94)."""
+        batch, frames, ld = amp_hi.shape
+        out = torch.empty(batch, n_mels, frames, dtype=torch.float32, device=amp_hi.device)
+        _abi.check(self.lib, self.lib.spl_mel_project(amp_hi.data_ptr(), amp_lo.data_ptr(), batch * frames, ld,
+                                                      w_hi.data_ptr(), w_lo.data_ptr(), n_mels, w_hi.shape[0], frames,
+                                                      eps, log_scale, out.data_ptr(), self._stream(amp_hi)))
+        self.launches += 1
+        return out
 
     # -- backward --------------------------------------------------------------------------------
     def backward(self, st: ForwardState, g_sc: Optional[torch.Tensor], g_mag: Optional[torch.Tensor],

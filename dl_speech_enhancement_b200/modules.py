@@ -20,7 +20,7 @@ import torch
 
 from . import melfb
 from ._abi import SPL_KIND_MEL, SPL_KIND_STFT
-from .engine import TransformPlan, fft_geometry, mel_tables, twiddle_table
+from .engine import TransformPlan, fft_geometry, mel_gemm_weights, mel_tables, twiddle_table
 from .functional import spectral_losses
 
 
@@ -38,12 +38,39 @@ def _window(name: str, win_length: int) -> torch.Tensor:
     return getattr(torch, name)(win_length)          # as stft_loss.py:97 / mel_loss.py:49
 
 
+_TWIDDLES = {}
+
+
+def _twiddle_on(n_fft: int, device) -> torch.Tensor:
+    key = (n_fft, str(device))
+    if key not in _TWIDDLES:
+        _TWIDDLES[key] = twiddle_table(n_fft).to(device)
+    return _TWIDDLES[key]
+
+
+def _explicit_input(x: torch.Tensor, what: str) -> torch.Tensor:
+    if not x.is_cuda or x.dtype != torch.float32:
+        raise RuntimeError(f"{what}: fp32 CUDA tensors only (sm_100a kernels, no CPU fallback)")
+    if x.requires_grad and torch.is_grad_enabled():
+        raise NotImplementedError(
+            f"{what} is forward-only here: differentiate through MultiResolutionSTFTLoss / MultiMelSpectrogramLoss "
+            "(the fused loss kernels), or call it under torch.no_grad()")
+    return x.contiguous()
+
+
 def stft(x, fft_size, hop_size, win_length, window, eps=1e-7):
-    """Magnitude spectrogram (B, #frames, fft_size // 2 + 1) -- import-compatibility shim for
-    losses/stft_loss.py:19-35.  The fused CUDA path never materialises this tensor; this helper
-    is not on the hot path and simply evaluates the same definition with torch ops."""
-    x_stft = torch.stft(x, fft_size, hop_size, win_length, window, return_complex=True)
-    return torch.sqrt(torch.clamp(x_stft.real ** 2 + x_stft.imag ** 2, min=eps)).transpose(2, 1)
+    """Magnitude spectrogram (B, #frames, fft_size // 2 + 1) of x (B, T): losses/stft_loss.py:19-35, i.e.
+    sqrt(clamp(|torch.stft(x, fft_size, hop_size, win_length, window)|^2, eps)).transpose(2, 1), computed by the
+    sm_100a spectrogram kernel (two frames per complex FFT).  Forward only; the fused loss path never materialises
+    this tensor."""
+    from .engine import cuda_engine
+    x = _explicit_input(x, "stft()")
+    if x.dim() != 2:
+        raise RuntimeError(f"stft(): expected (B, T), got {tuple(x.shape)}")
+    if window.numel() != win_length:
+        raise RuntimeError("stft(): window must have win_length taps")
+    window = window.to(device=x.device, dtype=torch.float32).contiguous()
+    return cuda_engine().spectrogram(x, fft_size, hop_size, win_length, window, _twiddle_on(fft_size, x.device), eps)
 
 
 class SpectralConvergenceLoss(torch.nn.Module):
@@ -104,9 +131,10 @@ class MultiResolutionSTFTLoss(torch.nn.Module):
 
 
 class MelSpectrogram(torch.nn.Module):
-    """Log-mel spectrogram configuration holder (mel_loss.py:19-94): same ctor, same `window` and
-    `melmat` buffers.  Inside MultiMelSpectrogramLoss the spectrogram is never materialised; calling
-    this module directly evaluates the definition with torch ops (not the hot path)."""
+    """Log-mel spectrogram (mel_loss.py:19-94): same ctor, same `window` and `melmat` buffers.  forward(x) returns
+    the explicit (B, num_mels, #frames) tensor: spectrogram kernel + mel projection as a tcgen05 tensor-core GEMM
+    (3xTF32) with the clamp and the log fused into its epilogue; forward only.  Inside MultiMelSpectrogramLoss the
+    spectrogram is never materialised (banded projection inside the fused loss kernel)."""
 
     def __init__(self, fs=22050, fft_size=1024, hop_size=256, win_length=None, window="hann_window",
                  num_mels=80, fmin=80, fmax=7600, center=True, normalized=False, onesided=True,
@@ -138,6 +166,10 @@ class MelSpectrogram(torch.nn.Module):
         self.register_buffer("_twiddle", twiddle_table(fft_size), persistent=False)
         for name, t in mel_tables(mel.T, fft_size).items():
             self.register_buffer("_" + name, t, persistent=False)
+        if num_mels <= 128:
+            w_hi, w_lo = mel_gemm_weights(mel.T, fft_size)
+            self.register_buffer("_w_hi", w_hi, persistent=False)
+            self.register_buffer("_w_lo", w_lo, persistent=False)
 
     def plan(self) -> TransformPlan:
         tables = {n: getattr(self, "_" + n) for n in ("mel_tasks", "mel_entries", "bin_tab")}
@@ -146,12 +178,17 @@ class MelSpectrogram(torch.nn.Module):
                              self.window, self._twiddle, self.num_mels, inv_ln, tables)
 
     def forward(self, x):
+        from .engine import cuda_engine, gemm_ld
         if x.dim() == 3:
-            x = x.reshape(-1, x.size(2))
-        x_stft = torch.stft(x, self.fft_size, self.hop_size, self.win_length, self.window, return_complex=True)
-        x_amp = torch.sqrt(torch.clamp(x_stft.real ** 2 + x_stft.imag ** 2, min=self.eps)).transpose(2, 1)
-        x_mel = torch.clamp(torch.matmul(x_amp, self.melmat), min=self.eps)
-        return self.log(x_mel).transpose(1, 2)
+            x = x.reshape(-1, x.size(2))             # mel_loss.py:84-85
+        x = _explicit_input(x, "MelSpectrogram.forward()")
+        if not hasattr(self, "_w_hi"):
+            raise NotImplementedError("MelSpectrogram.forward(): the tensor-core projection supports num_mels <= 128")
+        eng = cuda_engine()
+        hi, lo = eng.spectrogram(x, self.fft_size, self.hop_size, self.win_length, self.window, self._twiddle, self.eps,
+                                 ld=gemm_ld(self.fft_size), split=True)
+        log_scale = 1.0 if self.log_base is None else 1.0 / math.log(self.log_base)
+        return eng.mel_project(hi, lo, self._w_hi, self._w_lo, self.num_mels, self.eps, log_scale)
 
 
 class MultiMelSpectrogramLoss(torch.nn.Module):

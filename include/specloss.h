@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SPL_ABI_VERSION 6
+#define SPL_ABI_VERSION 7
 
 #define SPL_OK 0
 #define SPL_E_INVALID (-1)   /* bad argument / outside the supported envelope */
@@ -106,11 +106,23 @@ int32_t spl_backward(const spl_transform* ts, int32_t n, int32_t B, int32_t T, c
                      const float* g_sc, const float* g_mag, const float* g_mel, float* dx, void* stream);
 
 /* Explicit magnitude spectrogram out[b, t, k] = sqrt(max(|STFT(x)[b, t, k]|^2, eps)), (B, 1 + T/hop, ld) with
- * ld >= n_fft/2 + 1 floats per frame: the tensor stft() returns (stft_loss.py:19-35) and the operand of the mel
- * projection in MelSpectrogram.forward (mel_loss.py:88-91).  Forward only.  window: device, `win` taps; twiddle:
- * device, 2*n_fft floats from spl_fill_twiddle(). */
+ * ld >= n_fft/2 + 1 floats per frame (pad columns are zeroed): the tensor stft() returns (stft_loss.py:19-35) and the
+ * operand of the mel projection in MelSpectrogram.forward (mel_loss.py:88-91).  Forward only.  window: device, `win`
+ * taps; twiddle: device, 2*n_fft floats from spl_fill_twiddle().  out_lo: NULL, or a second (B, F, ld) buffer that
+ * receives A - tf32(A) while `out` receives tf32(A) -- the operand split spl_mel_project() consumes. */
 int32_t spl_spectrogram(const float* x, int32_t B, int32_t T, int32_t n_fft, int32_t hop, int32_t win,
-                        const float* window, const float* twiddle, float eps, float* out, int32_t ld, void* stream);
+                        const float* window, const float* twiddle, float eps, float* out, float* out_lo, int32_t ld,
+                        void* stream);
+
+/* Mel projection + clamp + log as a tensor-core GEMM (tcgen05.mma kind::tf32, 3xTF32 operand split, TMA-fed):
+ *     out[b, m, t] = log_scale * ln(max(sum_k A[b*frames + t, k] * W[m, k], eps))
+ * i.e. log_b(clamp(matmul(x_amp, melmat), eps)).transpose(1, 2) of MelSpectrogram.forward (mel_loss.py:91-94).
+ * amp_hi / amp_lo: device (rows, ld) from spl_spectrogram(out, out_lo); w_hi / w_lo: device (n_pad, ld) = melmat^T
+ * split the same way on the host, zero padded; n_pad = n_mels rounded up to 16 (<= 128); ld a multiple of 32.
+ * rows = B * frames.  All device pointers 16-byte aligned. */
+int32_t spl_mel_project(const float* amp_hi, const float* amp_lo, int64_t rows, int32_t ld,
+                        const float* w_hi, const float* w_lo, int32_t n_mels, int32_t n_pad, int32_t frames,
+                        float eps, float log_scale, float* out, void* stream);
 
 #ifdef __cplusplus
 }

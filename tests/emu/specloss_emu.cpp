@@ -5,6 +5,7 @@
 #define SPECLOSS_EMU 1
 #include "../../include/specloss.h"
 #include "../../dl_speech_enhancement_b200/csrc/specloss_kernels.cuh"
+#include "melgemm_params_emu.h"
 
 #include <cstdarg>
 #include <cstdio>
@@ -90,6 +91,11 @@ int spl_launch_spec(const spl::SpecParams& p, int grid, int wpc, size_t smem, vo
            [&](float* sm, int tid) { spl::cta_load_fft_tables<NFFT>(ct, p.twiddle, p.window, p.win, sm, tid, wpc * 32); },
            [&](float* sm, int block, int tid) { spl::spec_body<NFFT>(p, sm, block, tid, grid, wpc); });
   return SPL_OK;
+}
+
+// the tensor-core GEMM has no emulation: tcgen05 / TMA are GPU-only (covered by the -m gpu tests)
+int spl_launch_mel_gemm(const float*, const float*, const float*, const float*, int, const spl::MelGemmParams&, void*) {
+  return fail(SPL_E_INVALID, "spl_mel_project needs a GPU (tcgen05)");
 }
 
 int spl_launch_reduce(const spl::ReduceParams& rp, void*) {

@@ -54,6 +54,21 @@ def test_emulated_spectrogram_matches_torch_stft(emu_engine, n_fft, hop, win, t_
     assert float((out.double() - ref).abs().max()) <= 2e-5 * float(ref.max())
 
 
+def test_emulated_spectrogram_tf32_split(emu_engine):
+    """The GEMM operand form of the spectrogram: hi exactly TF32, hi + lo == the plain output, zero pad columns."""
+    from dl_speech_enhancement_b200.engine import gemm_ld, twiddle_table
+
+    x = 0.1 * torch.randn(2, 900, generator=torch.Generator().manual_seed(3))
+    window, tw = torch.hann_window(512), twiddle_table(512)
+    plain = emu_engine.spectrogram(x, 512, 128, 512, window, tw, 1e-10)
+    hi, lo = emu_engine.spectrogram(x, 512, 128, 512, window, tw, 1e-10, ld=gemm_ld(512), split=True)
+    assert hi.shape == (2, 8, 288) and lo.shape == hi.shape
+    assert torch.equal(hi[:, :, :257] + lo[:, :, :257], plain)
+    assert int((hi.view(torch.int32) & 0x1fff).abs().max()) == 0
+    assert float(hi[:, :, 257:].abs().max()) == 0.0 and float(lo[:, :, 257:].abs().max()) == 0.0
+    assert float((lo.abs() / plain.abs().max()).max()) < 2.0 ** -10
+
+
 def test_emulated_no_grad(emu_engine):
     from dl_speech_enhancement_b200.functional import spectral_losses
 
