@@ -49,6 +49,10 @@ int spl_launch_shape(int n_fft, size_t table_bytes, size_t warp_bytes, long long
   int rc = device_sm_count(&sms);
   if (rc) return rc;
   int w = n_fft == 2048 ? spl::MaxWarps<2048>::value : spl::MaxWarps<1024>::value;
+  static const int cap2048 = [] { const char* e = std::getenv("SPECLOSS_WARPS_2048"); return e ? std::atoi(e) : 0; }();
+  static const int cap_small = [] { const char* e = std::getenv("SPECLOSS_WARPS_SMALL"); return e ? std::atoi(e) : 0; }();
+  const int cap = n_fft == 2048 ? cap2048 : cap_small;          // tuning knobs (profiles/): fewer resident warps per SM
+  if (cap > 0 && cap < w) w = cap;
   const int by_smem = (int)((kMaxSmem - table_bytes) / warp_bytes);
   if (by_smem < w) w = by_smem;
   const long long spread = (items + sms - 1) / sms;

@@ -170,6 +170,23 @@ SPL_DEVICE int reflect(int s, int T) {
   return s >= T ? 2 * (T - 1) - s : s;
 }
 
+// Opaque copy: stops the compiler from hoisting everything derived from the value out of the enclosing loop
+// (with rolled row loops, hoisted per-lane addresses otherwise stay live across the tap loads and force spills).
+template <typename T>
+SPL_DEVICE T launder(T v) {
+#ifndef SPECLOSS_EMU
+  asm volatile("" : "+r"(v));
+#endif
+  return v;
+}
+template <typename T>
+SPL_DEVICE T* launder_ptr(T* v) {
+#ifndef SPECLOSS_EMU
+  asm volatile("" : "+l"(v));
+#endif
+  return v;
+}
+
 SPL_DEVICE float bits_to_float(int b) {
 #ifdef SPECLOSS_EMU
   float f; memcpy(&f, &b, 4); return f;
@@ -582,15 +599,19 @@ SPL_DEVICE void transform_body(const TransformParams& p, float* smem, int block,
       if (phase == 0) {
         fwd_store_cols<NFFT>(v, S, tw, l);
         float2 A[G::AROWS][G::HL];
-        fwd_pass_b<NFFT>(A, S, l);
+        // PARK: the row passes below are rolled loops; fresh opaque copies of the lane index and the slot pointer
+        // keep their address arithmetic inside this frame instead of live across the tap loads
+        const int lr = G::PARK ? launder(l) : l;
+        float2* Sr = G::PARK ? launder_ptr(S) : S;
+        fwd_pass_b<NFFT>(A, Sr, lr);
         if (KIND == kKindStft) {
-          stft_epilogue<NFFT, GRAD>(A, S, l, frame_equal, 4.f * p.eps, s1, s2, s3);
+          stft_epilogue<NFFT, GRAD>(A, Sr, lr, frame_equal, 4.f * p.eps, s1, s2, s3);
           __syncwarp();    // mirror halves: all reads (and the H written back over them) done before the slot is reused
         } else {
-          mel_epilogue<NFFT, GRAD>(A, S, msum, l, frame_equal, active, p, mel_tasks, mel_entries, bin_tab, s1);
+          mel_epilogue<NFFT, GRAD>(A, Sr, msum, lr, frame_equal, active, p, mel_tasks, mel_entries, bin_tab, s1);
         }
         if (active) { d1 += (double)s1; d2 += (double)s2; d3 += (double)s3; }
-        if (GRAD) inv_pass_b<NFFT>(A, S, tw, l);
+        if (GRAD) inv_pass_b<NFFT>(A, Sr, tw, lr);
       } else if (active) {
         // [region: window + store]
         // v[n2] = sample n = l + L*n2 of the two real gradient sequences with swapped components: (.y, .x) = (u, v).
