@@ -58,7 +58,9 @@ void geometry(const spl_transform* t, int B, int T, spl_geometry* g) {
   g->n_bins = t->n_fft / 2 + 1;
   g->n_sums = t->kind == SPL_KIND_STFT ? 3 : 1;
   const long long items = warp_items(t, B, T);
-  g->partial_count = (int64_t)(items < kMaxPartialRows ? items : kMaxPartialRows) * g->n_sums;
+  // one row per warp of the launch: grid * wpc < items + wpc (the last CTA may hold idle warps, which still write a
+  // row of zeros), wpc <= 32
+  g->partial_count = (int64_t)((items < kMaxPartialRows ? items : kMaxPartialRows) + 32) * g->n_sums;
   g->gframe_bytes = (int64_t)B * g->n_frames * t->win * (t->kind == SPL_KIND_STFT ? 8 : 4);
   const spl::CtaTables ct = spl::cta_tables(t->n_fft, t->win, t->kind, t->mel_rounds, t->mel_entry_rows);
   g->smem_table_bytes = (int64_t)ct.total * 4;
@@ -71,7 +73,8 @@ int shape_of(const spl_transform* t, int B, int T, int* grid, int* wpc) {
   geometry(t, B, T, &g);
   int rc = spl_launch_shape(t->n_fft, (size_t)g.smem_table_bytes, (size_t)g.smem_warp_bytes, warp_items(t, B, T), grid, wpc);
   if (rc) return rc;
-  if ((long long)*grid * *wpc > kMaxPartialRows) return fail(SPL_E_INVALID, "launch of %d x %d warps exceeds the partial-sum rows", *grid, *wpc);
+  if ((long long)*grid * *wpc * g.n_sums > g.partial_count)
+    return fail(SPL_E_INVALID, "launch of %d x %d warps exceeds the %lld partial-sum rows", *grid, *wpc, (long long)(g.partial_count / g.n_sums));
   return SPL_OK;
 }
 

@@ -63,10 +63,10 @@ def test_geometry(lib):
     g = _abi.SplGeometry()
     assert lib.spl_geometry_of(ctypes.byref(_tr()), 16, 48000, ctypes.byref(g)) == 0
     assert (g.n_frames, g.n_bins, g.n_sums) == (401, 513, 3)
-    assert g.partial_count == 16 * 401 * 3 and g.gframe_bytes == 16 * 401 * 600 * 8
+    assert g.partial_count == (16 * 401 + 32) * 3 and g.gframe_bytes == 16 * 401 * 600 * 8
     assert g.smem_table_bytes == (2 * 32 * 33 + 600) * 4 and 0 < g.smem_warp_bytes <= 32 * 1024
     assert lib.spl_geometry_of(ctypes.byref(_tr()), 256, 192000, ctypes.byref(g)) == 0
-    assert g.partial_count == 32768 * 3            # capped: one row per warp of the launch
+    assert g.partial_count == (32768 + 32) * 3     # capped: one row per warp of the launch
 
 
 @pytest.mark.parametrize("kw,frag", [

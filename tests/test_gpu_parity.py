@@ -284,6 +284,25 @@ def test_non_default_stream_and_dtype_errors(dev):
         stft(y_hat, y)
 
 
+def test_partial_sum_rows_of_partly_idle_launches(dev):
+    """Batches so small that the last CTA of a launch holds idle warps (they still write a row of zeros): the rows
+    must not spill into the next transform's partial sums.  8 x 0.5 s is the shape that exposed it; a sweep of
+    batch sizes covers the other grid x warps roundings.  Checked against the oracle's sums."""
+    import dl_speech_enhancement_b200 as pkg
+    from dl_speech_enhancement_b200.engine import cuda_engine
+    from oracle import spectral_oracle as so
+    y_hat, y = so.synth_pair(8, 24000, seed=14)
+    plans = pkg.MultiResolutionSTFTLoss().to(dev).plans() + pkg.MultiMelSpectrogramLoss(**MEL48).to(dev).plans()
+    eng = cuda_engine()
+    per_utt = []
+    for b in range(8):
+        _, _, sums = so.analytic(y_hat[b:b + 1], y[b:b + 1], so.DEFAULT_STFT, so.mel_from_kwargs(**MEL48), dtype=np.float64)
+        per_utt.append(np.array([v for s in sums for v in s[:-1]]))
+    for nb in (1, 2, 3, 5, 8):
+        got = eng.forward(plans, y_hat[:nb, 0].to(dev).contiguous(), y[:nb, 0].to(dev).contiguous(), False).sums.cpu().numpy()
+        np.testing.assert_allclose(got, sum(per_utt[:nb]), rtol=2e-5, err_msg=f"batch {nb}")
+
+
 def test_two_gpu_sharded_equals_single(dev):
     """Sharded batch on 2 GPUs in one process (peer copies of the 10 sums stand in for NCCL here; the
     NCCL path itself is exercised by bench.py --gpus N and tests/test_distributed_gloo.py)."""
