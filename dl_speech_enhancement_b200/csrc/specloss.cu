@@ -158,6 +158,17 @@ int spl_launch_spec(const spl::SpecParams& p, int grid, int wpc, size_t smem, vo
   return SPL_OK;
 }
 
+template <int NFFT, int KIND>
+int spl_launch_specgrad(const spl::SpecGradParams& q, int grid, int wpc, size_t smem, void* stream) {
+  auto kern = spl::specgrad_kernel<NFFT, KIND>;
+  static thread_local bool configured[64] = {false};
+  int rc = opt_in_smem(kern, configured);
+  if (rc) return rc;
+  kern<<<grid, wpc * 32, smem, static_cast<cudaStream_t>(stream)>>>(q);
+  SPL_CUDA(cudaGetLastError());
+  return SPL_OK;
+}
+
 // ---- tensor-core mel projection: TMA descriptors through the driver entry point (no link-time libcuda dependency) ----
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,

@@ -7,6 +7,7 @@
 //          same numbers: one row of partial sums per warp)
 //   template <int NFFT, int KIND, bool GRAD, int WIN_T> int spl_launch_transform(const spl::TransformParams&, int grid, int wpc, size_t smem, void* stream);
 //   template <int NFFT> int spl_launch_spec(const spl::SpecParams&, int grid, int wpc, size_t smem, void* stream);
+//   template <int NFFT, int KIND> int spl_launch_specgrad(const spl::SpecGradParams&, int grid, int wpc, size_t smem, void* stream);
 //   int spl_fork(void* stream, int n, void** streams);   -- streams[0] = stream, streams[1..n) run concurrently after
 //   int spl_join(void* stream, int n, void** streams);      everything queued on `stream` so far; join = stream waits for all
 //   int spl_launch_mel_gemm(const float* amp_hi, const float* amp_lo, const float* w_hi, const float* w_lo, int ld,
@@ -211,6 +212,62 @@ int32_t spl_spectrogram(const float* x, int32_t B, int32_t T, int32_t n_fft, int
   if (n_fft == 512) return spl_launch_spec<512>(p, grid, wpc, smem, stream);
   if (n_fft == 1024) return spl_launch_spec<1024>(p, grid, wpc, smem, stream);
   return spl_launch_spec<2048>(p, grid, wpc, smem, stream);
+}
+
+int32_t spl_spectrogram_backward(const spl_transform* t, const float* x, int32_t B, int32_t T,
+                                 const float* g, int32_t ld, float* dx, void* stream) {
+  if (!t) return fail(SPL_E_INVALID, "null transform");
+  if (t->kind != SPL_KIND_STFT && t->kind != SPL_KIND_MEL) return fail(SPL_E_INVALID, "kind %d unknown", t->kind);
+  const int n_fft = t->n_fft, hop = t->hop, win = t->win;
+  if (!supported_nfft(n_fft)) return fail(SPL_E_INVALID, "n_fft %d not in {512,1024,2048}", n_fft);
+  if (win < 1 || win > n_fft) return fail(SPL_E_INVALID, "win %d must be in [1, n_fft=%d]", win, n_fft);
+  if (hop < 1) return fail(SPL_E_INVALID, "hop %d < 1", hop);
+  if (B < 1) return fail(SPL_E_INVALID, "batch %d < 1", B);
+  if (T <= n_fft / 2) return fail(SPL_E_INVALID, "reflect padding needs T > n_fft/2 (T=%d, n_fft=%d)", T, n_fft);
+  if (!x || !g || !dx || !t->window || !t->twiddle || !t->gframes)
+    return fail(SPL_E_INVALID, "spl_spectrogram_backward: null pointer (x, g, dx, window, twiddle or gframes workspace)");
+  const bool mel = t->kind == SPL_KIND_MEL;
+  if (mel) {
+    if (t->n_mels < 2 || t->n_mels > 512) return fail(SPL_E_INVALID, "n_mels %d must be in [2, 512]", t->n_mels);
+    if (!t->mel_tasks || !t->mel_entries || t->mel_rounds < 1 || t->mel_entry_rows < 1 || !t->bin_tab)
+      return fail(SPL_E_INVALID, "spl_spectrogram_backward: null mel table");
+  } else if (ld < n_fft / 2 + 1) {
+    return fail(SPL_E_INVALID, "ld %d < n_fft/2+1", ld);
+  }
+  const int n_frames = 1 + T / hop, n_pairs = (n_frames + 1) / 2;
+  if ((long long)B * n_frames > 0x7fffffffLL) return fail(SPL_E_INVALID, "B * frames exceeds 2^31");
+  const spl::CtaTables ct = spl::cta_tables(n_fft, win, t->kind, t->mel_rounds, t->mel_entry_rows);
+  const size_t table_bytes = (size_t)ct.total * 4, warp_bytes = (size_t)warp_words(n_fft, t->kind, t->n_mels) * 4;
+  const int fpw = frames_in_flight(n_fft);
+  int grid = 0, wpc = 0;
+  int rc = spl_launch_shape(n_fft, table_bytes, warp_bytes, ((long long)B * n_pairs + fpw - 1) / fpw, &grid, &wpc);
+  if (rc) return rc;
+  spl::SpecGradParams q;
+  std::memset(&q, 0, sizeof(q));
+  spl::TransformParams& p = q.t;
+  p.x = x; p.B = B; p.T = T; p.hop = hop; p.win = win; p.left = (n_fft - win) / 2; p.n_frames = n_frames;
+  p.eps = t->eps; p.window = t->window; p.twiddle = reinterpret_cast<const float2*>(t->twiddle);
+  p.gframes = t->gframes;
+  p.n_mels = mel ? t->n_mels : 0;
+  p.inv_ln_base = t->inv_ln_base;
+  p.mel_tasks = t->mel_tasks; p.mel_entries = t->mel_entries;
+  p.mel_rounds = mel ? t->mel_rounds : 0;
+  p.mel_entry_rows = mel ? t->mel_entry_rows : 0;
+  p.bin_tab = t->bin_tab;
+  q.n_pairs = n_pairs; q.g = g; q.ld = ld;
+  const size_t smem = table_bytes + warp_bytes * wpc;
+  if (n_fft == 512) rc = mel ? spl_launch_specgrad<512, spl::kKindMel>(q, grid, wpc, smem, stream) : spl_launch_specgrad<512, spl::kKindStft>(q, grid, wpc, smem, stream);
+  else if (n_fft == 1024) rc = mel ? spl_launch_specgrad<1024, spl::kKindMel>(q, grid, wpc, smem, stream) : spl_launch_specgrad<1024, spl::kKindStft>(q, grid, wpc, smem, stream);
+  else rc = mel ? spl_launch_specgrad<2048, spl::kKindMel>(q, grid, wpc, smem, stream) : spl_launch_specgrad<2048, spl::kKindStft>(q, grid, wpc, smem, stream);
+  if (rc) return rc;
+  spl::CombineParams cp;
+  std::memset(&cp, 0, sizeof(cp));
+  cp.n = 1;
+  spl::CombineEntry& e = cp.e[0];
+  e.frames = t->gframes; e.kind = SPL_KIND_MEL /* one float per tap */; e.half = n_fft / 2; e.hop = hop; e.win = win;
+  e.left = (n_fft - win) / 2; e.n_frames = n_frames;
+  cp.dx = dx; cp.B = B; cp.T = T; cp.unit = 1;
+  return spl_launch_combine(cp, stream);
 }
 
 int32_t spl_mel_project(const float* amp_hi, const float* amp_lo, int64_t rows, int32_t ld,

@@ -438,6 +438,35 @@ SPL_DEVICE float2 mel_bin_grad(float2 x2, bool self, int4 bt, const float2* msum
   return __fmul2_rn(x2, make_float2(g, g));
 }
 
+// mel, pass 2: balanced banded projection of the amplitude pairs parked in the frame slot.  Every mel row is summed
+// by a group of 1..L lanes walking a host-built table of (amplitude slot, weight) entries, then reduced with
+// shuffles; msum[row] receives the pair of mel energies.  Ends with the warp barrier that publishes msum.
+template <int L>
+SPL_DEVICE void mel_project_pairs(const float2* S, float2* msum, int l, int mel_rounds, const int4* mel_tasks,
+                                  const int2* mel_entries) {
+  for (int r = 0; r < mel_rounds; ++r) {
+    const int4 tk = mel_tasks[r * L + l];
+    const int row = tk.x & 0xfff, grp = (tk.x >> 12) & 0xff, iters = tk.x >> 20;
+    const int2* en = mel_entries + tk.y * L + l;
+    float mx = 0.f, my = 0.f;
+#pragma unroll 4
+    for (int s = 0; s < iters; ++s) {
+      const int2 e = en[s * L];
+      const float2 amp = S[e.x];
+      const float w = bits_to_float(e.y);
+      mx = fmaf(amp.x, w, mx);
+      my = fmaf(amp.y, w, my);
+    }
+#pragma unroll
+    for (int o = 1; o < L; o <<= 1) {
+      const float tx = __shfl_xor_sync(0xffffffffu, mx, o), ty = __shfl_xor_sync(0xffffffffu, my, o);
+      if (o < grp) { mx += tx; my += ty; }
+    }
+    if (row != 0xfff && (l & (grp - 1)) == 0) msum[row] = make_float2(mx, my);
+  }
+  __syncwarp();
+}
+
 // mel epilogue of one frame: amplitudes -> banded projection -> log-mel L1 -> (GRAD) gradient spectrum.
 // In: Z columns < L/2 in A (PARK: in the slot), mirror halves in the slot.  Out (GRAD): H in the same places.
 // The amplitudes of bin k <= N/2 are parked at the bin's own slot position; 2X[k] waits for pass 3 in A (PARK: in
@@ -475,29 +504,7 @@ SPL_DEVICE void mel_epilogue(float2 (&A)[Geo<NFFT>::AROWS][Geo<NFFT>::HL], float
     S[G::HL] = amp;
   }
   __syncwarp();
-  // pass 2: balanced projection.  Every mel row is summed by a group of 1..L lanes walking a host-built table
-  // of (amplitude slot, weight) entries, then reduced with shuffles.
-  for (int r = 0; r < p.mel_rounds; ++r) {
-    const int4 tk = mel_tasks[r * L + l];
-    const int row = tk.x & 0xfff, grp = (tk.x >> 12) & 0xff, iters = tk.x >> 20;
-    const int2* en = mel_entries + tk.y * L + l;
-    float mx = 0.f, my = 0.f;
-#pragma unroll 4
-    for (int s = 0; s < iters; ++s) {
-      const int2 e = en[s * L];
-      const float2 amp = S[e.x];
-      const float w = bits_to_float(e.y);
-      mx = fmaf(amp.x, w, mx);
-      my = fmaf(amp.y, w, my);
-    }
-#pragma unroll
-    for (int o = 1; o < L; o <<= 1) {
-      const float tx = __shfl_xor_sync(0xffffffffu, mx, o), ty = __shfl_xor_sync(0xffffffffu, my, o);
-      if (o < grp) { mx += tx; my += ty; }
-    }
-    if (row != 0xfff && (l & (grp - 1)) == 0) msum[row] = make_float2(mx, my);
-  }
-  __syncwarp();
+  mel_project_pairs<L>(S, msum, l, p.mel_rounds, mel_tasks, mel_entries);
   for (int row = l; row < p.n_mels; row += L) {
     const float2 mm = msum[row];
     const float mxc = fmaxf(mm.x, p.eps), myc = fmaxf(mm.y, p.eps);
@@ -762,6 +769,202 @@ SPL_DEVICE void spec_body(const SpecParams& p, float* smem, int block, int tid, 
 }
 
 // ---------------------------------------------------------------------------------------------
+// Backward of the explicit spectrograms: what autograd derives for stft() (losses/stft_loss.py:19-35) and for
+// MelSpectrogram.forward (losses/mel_loss.py:74-94) given the upstream gradient of their OUTPUT tensor
+// (SURVEY appendix A.2 steps 3-6).  The spectra are recomputed (frames t and t+1 of the same signal share one
+// complex FFT, as in spec_body), multiplied by the upstream gradient and sent back through the adjoint transform;
+// one complex inverse FFT returns the two real frame gradients.  The windowed frame gradients go to one slot per
+// frame (float [B * F][win]); combine_kernel (unit coefficients) overlap-adds and folds them into dx.
+//   kStft: g = dL/dA          (B, F, ld)       gX = g [|X|^2 >= eps] X / |X|
+//   kMel : g = dL/d log-mel   (B, n_mels, F)   gM = g [M >= eps] / (M ln b),  gA = gM W^T (banded),  gX as above
+// ---------------------------------------------------------------------------------------------
+struct SpecGradParams {
+  TransformParams t;     // x, B, T, hop, win, left, n_frames, eps, window, twiddle, gframes, mel tables (y, partials unused)
+  int n_pairs;           // frame pairs per utterance = (n_frames + 1) / 2
+  const float* g;        // upstream gradient
+  int ld;                // kStft: floats per frame row of g
+};
+
+// One mirror pair (k, N-k) of the packed spectrum Z = FFT(f_t + i f_{t+1}):
+//   H[k] = w (c0 2X_t[k] + i c1 2X_{t+1}[k]),  H[N-k] = w (c0 conj(2X_t[k]) + i c1 conj(2X_{t+1}[k])),
+//   c = gA gate / sqrt(4 |X|^2),  w = 1/2 (1 when k mirrors itself).
+SPL_DEVICE void specgrad_pair(float2 a, float2 bm, bool self, float eps4, float g0, float g1, float2& ha, float2& hb) {
+  const float2 x2 = __fadd2_rn(a, make_float2(bm.x, -bm.y));
+  const float2 y2 = __fadd2_rn(make_float2(a.y, -a.x), make_float2(bm.y, bm.x));
+  const float p0 = fmaf(x2.x, x2.x, x2.y * x2.y);
+  const float p1 = fmaf(y2.x, y2.x, y2.y * y2.y);
+  const float w = self ? 1.f : 0.5f;
+  const float c0 = p0 >= eps4 ? w * g0 * spl_fast_rsqrt(p0) : 0.f;      // clamp gate of the reference
+  const float c1 = p1 >= eps4 ? w * g1 * spl_fast_rsqrt(p1) : 0.f;
+  const float2 u = __fmul2_rn(x2, make_float2(c0, c0));
+  const float2 v = __fmul2_rn(y2, make_float2(c1, c1));
+  ha = make_float2(u.x - v.y, u.y + v.x);
+  hb = make_float2(u.x + v.y, v.x - u.y);
+}
+
+// [region: spectrogram backward]
+template <int NFFT, int KIND>
+SPL_DEVICE void specgrad_body(const SpecGradParams& q, float* smem, int block, int tid, int grid, int wpc) {
+  using G = Geo<NFFT>;
+  using SL = SmemLayout<NFFT, KIND>;
+  static_assert(!G::PARK, "the spectrogram backward keeps its rows in registers");
+  constexpr int L = G::L, R = G::R, FPW = G::FPW, HALF = NFFT / 2;
+  const TransformParams& p = q.t;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int l = lane & (L - 1), h = lane / L;
+  const CtaTables ct = cta_tables(NFFT, p.win, KIND, p.mel_rounds, p.mel_entry_rows);
+  const float2* tw = reinterpret_cast<const float2*>(smem + ct.tw);
+  const float* wtab = smem + ct.win;
+  const int4* mel_tasks = reinterpret_cast<const int4*>(smem + ct.tasks);
+  const int2* mel_entries = reinterpret_cast<const int2*>(smem + ct.entries);
+  const int4* bin_tab = reinterpret_cast<const int4*>(smem + ct.bintab);
+  float* wsm = smem + ct.total + (size_t)warp * SL::words_per_warp(p.n_mels);
+  float2* S = reinterpret_cast<float2*>(wsm) + h * G::SLOT_F2;
+  float2* msum = reinterpret_cast<float2*>(wsm + FPW * G::SLOT_F2 * 2) + h * align4(p.n_mels);
+  const int total = p.B * q.n_pairs;                 // work items: (utterance, frame pair)
+  const float eps4 = 4.f * p.eps;
+  for (int base = (block * wpc + warp) * FPW; base < total; base += grid * wpc * FPW) {
+    const int item = base + h;
+    const bool active = item < total;
+    const int b = active ? item / q.n_pairs : 0, pr = active ? item - b * q.n_pairs : 0;
+    const int t = 2 * pr;
+    const bool second = active && (t + 1 < p.n_frames);
+    const float* __restrict__ xb = p.x + (size_t)b * p.T;
+    float2 A[G::AROWS][G::HL];
+    {
+      float2 v[R];
+#pragma unroll
+      for (int n2 = 0; n2 < R; ++n2) {
+        const int tap = L * n2 - p.left + l;
+        float a0 = 0.f, a1 = 0.f;
+        if (active && tap >= 0 && tap < p.win) {
+          const float w = wtab[tap];
+          const int s = t * p.hop + L * n2 + l - HALF;
+          a0 = __ldg(&xb[reflect(s, p.T)]) * w;
+          if (second) a1 = __ldg(&xb[reflect(s + p.hop, p.T)]) * w;
+        }
+        v[n2] = make_float2(a0, a1);
+      }
+      Dft<R>::run(v);
+      fwd_store_cols<NFFT>(v, S, tw, l);
+    }
+    fwd_pass_b<NFFT>(A, S, l);
+    if (KIND == kKindStft) {
+      const float* __restrict__ g0 = q.g + ((size_t)b * p.n_frames + t) * q.ld;
+      const float* __restrict__ g1 = g0 + q.ld;
+#pragma unroll
+      for (int j = 0; j < G::RPL; ++j) {
+        const int row = l + L * j;
+        float2* pb = mirror_ptr<NFFT>(S, row);
+#pragma unroll
+        for (int k1 = 0; k1 < G::HL; ++k1) {
+          const float2 a = A[j][k1];
+          const bool self = k1 == 0 && row == 0;
+          float2 bm = pb[-k1];
+          if (k1 == 0) bm = self ? a : bm;
+          const int k = row + R * k1;
+          float2 ha, hb;
+          specgrad_pair(a, bm, self, eps4, active ? __ldg(g0 + k) : 0.f, second ? __ldg(g1 + k) : 0.f, ha, hb);
+          A[j][k1] = ha;
+          pb[-k1] = hb;
+        }
+      }
+      if (l == 0) {                                                    // bin N/2
+        const float2 a = S[G::HL];
+        float2 ha, hb;
+        specgrad_pair(a, a, true, eps4, active ? __ldg(g0 + HALF) : 0.f, second ? __ldg(g1 + HALF) : 0.f, ha, hb);
+        S[G::HL] = ha;
+      }
+    } else {
+      // pass 1: amplitude pairs (A_t, A_{t+1}) parked at the bins' own slot positions; Z stays where it is
+      float2 ah = make_float2(0.f, 0.f);                               // Z[N/2], lane 0
+#pragma unroll
+      for (int j = 0; j < G::RPL; ++j) {
+        const int row = l + L * j;
+        const float2* pb = mirror_ptr<NFFT>(S, row);
+        float2* arow = S + row * G::PITCH;
+#pragma unroll
+        for (int k1 = 0; k1 < G::HL; ++k1) {
+          const float2 a = A[j][k1];
+          float2 bm = pb[-k1];
+          if (k1 == 0) bm = (row == 0) ? a : bm;
+          float2 x2, amp;
+          mel_pair_amp(a, bm, false, eps4, x2, amp);
+          arow[k1] = amp;
+        }
+      }
+      if (l == 0) {
+        ah = S[G::HL];
+        float2 x2, amp;
+        mel_pair_amp(ah, ah, false, eps4, x2, amp);
+        S[G::HL] = amp;
+      }
+      __syncwarp();
+      mel_project_pairs<L>(S, msum, l, p.mel_rounds, mel_tasks, mel_entries);
+      // gM = g [M >= eps] / (M ln b) for both frames
+      for (int row = l; row < p.n_mels; row += L) {
+        const float2 mm = msum[row];
+        const float* gp = q.g + ((size_t)b * p.n_mels + row) * p.n_frames + t;
+        const float u0 = active ? __ldg(gp) : 0.f, u1 = second ? __ldg(gp + 1) : 0.f;
+        msum[row] = make_float2(mm.x >= p.eps ? u0 * p.inv_ln_base / mm.x : 0.f,
+                                mm.y >= p.eps ? u1 * p.inv_ln_base / mm.y : 0.f);
+      }
+      __syncwarp();
+      // pass 3: gA[k] = sum_m gM[m] W[k, m] (<= 2 adjacent rows) for both frames -> H
+#pragma unroll
+      for (int j = 0; j < G::RPL; ++j) {
+        const int row = l + L * j;
+        float2* pb = mirror_ptr<NFFT>(S, row);
+        const int4* btr = bin_tab + row;
+#pragma unroll
+        for (int k1 = 0; k1 < G::HL; ++k1) {
+          const float2 a = A[j][k1];
+          const bool self = k1 == 0 && row == 0;
+          float2 bm = pb[-k1];
+          if (k1 == 0) bm = self ? a : bm;
+          const int4 bt = btr[R * k1];
+          const float2 m0 = msum[bt.x], m1 = msum[bt.x + 1];
+          const float w0 = bits_to_float(bt.y), w1 = bits_to_float(bt.z);
+          float2 ha, hb;
+          specgrad_pair(a, bm, self, eps4, fmaf(m0.x, w0, m1.x * w1), fmaf(m0.y, w0, m1.y * w1), ha, hb);
+          A[j][k1] = ha;
+          pb[-k1] = hb;
+        }
+      }
+      if (l == 0) {
+        const int4 bt = bin_tab[HALF];
+        const float2 m0 = msum[bt.x], m1 = msum[bt.x + 1];
+        const float w0 = bits_to_float(bt.y), w1 = bits_to_float(bt.z);
+        float2 ha, hb;
+        specgrad_pair(ah, ah, true, eps4, fmaf(m0.x, w0, m1.x * w1), fmaf(m0.y, w0, m1.y * w1), ha, hb);
+        S[G::HL] = ha;
+      }
+    }
+    __syncwarp();          // H complete in the slot (mirror halves, bin N/2) before the row passes read it
+    inv_pass_b<NFFT>(A, S, tw, l);
+    {
+      float2 v[R];
+#pragma unroll
+      for (int m2 = 0; m2 < R; ++m2) v[m2] = S[m2 * G::PITCH + l];
+      Dft<R>::run(v);
+      // v[n2] = sample n = l + L*n2 with swapped components: .y = frame t, .x = frame t+1
+      float* o0 = p.gframes ? reinterpret_cast<float*>(p.gframes) + ((size_t)b * p.n_frames + t) * p.win : nullptr;
+      float* o1 = o0 + p.win;
+#pragma unroll
+      for (int n2 = 0; n2 < R; ++n2) {
+        const int tap = L * n2 - p.left + l;
+        if (tap >= 0 && tap < p.win) {
+          const float w = wtab[tap];
+          if (active) o0[tap] = v[n2].y * w;
+          if (second) o1[tap] = v[n2].x * w;
+        }
+      }
+    }
+    __syncwarp();          // column reads done before the next item's pass-A store
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // deterministic reduction of the per-warp partial sums: one CTA per output sum
 // ---------------------------------------------------------------------------------------------
 struct ReduceParams {
@@ -842,6 +1045,7 @@ struct CombineParams {
   const float* g_mel;
   float* dx;             // (B, T)
   int B, T;
+  int unit;              // 1: every entry is taken with coefficient 1 (spectrogram backward; coefs / g_* unused)
 };
 
 // overlap-added value at one padded position (used for the reflect-fold margins): frames t with
@@ -915,7 +1119,8 @@ SPL_DEVICE void combine_body(const CombineParams& p, long long gid) {
   for (int r = 0; r < p.n; ++r) {
     const CombineEntry& e = p.e[r];
     float cu, cv;
-    if (e.kind == kKindStft) { cu = gsc * p.coefs[2 * r]; cv = gmag * p.coefs[2 * r + 1]; }
+    if (p.unit) { cu = 1.f; cv = 0.f; }
+    else if (e.kind == kKindStft) { cu = gsc * p.coefs[2 * r]; cv = gmag * p.coefs[2 * r + 1]; }
     else { cu = gmel * p.coefs[2 * r]; cv = 0.f; }
     const int P = e.half;
     gather_padded4(e, b, P + i0, cu, cv, acc);
@@ -967,6 +1172,13 @@ __global__ void __launch_bounds__(MaxWarps<NFFT>::value * 32, 1) spec_kernel(con
                             blockDim.x);
   __syncthreads();
   spec_body<NFFT>(p, smem_dyn, blockIdx.x, threadIdx.x, gridDim.x, blockDim.x >> 5);
+}
+template <int NFFT, int KIND>
+__global__ void __launch_bounds__(MaxWarps<NFFT>::value * 32, 1) specgrad_kernel(const SpecGradParams q) {
+  extern __shared__ __align__(16) float smem_dyn[];
+  cta_load_tables<NFFT, KIND>(q.t, smem_dyn, threadIdx.x, blockDim.x);
+  __syncthreads();
+  specgrad_body<NFFT, KIND>(q, smem_dyn, blockIdx.x, threadIdx.x, gridDim.x, blockDim.x >> 5);
 }
 __global__ void __launch_bounds__(256) reduce_kernel(const ReduceParams p) {
   __shared__ double sh[256];

@@ -151,6 +151,16 @@ class TransformPlan:
         if self.window.dtype != torch.float32 or self.window.numel() != self.win:
             raise RuntimeError("window buffer must be float32 with win_length taps (fp32-only implementation)")
 
+    def validate_explicit(self):
+        """Envelope of the explicit spectrogram kernels (any hop >= 1)."""
+        fft_geometry(self.n_fft)
+        if not (1 <= self.win <= self.n_fft):
+            raise RuntimeError(f"win_length {self.win} must be in [1, fft_size={self.n_fft}] (torch.stft raises likewise)")
+        if self.hop < 1:
+            raise RuntimeError(f"hop_size {self.hop} < 1")
+        if self.window.dtype != torch.float32 or self.window.numel() != self.win:
+            raise RuntimeError("window buffer must be float32 with win_length taps (fp32-only implementation)")
+
 
 def gemm_ld(n_fft: int) -> int:
     """Row pitch (floats) of the amplitude operand of the mel GEMM: n_fft/2+1 bins padded to whole 32-float k-blocks."""
@@ -364,6 +374,40 @@ class Engine:
                                                       eps, log_scale, out.data_ptr(), self._stream(amp_hi)))
         self.launches += 1
         return out
+
+    def spectrogram_backward(self, plan: TransformPlan, x: torch.Tensor, g: torch.Tensor) -> torch.Tensor:
+        """dL/dx (B, T) from the gradient of an explicit spectrogram of x: g = dL/d stft(x) (B, F, K) for an STFT plan
+        (stft_loss.py:19-35), g = dL/d MelSpectrogram(x) (B, n_mels, F) for a mel plan (mel_loss.py:74-94).  Two
+        launches (recompute + adjoint transform, overlap-add gather) on the current stream."""
+        plan.validate_explicit()
+        batch, t_len = x.shape
+        frames = 1 + t_len // plan.hop
+        dev = x.device
+        tr = SplTransform()
+        tr.kind, tr.n_fft, tr.hop, tr.win, tr.eps = plan.kind, plan.n_fft, plan.hop, plan.win, plan.eps
+        tr.window, tr.twiddle = _ptr(plan.window), _ptr(plan.twiddle)
+        tr.n_mels, tr.inv_ln_base = plan.n_mels, plan.inv_ln_base
+        if plan.kind == SPL_KIND_MEL:
+            want = (batch, plan.n_mels, frames)
+            for name, t in plan.tables.items():
+                setattr(tr, name, _ptr(t))
+            lanes = fft_geometry(plan.n_fft)[0]
+            tr.mel_rounds = plan.tables["mel_tasks"].numel() // (4 * lanes)
+            tr.mel_entry_rows = plan.tables["mel_entries"].numel() // (2 * lanes)
+            ld = frames
+        else:
+            want = (batch, frames, plan.n_fft // 2 + 1)
+            ld = want[2]
+        if tuple(g.shape) != want or g.dtype != torch.float32 or g.device != dev:
+            raise RuntimeError(f"spectrogram gradient must be fp32 {want} on {dev}, got {g.dtype} {tuple(g.shape)} on {g.device}")
+        g = g.contiguous()
+        gframes = torch.empty(batch * frames * plan.win, dtype=torch.float32, device=dev)
+        tr.gframes = gframes.data_ptr()
+        dx = torch.empty(batch, t_len, dtype=torch.float32, device=dev)
+        _abi.check(self.lib, self.lib.spl_spectrogram_backward(ctypes.byref(tr), x.data_ptr(), batch, t_len, g.data_ptr(),
+                                                               ld, dx.data_ptr(), self._stream(x)))
+        self.launches += 2
+        return dx
 
     # -- backward --------------------------------------------------------------------------------
     def backward(self, st: ForwardState, g_sc: Optional[torch.Tensor], g_mag: Optional[torch.Tensor],

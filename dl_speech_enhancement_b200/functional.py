@@ -82,3 +82,50 @@ def spectral_losses(x: torch.Tensor, y: torch.Tensor, plans: Sequence[TransformP
         _check_inputs(x, y)
         engine = cuda_engine()
     return _SpectralLossFn.apply(x, y, tuple(plans), engine, group, global_batch)
+
+
+class _SpectrogramFn(torch.autograd.Function):
+    """Explicit magnitude spectrogram stft() (stft_loss.py:19-35) with its backward (ABI spl_spectrogram /
+    spl_spectrogram_backward).  plan: an STFT TransformPlan carrying window, twiddle and eps."""
+
+    @staticmethod
+    def forward(ctx, x, plan, engine):
+        ctx.plan, ctx.engine = plan, engine
+        xd = x.detach()
+        ctx.save_for_backward(xd)
+        return engine.spectrogram(xd, plan.n_fft, plan.hop, plan.win, plan.window, plan.twiddle, plan.eps)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        return ctx.engine.spectrogram_backward(ctx.plan, x, g), None, None
+
+
+class _LogMelFn(torch.autograd.Function):
+    """MelSpectrogram.forward (mel_loss.py:74-94): spectrogram kernel + tcgen05 mel projection GEMM forward;
+    backward recomputes the spectra and applies the banded transposed projection inside the FFT kernel."""
+
+    @staticmethod
+    def forward(ctx, x, plan, w_hi, w_lo, ld, log_scale, engine):
+        ctx.plan, ctx.engine = plan, engine
+        xd = x.detach()
+        ctx.save_for_backward(xd)
+        hi, lo = engine.spectrogram(xd, plan.n_fft, plan.hop, plan.win, plan.window, plan.twiddle, plan.eps, ld=ld,
+                                    split=True)
+        return engine.mel_project(hi, lo, w_hi, w_lo, plan.n_mels, plan.eps, log_scale)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        return ctx.engine.spectrogram_backward(ctx.plan, x, g), None, None, None, None, None, None
+
+
+def spectrogram(x: torch.Tensor, plan: TransformPlan, engine: Optional[Engine] = None) -> torch.Tensor:
+    return _SpectrogramFn.apply(x, plan, engine or cuda_engine())
+
+
+def log_mel_spectrogram(x: torch.Tensor, plan: TransformPlan, w_hi, w_lo, ld: int, log_scale: float,
+                        engine: Optional[Engine] = None) -> torch.Tensor:
+    return _LogMelFn.apply(x, plan, w_hi, w_lo, ld, log_scale, engine or cuda_engine())

@@ -21,7 +21,7 @@ import torch
 from . import melfb
 from ._abi import SPL_KIND_MEL, SPL_KIND_STFT
 from .engine import TransformPlan, fft_geometry, mel_gemm_weights, mel_tables, twiddle_table
-from .functional import spectral_losses
+from .functional import log_mel_spectrogram, spectral_losses, spectrogram
 
 
 def _cached_plans(owner, children) -> List[TransformPlan]:
@@ -51,26 +51,27 @@ def _twiddle_on(n_fft: int, device) -> torch.Tensor:
 def _explicit_input(x: torch.Tensor, what: str) -> torch.Tensor:
     if not x.is_cuda or x.dtype != torch.float32:
         raise RuntimeError(f"{what}: fp32 CUDA tensors only (sm_100a kernels, no CPU fallback)")
-    if x.requires_grad and torch.is_grad_enabled():
-        raise NotImplementedError(
-            f"{what} is forward-only here: differentiate through MultiResolutionSTFTLoss / MultiMelSpectrogramLoss "
-            "(the fused loss kernels), or call it under torch.no_grad()")
     return x.contiguous()
 
 
 def stft(x, fft_size, hop_size, win_length, window, eps=1e-7):
     """Magnitude spectrogram (B, #frames, fft_size // 2 + 1) of x (B, T): losses/stft_loss.py:19-35, i.e.
     sqrt(clamp(|torch.stft(x, fft_size, hop_size, win_length, window)|^2, eps)).transpose(2, 1), computed by the
-    sm_100a spectrogram kernel (two frames per complex FFT).  Forward only; the fused loss path never materialises
-    this tensor."""
-    from .engine import cuda_engine
+    sm_100a spectrogram kernel (two frames per complex FFT).  Differentiable w.r.t. x (not the window): backward
+    recomputes the spectra and runs the adjoint transform (spl_spectrogram_backward).  The fused loss path never
+    materialises this tensor."""
     x = _explicit_input(x, "stft()")
     if x.dim() != 2:
         raise RuntimeError(f"stft(): expected (B, T), got {tuple(x.shape)}")
     if window.numel() != win_length:
         raise RuntimeError("stft(): window must have win_length taps")
-    window = window.to(device=x.device, dtype=torch.float32).contiguous()
-    return cuda_engine().spectrogram(x, fft_size, hop_size, win_length, window, _twiddle_on(fft_size, x.device), eps)
+    if window.requires_grad and torch.is_grad_enabled():
+        raise NotImplementedError("stft(): the gradient w.r.t. the window is not implemented (it is a constant buffer "
+                                  "in every reference module, stft_loss.py:97)")
+    window = window.detach().to(device=x.device, dtype=torch.float32).contiguous()
+    plan = TransformPlan(SPL_KIND_STFT, fft_size, hop_size, win_length, eps, window, _twiddle_on(fft_size, x.device))
+    plan.validate_explicit()
+    return spectrogram(x, plan)
 
 
 class SpectralConvergenceLoss(torch.nn.Module):
@@ -133,8 +134,9 @@ class MultiResolutionSTFTLoss(torch.nn.Module):
 class MelSpectrogram(torch.nn.Module):
     """Log-mel spectrogram (mel_loss.py:19-94): same ctor, same `window` and `melmat` buffers.  forward(x) returns
     the explicit (B, num_mels, #frames) tensor: spectrogram kernel + mel projection as a tcgen05 tensor-core GEMM
-    (3xTF32) with the clamp and the log fused into its epilogue; forward only.  Inside MultiMelSpectrogramLoss the
-    spectrogram is never materialised (banded projection inside the fused loss kernel)."""
+    (3xTF32) with the clamp and the log fused into its epilogue.  Differentiable w.r.t. x: backward recomputes the
+    spectra and applies the transposed (banded) projection inside the FFT kernel (spl_spectrogram_backward).  Inside
+    MultiMelSpectrogramLoss the spectrogram is never materialised (banded projection inside the fused loss kernel)."""
 
     def __init__(self, fs=22050, fft_size=1024, hop_size=256, win_length=None, window="hann_window",
                  num_mels=80, fmin=80, fmax=7600, center=True, normalized=False, onesided=True,
@@ -178,17 +180,14 @@ class MelSpectrogram(torch.nn.Module):
                              self.window, self._twiddle, self.num_mels, inv_ln, tables)
 
     def forward(self, x):
-        from .engine import cuda_engine, gemm_ld
+        from .engine import gemm_ld
         if x.dim() == 3:
             x = x.reshape(-1, x.size(2))             # mel_loss.py:84-85
         x = _explicit_input(x, "MelSpectrogram.forward()")
         if not hasattr(self, "_w_hi"):
             raise NotImplementedError("MelSpectrogram.forward(): the tensor-core projection supports num_mels <= 128")
-        eng = cuda_engine()
-        hi, lo = eng.spectrogram(x, self.fft_size, self.hop_size, self.win_length, self.window, self._twiddle, self.eps,
-                                 ld=gemm_ld(self.fft_size), split=True)
         log_scale = 1.0 if self.log_base is None else 1.0 / math.log(self.log_base)
-        return eng.mel_project(hi, lo, self._w_hi, self._w_lo, self.num_mels, self.eps, log_scale)
+        return log_mel_spectrogram(x, self.plan(), self._w_hi, self._w_lo, gemm_ld(self.fft_size), log_scale)
 
 
 class MultiMelSpectrogramLoss(torch.nn.Module):

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SPL_ABI_VERSION 7
+#define SPL_ABI_VERSION 8
 
 #define SPL_OK 0
 #define SPL_E_INVALID (-1)   /* bad argument / outside the supported envelope */
@@ -107,12 +107,22 @@ int32_t spl_backward(const spl_transform* ts, int32_t n, int32_t B, int32_t T, c
 
 /* Explicit magnitude spectrogram out[b, t, k] = sqrt(max(|STFT(x)[b, t, k]|^2, eps)), (B, 1 + T/hop, ld) with
  * ld >= n_fft/2 + 1 floats per frame (pad columns are zeroed): the tensor stft() returns (stft_loss.py:19-35) and the
- * operand of the mel projection in MelSpectrogram.forward (mel_loss.py:88-91).  Forward only.  window: device, `win`
+ * operand of the mel projection in MelSpectrogram.forward (mel_loss.py:88-91).  Backward: spl_spectrogram_backward().  window: device, `win`
  * taps; twiddle: device, 2*n_fft floats from spl_fill_twiddle().  out_lo: NULL, or a second (B, F, ld) buffer that
  * receives A - tf32(A) while `out` receives tf32(A) -- the operand split spl_mel_project() consumes. */
 int32_t spl_spectrogram(const float* x, int32_t B, int32_t T, int32_t n_fft, int32_t hop, int32_t win,
                         const float* window, const float* twiddle, float eps, float* out, float* out_lo, int32_t ld,
                         void* stream);
+
+/* Backward of the explicit spectrograms: what autograd derives for stft() (stft_loss.py:19-35: torch.stft -> power ->
+ * clamp -> sqrt) and for MelSpectrogram.forward (mel_loss.py:88-94: ... -> matmul(melmat) -> clamp -> log -> transpose)
+ * given the gradient of their output tensor.  The spectra are recomputed from x (two frames per complex FFT).
+ *   t->kind == SPL_KIND_STFT: g = dL/d stft(x),             (B, 1 + T/hop, ld) with ld >= n_fft/2+1 floats per frame
+ *   t->kind == SPL_KIND_MEL : g = dL/d MelSpectrogram(x),   (B, n_mels, 1 + T/hop); ld is ignored; t carries the mel
+ *                             tables, n_mels, inv_ln_base and eps (used for both clamps, mel_loss.py:90,92)
+ * t->gframes: device workspace of B * (1 + T/hop) * win floats; t->partials is not used.  dx (B, T) is overwritten. */
+int32_t spl_spectrogram_backward(const spl_transform* t, const float* x, int32_t B, int32_t T,
+                                 const float* g, int32_t ld, float* dx, void* stream);
 
 /* Mel projection + clamp + log as a tensor-core GEMM (tcgen05.mma kind::tf32, 3xTF32 operand split, TMA-fed):
  *     out[b, m, t] = log_scale * ln(max(sum_k A[b*frames + t, k] * W[m, k], eps))

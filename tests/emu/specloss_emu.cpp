@@ -93,6 +93,14 @@ int spl_launch_spec(const spl::SpecParams& p, int grid, int wpc, size_t smem, vo
   return SPL_OK;
 }
 
+template <int NFFT, int KIND>
+int spl_launch_specgrad(const spl::SpecGradParams& q, int grid, int wpc, size_t smem, void*) {
+  run_grid(grid, wpc, smem,
+           [&](float* sm, int tid) { spl::cta_load_tables<NFFT, KIND>(q.t, sm, tid, wpc * 32); },
+           [&](float* sm, int block, int tid) { spl::specgrad_body<NFFT, KIND>(q, sm, block, tid, grid, wpc); });
+  return SPL_OK;
+}
+
 // the tensor-core GEMM has no emulation: tcgen05 / TMA are GPU-only (covered by the -m gpu tests)
 int spl_launch_mel_gemm(const float*, const float*, const float*, const float*, int, const spl::MelGemmParams&, void*) {
   return fail(SPL_E_INVALID, "spl_mel_project needs a GPU (tcgen05)");

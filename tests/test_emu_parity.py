@@ -103,3 +103,59 @@ def test_emulated_identical_signals_are_exactly_zero(emu_engine):
     sum(outs).backward()
     assert [float(o.detach()) for o in outs] == [0.0, 0.0, 0.0]
     assert torch.count_nonzero(x.grad) == 0
+
+
+def _ref_spectrogram(x, n_fft, hop, win, window, eps):
+    s = torch.stft(x, n_fft, hop, win, window.to(x.dtype), return_complex=True)
+    return torch.sqrt(torch.clamp(s.real ** 2 + s.imag ** 2, min=eps)).transpose(2, 1)
+
+
+@pytest.mark.parametrize("n_fft,hop,win,t_len", [(512, 50, 240, 777), (1024, 120, 600, 1500), (2048, 300, 2048, 2500),
+                                                 (1024, 256, 1024, 1301), (512, 128, 512, 300)])
+def test_emulated_spectrogram_backward_matches_autograd(emu_engine, n_fft, hop, win, t_len):
+    """d/dx of stft() (stft_loss.py:19-35) for an arbitrary upstream gradient, against torch autograd in fp64;
+    odd frame counts (last pair half empty), reflect margins and the clamp gate (exact-zero block) included."""
+    from dl_speech_enhancement_b200._abi import SPL_KIND_STFT
+    from dl_speech_enhancement_b200.engine import TransformPlan, twiddle_table
+    from dl_speech_enhancement_b200.functional import spectrogram
+
+    gen = torch.Generator().manual_seed(n_fft + t_len)
+    x = 0.1 * torch.randn(3, t_len, generator=gen)
+    x[1, :] = 0.0                                           # every bin clamped: zero gradient rows
+    window = torch.hann_window(win)
+    plan = TransformPlan(SPL_KIND_STFT, n_fft, hop, win, 1e-7, window, twiddle_table(n_fft))
+    xg = x.clone().requires_grad_(True)
+    out = spectrogram(xg, plan, engine=emu_engine)
+    gout = torch.randn(out.shape, generator=gen)
+    (out * gout).sum().backward()
+    xr = x.double().requires_grad_(True)
+    (_ref_spectrogram(xr, n_fft, hop, win, window, 1e-7) * gout.double()).sum().backward()
+    assert torch.count_nonzero(xg.grad[1]) == 0
+    assert rel_l2(xg.grad.numpy(), xr.grad.numpy()) <= 1e-5
+
+
+@pytest.mark.parametrize("kw,t_len", [(dict(fs=48000, fft_size=2048, hop_size=300, win_length=None, num_mels=80, fmin=0,
+                                            fmax=24000, log_base=None), 3100),
+                                      (dict(fs=24000, fft_size=1024, hop_size=256, num_mels=80, fmin=80, fmax=7600,
+                                            log_base=10.0), 1500),
+                                      (dict(fs=24000, fft_size=512, hop_size=120, win_length=400, num_mels=40, fmin=0,
+                                            fmax=24000, log_base=2.0), 900)])
+def test_emulated_logmel_backward_matches_autograd(emu_engine, kw, t_len):
+    """d/dx of MelSpectrogram.forward (mel_loss.py:74-94) for an arbitrary upstream gradient, fp64 autograd reference
+    (includes empty filters above Nyquist -> clamped mel energies -> zero gradient through them)."""
+    import math
+
+    from dl_speech_enhancement_b200 import modules
+
+    mod = modules.MelSpectrogram(**kw)
+    gen = torch.Generator().manual_seed(t_len)
+    x = 0.1 * torch.randn(2, t_len, generator=gen)
+    frames = 1 + t_len // mod.hop_size
+    g = torch.randn(2, mod.num_mels, frames, generator=gen)
+    dx = emu_engine.spectrogram_backward(mod.plan(), x, g)
+    xr = x.double().requires_grad_(True)
+    amp = _ref_spectrogram(xr, mod.fft_size, mod.hop_size, mod.win_length, mod.window, mod.eps)
+    mel = torch.clamp(torch.matmul(amp, mod.melmat.double()), min=mod.eps)
+    logmel = torch.log(mel) / (1.0 if mod.log_base is None else math.log(mod.log_base))
+    (logmel.transpose(1, 2) * g.double()).sum().backward()
+    assert rel_l2(dx.numpy(), xr.grad.numpy()) <= 1e-5

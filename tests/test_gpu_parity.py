@@ -229,15 +229,104 @@ def test_melspectrogram_forward_tensor_core_gemm(dev, kw, shape):
     assert err <= 5e-5
 
 
-def test_explicit_spectrograms_are_forward_only(dev):
+def _ref_amp(x, fft, hop, win, window, eps):
+    st = torch.stft(x, fft, hop, win, window.to(x.dtype), return_complex=True)
+    return torch.sqrt(torch.clamp(st.real ** 2 + st.imag ** 2, min=eps)).transpose(2, 1)
+
+
+@pytest.mark.parametrize("fft,hop,win,t_len", [(1024, 120, 600, 48000), (2048, 240, 1200, 48000), (512, 50, 240, 24001),
+                                               (2048, 300, 2048, 9999), (1024, 2000, 1024, 5000), (512, 128, 333, 4000)])
+def test_stft_function_backward_matches_autograd(dev, fft, hop, win, t_len):
+    """stft() is differentiable like the reference's (stft_loss.py:19-35 under autograd): arbitrary upstream
+    gradient, fp64 autograd of the definition as the yardstick."""
     import dl_speech_enhancement_b200 as pkg
-    x = torch.randn(2, 4800, device=dev, requires_grad=True)
-    with pytest.raises(NotImplementedError, match="forward-only"):
-        pkg.stft(x, 1024, 120, 600, torch.hann_window(600, device=dev))
-    with pytest.raises(NotImplementedError, match="forward-only"):
-        pkg.MelSpectrogram(fs=48000, fft_size=2048, hop_size=300, fmin=0, fmax=24000).to(dev)(x)
+    g = torch.Generator().manual_seed(t_len + fft)
+    x = 0.1 * torch.randn(5, t_len, generator=g)
+    x[2, :] = 0.0                                         # clamped everywhere: the gradient row must be exactly zero
+    window = torch.hann_window(win)
+    xg = x.to(dev).requires_grad_(True)
+    out = pkg.stft(xg, fft, hop, win, window.to(dev))
+    gout = torch.randn(out.shape, generator=g)
+    (out * gout.to(dev)).sum().backward()
+    xr = x.double().requires_grad_(True)
+    (_ref_amp(xr, fft, hop, win, window, 1e-7) * gout.double()).sum().backward()
+    got = xg.grad.cpu()
+    assert torch.count_nonzero(got[2]) == 0
+    assert rel_l2(got.numpy(), xr.grad.numpy()) <= 2e-5
+
+
+def test_explicit_stft_loss_equals_fused(dev):
+    """The reference's own composition -- SpectralConvergenceLoss / LogSTFTMagnitudeLoss on explicit stft() tensors
+    (stft_loss.py:100-117) -- differentiated through the explicit kernels, against the fused loss kernels."""
+    import dl_speech_enhancement_b200 as pkg
+    from oracle import spectral_oracle as so
+    y_hat, y = so.synth_pair(4, 24000, seed=1234)
+    y_hat, y = y_hat.reshape(4, -1), y.reshape(4, -1)
+    fused = pkg.STFTLoss(1024, 120, 600).to(dev)
+    x1 = y_hat.to(dev).requires_grad_(True)
+    sc1, mag1 = fused(x1, y.to(dev))
+    (sc1 + mag1).backward()
+    x2 = y_hat.to(dev).requires_grad_(True)
+    xm = pkg.stft(x2, 1024, 120, 600, fused.window)
+    ym = pkg.stft(y.to(dev), 1024, 120, 600, fused.window)
+    sc2, mag2 = pkg.SpectralConvergenceLoss()(xm, ym), pkg.LogSTFTMagnitudeLoss()(xm, ym)
+    (sc2 + mag2).backward()
+    assert abs(float(sc1) - float(sc2)) <= 1e-5 * float(sc1) and abs(float(mag1) - float(mag2)) <= 1e-5 * float(mag1)
+    assert rel_l2(x2.grad.cpu().numpy(), x1.grad.cpu().numpy()) <= 1e-4
+
+
+@pytest.mark.parametrize("kw,shape", [(MEL48, (4, 1, 24000)), (MEL24, (3, 24000)),
+                                      (dict(fs=22050, fft_size=1024, hop_size=256, num_mels=80, fmin=80, fmax=7600, log_base=10.0), (4, 22050)),
+                                      (dict(fs=24000, fft_size=512, hop_size=128, num_mels=20, fmin=0, fmax=24000, log_base=2.0), (2, 1, 6001))])
+def test_melspectrogram_backward_matches_autograd(dev, kw, shape):
+    """MelSpectrogram.forward is differentiable like the reference's (mel_loss.py:74-94 under autograd)."""
+    import math
+
+    import dl_speech_enhancement_b200 as pkg
+    if "fft_sizes" in kw:
+        kw = dict(fs=kw["fs"], fft_size=kw["fft_sizes"][0], hop_size=kw["hop_sizes"][0], win_length=kw["win_lengths"][0],
+                  num_mels=kw["num_mels"], fmin=kw["fmin"], fmax=kw["fmax"], log_base=kw["log_base"])
+    mod = pkg.MelSpectrogram(**kw).to(dev)
+    g = torch.Generator().manual_seed(11)
+    x = 0.1 * torch.randn(*shape, generator=g)
+    xg = x.to(dev).requires_grad_(True)
+    out = mod(xg)
+    gout = torch.randn(out.shape, generator=g)
+    (out * gout.to(dev)).sum().backward()
+    xr = x.double().requires_grad_(True)
+    amp = _ref_amp(xr.reshape(-1, shape[-1]), mod.fft_size, mod.hop_size, mod.win_length, mod.window.cpu(), mod.eps)
+    mel = torch.clamp(amp @ mod.melmat.cpu().double(), min=mod.eps)
+    ref = torch.log(mel) / (1.0 if mod.log_base is None else math.log(mod.log_base))
+    (ref.transpose(1, 2) * gout.double()).sum().backward()
+    assert xg.grad.shape == xg.shape
+    assert rel_l2(xg.grad.cpu().numpy(), xr.grad.numpy()) <= 2e-5
+
+
+def test_explicit_mel_l1_equals_fused(dev):
+    """F.l1_loss(MelSpectrogram(y_hat), MelSpectrogram(y)) (mel_loss.py:151-154) through the explicit kernels (tcgen05
+    GEMM forward, banded adjoint backward) against the fused loss kernel."""
+    import dl_speech_enhancement_b200 as pkg
+    from oracle import spectral_oracle as so
+    y_hat, y = so.synth_pair(4, 24000, seed=99)
+    fused = pkg.MultiMelSpectrogramLoss(**MEL48).to(dev)
+    x1 = y_hat.to(dev).requires_grad_(True)
+    l1 = fused(x1, y.to(dev))
+    l1.backward()
+    mod = fused.mel_transfers[0]
+    x2 = y_hat.to(dev).requires_grad_(True)
+    l2 = torch.nn.functional.l1_loss(mod(x2), mod(y.to(dev)))
+    l2.backward()
+    assert abs(float(l1) - float(l2)) <= 1e-5 * float(l1)
+    assert rel_l2(x2.grad.cpu().numpy(), x1.grad.cpu().numpy()) <= 1e-3      # sign flips where |dL| ~ GEMM rounding
+
+
+def test_explicit_spectrogram_errors(dev):
+    import dl_speech_enhancement_b200 as pkg
     with pytest.raises(RuntimeError, match="CUDA"):
         pkg.stft(torch.randn(2, 4800), 1024, 120, 600, torch.hann_window(600))
+    w = torch.hann_window(600, device=dev).requires_grad_(True)
+    with pytest.raises(NotImplementedError, match="window"):
+        pkg.stft(torch.randn(2, 4800, device=dev), 1024, 120, 600, w)
 
 
 def test_trainer_contract(dev):
