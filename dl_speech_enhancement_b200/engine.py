@@ -234,10 +234,13 @@ class Engine:
         _abi.check(self.lib, self.lib.spl_geometry_of(ctypes.byref(tr), batch, t_len, ctypes.byref(g)))
         return g
 
-    def _counter(self, dev) -> torch.Tensor:
-        c = self._counters.get(dev)
+    def _counter(self, dev, owner=0) -> torch.Tensor:
+        """Zero-initialised, self-resetting device counter of spl_reduce_finalize: one per recipe, so that two
+        criteria evaluated concurrently on different streams never share one."""
+        key = (str(dev), owner)
+        c = self._counters.get(key)
         if c is None:
-            c = self._counters[dev] = torch.zeros(1, dtype=torch.int32, device=dev)
+            c = self._counters[key] = torch.zeros(1, dtype=torch.int32, device=dev)
         return c
 
     def _recipe(self, plans: Sequence[TransformPlan], batch: int, t_len: int, need_grad: bool, dev) -> _Recipe:
@@ -293,6 +296,7 @@ class Engine:
         rec.template, rec.nbytes = arr, ctypes.sizeof(arr)
         if len(self._recipes) > 64:
             self._recipes.clear()
+            self._counters.clear()
         self._recipes[key] = rec
         return rec
 
@@ -327,7 +331,7 @@ class Engine:
         sums_ptr, coefs_ptr = base + rec.off_sums, base + rec.off_coefs
         if group is None and (global_batch is None or global_batch == batch):
             _abi.check(lib, lib.spl_reduce_finalize(arr, n, batch, t_len, sums_ptr, _ptr(st.sc), _ptr(st.mag),
-                                                    _ptr(st.mel), coefs_ptr, self._counter(dev).data_ptr(), stream))
+                                                    _ptr(st.mel), coefs_ptr, self._counter(dev, id(rec)).data_ptr(), stream))
             st.n_launches = n + 1
         else:
             _abi.check(lib, lib.spl_reduce(arr, n, batch, t_len, sums_ptr, stream))
