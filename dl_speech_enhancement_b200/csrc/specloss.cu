@@ -245,6 +245,37 @@ int spl_launch_reduce_finalize(const spl::ReduceFinalizeParams& rf, void* stream
   return SPL_OK;
 }
 
+int spl_shape_dims(long long items, int* grid, int* wpc) {
+  int sms = 0;
+  int rc = device_sm_count(&sms);
+  if (rc) return rc;
+  const long long need = (items + 7) / 8, cap = (long long)sms * 8;       // 8 warps per CTA, 8 CTAs per SM
+  *grid = (int)(need < 1 ? 1 : (need < cap ? need : cap));
+  *wpc = 8;
+  return SPL_OK;
+}
+
+int spl_launch_shape_forward(const spl::ShapeParams& p, int grid, int wpc, void* stream) {
+  spl::shape_forward_kernel<<<grid, wpc * 32, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  SPL_CUDA(cudaGetLastError());
+  return SPL_OK;
+}
+
+int spl_launch_shape_backward(const spl::ShapeParams& p, int grid, int wpc, void* stream) {
+  static thread_local bool configured[64] = {false};
+  int rc = opt_in_smem(spl::shape_backward_kernel, configured);
+  if (rc) return rc;
+  spl::shape_backward_kernel<<<grid, wpc * 32, (size_t)wpc * spl::kShapeSpan * 4, static_cast<cudaStream_t>(stream)>>>(p);
+  SPL_CUDA(cudaGetLastError());
+  return SPL_OK;
+}
+
+int spl_launch_shape_finalize(const spl::ShapeFinalizeParams& fp, void* stream) {
+  spl::shape_finalize_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(fp);
+  SPL_CUDA(cudaGetLastError());
+  return SPL_OK;
+}
+
 int spl_launch_combine(const spl::CombineParams& cp, void* stream) {
   const long long total = (long long)cp.B * ((cp.T + 3) / 4);
   const unsigned grid = (unsigned)((total + 127) / 128);

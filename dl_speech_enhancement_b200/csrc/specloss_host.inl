@@ -16,6 +16,10 @@
 //   int spl_launch_finalize(const spl::FinalizeParams&, void* stream);
 //   int spl_launch_reduce_finalize(const spl::ReduceFinalizeParams&, void* stream);
 //   int spl_launch_combine(const spl::CombineParams&, void* stream);
+//   int spl_shape_dims(long long items, int* grid, int* wpc);      -- CTAs x warps of the shape-loss kernels
+//   int spl_launch_shape_forward(const spl::ShapeParams&, int grid, int wpc, void* stream);
+//   int spl_launch_shape_backward(const spl::ShapeParams&, int grid, int wpc, void* stream);
+//   int spl_launch_shape_finalize(const spl::ShapeFinalizeParams&, void* stream);
 namespace {
 
 constexpr long long kMaxPartialRows = 1024 * 32;      // upper bound on grid * warps per CTA on any device
@@ -377,6 +381,110 @@ int32_t spl_backward(const spl_transform* ts, int32_t n, int32_t B, int32_t T, c
   }
   cp.coefs = coefs; cp.g_sc = g_sc; cp.g_mag = g_mag; cp.g_mel = g_mel; cp.dx = dx; cp.B = B; cp.T = T;
   return spl_launch_combine(cp, stream);
+}
+
+// ---- waveform shape loss (losses/waveform_loss.py) ---------------------------------------------------------------
+static int shape_params(int rows, int T, const int32_t* winlens, int n, spl::ShapeParams* p, long long* records) {
+  if (rows < 1 || T < 1) return fail(SPL_E_INVALID, "shape loss: rows %d / T %d must be positive", rows, T);
+  if (T >= (1 << 29)) return fail(SPL_E_INVALID, "shape loss: T %d must be below 2^29", T);
+  if (!winlens || n < 1 || n > spl::kShapeMaxWin) return fail(SPL_E_INVALID, "shape loss: %d window lengths not in [1,%d]", n, spl::kShapeMaxWin);
+  std::memset(p, 0, sizeof(*p));
+  p->rows = rows; p->T = T; p->n = n;
+  long long ofs = 0;
+  for (int r = 0; r < n; ++r) {
+    if (winlens[r] < 1 || winlens[r] > T)
+      return fail(SPL_E_INVALID, "shape loss: window length %d must be in [1, T=%d] (MaxPool1d raises likewise)", winlens[r], T);
+    p->win[r] = winlens[r];
+    p->rec_ofs[r] = ofs;
+    ofs += (long long)rows * (T / winlens[r]);
+  }
+  *records = ofs;
+  return SPL_OK;
+}
+
+static long long shape_items(int rows, int T, int span = spl::kShapeSpan) { return (long long)rows * ((T + span - 1) / span); }
+
+// forward span: halve from kShapeSpan down to 128 samples until there are at least `want` warp work items
+static int shape_forward_span(int rows, int T, long long want) {
+  int span = spl::kShapeSpan;
+  while (span > 128 && shape_items(rows, T, span) < want) span >>= 1;
+  return span;
+}
+
+// grid, warps per CTA and span of the forward launch (geometry and forward must agree: one partial row per warp)
+static int shape_forward_dims(int rows, int T, int* grid, int* wpc, int* span) {
+  int g0 = 0, w0 = 0;
+  int rc = spl_shape_dims(1LL << 40, &g0, &w0);          // the device's full complement of warps
+  if (rc) return rc;
+  *span = shape_forward_span(rows, T, (long long)g0 * w0);
+  return spl_shape_dims(shape_items(rows, T, *span), grid, wpc);
+}
+
+int32_t spl_shape_geometry(int32_t rows, int32_t T, const int32_t* winlens, int32_t n, int64_t* record_count,
+                           int64_t* partial_count) {
+  spl::ShapeParams p;
+  long long recs = 0;
+  int rc = shape_params(rows, T, winlens, n, &p, &recs);
+  if (rc) return rc;
+  int grid = 0, wpc = 0, span = 0;
+  rc = shape_forward_dims(rows, T, &grid, &wpc, &span);
+  if (rc) return rc;
+  if (record_count) *record_count = recs;
+  if (partial_count) *partial_count = (int64_t)grid * wpc * n;
+  return SPL_OK;
+}
+
+int32_t spl_shape_forward(const float* x, const float* y, int32_t rows, int32_t T, const int32_t* winlens, int32_t n,
+                          int32_t* records, double* partials, double* sums, void* stream) {
+  if (!x || !y || !records || !partials || !sums) return fail(SPL_E_INVALID, "spl_shape_forward: null pointer");
+  spl::ShapeParams p;
+  long long recs = 0;
+  int rc = shape_params(rows, T, winlens, n, &p, &recs);
+  if (rc) return rc;
+  int grid = 0, wpc = 0, span = 0;
+  rc = shape_forward_dims(rows, T, &grid, &wpc, &span);
+  if (rc) return rc;
+  p.x = x; p.y = y; p.records = records; p.partials = partials; p.span = span;
+  rc = spl_launch_shape_forward(p, grid, wpc, stream);
+  if (rc) return rc;
+  spl::ReduceParams rp;
+  std::memset(&rp, 0, sizeof(rp));
+  rp.n_sums = n;
+  for (int r = 0; r < n; ++r) { rp.base[r] = partials + r; rp.stride[r] = n; rp.count[r] = grid * wpc; }
+  rp.out = sums;
+  return spl_launch_reduce(rp, stream);
+}
+
+int32_t spl_shape_finalize(const double* sums, int64_t rows_global, int32_t T, const int32_t* winlens, int32_t n,
+                           float* loss, void* stream) {
+  if (!sums || !loss) return fail(SPL_E_INVALID, "spl_shape_finalize: null pointer");
+  if (rows_global < 1) return fail(SPL_E_INVALID, "rows_global %lld < 1", (long long)rows_global);
+  spl::ShapeParams p;
+  long long recs = 0;
+  int rc = shape_params(1, T, winlens, n, &p, &recs);
+  if (rc) return rc;
+  spl::ShapeFinalizeParams fp;
+  std::memset(&fp, 0, sizeof(fp));
+  fp.n = n;
+  for (int r = 0; r < n; ++r) fp.count[r] = (double)rows_global * (T / winlens[r]);
+  fp.sums = sums; fp.loss = loss;
+  return spl_launch_shape_finalize(fp, stream);
+}
+
+int32_t spl_shape_backward(const int32_t* records, int32_t rows, int64_t rows_global, int32_t T, const int32_t* winlens,
+                           int32_t n, const float* g, float* dx, void* stream) {
+  if (!records || !g || !dx) return fail(SPL_E_INVALID, "spl_shape_backward: null pointer");
+  if (rows_global < 1) return fail(SPL_E_INVALID, "rows_global %lld < 1", (long long)rows_global);
+  spl::ShapeParams p;
+  long long recs = 0;
+  int rc = shape_params(rows, T, winlens, n, &p, &recs);
+  if (rc) return rc;
+  int grid = 0, wpc = 0;
+  rc = spl_shape_dims(shape_items(rows, T), &grid, &wpc);
+  if (rc) return rc;
+  p.records = const_cast<int32_t*>(records); p.g = g; p.dx = dx;
+  for (int r = 0; r < n; ++r) p.coef[r] = (float)(1.0 / ((double)n * (double)rows_global * (double)(T / winlens[r])));
+  return spl_launch_shape_backward(p, grid, wpc, stream);
 }
 
 }  // extern "C"

@@ -187,6 +187,14 @@ SPL_DEVICE T* launder_ptr(T* v) {
   return v;
 }
 
+SPL_DEVICE unsigned float_bits(float f) {
+#ifdef SPECLOSS_EMU
+  unsigned u; memcpy(&u, &f, 4); return u;
+#else
+  return __float_as_uint(f);
+#endif
+}
+
 SPL_DEVICE float bits_to_float(int b) {
 #ifdef SPECLOSS_EMU
   float f; memcpy(&f, &b, 4); return f;
@@ -690,6 +698,10 @@ SPL_DEVICE void spec_store(float* o, float* o_lo, int k, float a) {
   }
 }
 
+// sqrt(p4 / 4) for p4 = max(4 |X|^2, 4 eps); eps = 0 (plain |X|, torchaudio power=1) must give exactly 0 at p4 = 0, not
+// 0 * rsqrt(0) = NaN
+SPL_DEVICE float half_sqrt(float p4) { return p4 >= 1.17549435e-38f ? 0.5f * p4 * spl_fast_rsqrt(p4) : 0.f; }
+
 // [region: spectrogram]
 template <int NFFT>
 SPL_DEVICE void spec_body(const SpecParams& p, float* smem, int block, int tid, int grid, int wpc) {
@@ -750,8 +762,8 @@ SPL_DEVICE void spec_body(const SpecParams& p, float* smem, int block, int tid, 
         const float p0 = fmaxf(fmaf(x2.x, x2.x, x2.y * x2.y), eps4);
         const float p1 = fmaxf(fmaf(y2.x, y2.x, y2.y * y2.y), eps4);
         const int k = row + R * k1;
-        if (active) spec_store(o0, l0, k, 0.5f * p0 * spl_fast_rsqrt(p0));
-        if (second) spec_store(o1, l1, k, 0.5f * p1 * spl_fast_rsqrt(p1));
+        if (active) spec_store(o0, l0, k, half_sqrt(p0));
+        if (second) spec_store(o1, l1, k, half_sqrt(p1));
       }
     }
     for (int k = NFFT / 2 + 1 + l; k < p.ld; k += L) {               // pad columns of the GEMM operand
@@ -761,8 +773,8 @@ SPL_DEVICE void spec_body(const SpecParams& p, float* smem, int block, int tid, 
     if (l == 0) {                                                    // bin N/2
       const float2 a = S[G::HL];
       const float p0 = fmaxf(4.f * a.x * a.x, eps4), p1 = fmaxf(4.f * a.y * a.y, eps4);
-      if (active) spec_store(o0, l0, NFFT / 2, 0.5f * p0 * spl_fast_rsqrt(p0));
-      if (second) spec_store(o1, l1, NFFT / 2, 0.5f * p1 * spl_fast_rsqrt(p1));
+      if (active) spec_store(o0, l0, NFFT / 2, half_sqrt(p0));
+      if (second) spec_store(o1, l1, NFFT / 2, half_sqrt(p1));
     }
     __syncwarp();       // the slot's mirror halves are read above; the next pass-A store must wait for every lane
   }
@@ -822,7 +834,8 @@ SPL_DEVICE void specgrad_body(const SpecGradParams& q, float* smem, int block, i
   float2* S = reinterpret_cast<float2*>(wsm) + h * G::SLOT_F2;
   float2* msum = reinterpret_cast<float2*>(wsm + FPW * G::SLOT_F2 * 2) + h * align4(p.n_mels);
   const int total = p.B * q.n_pairs;                 // work items: (utterance, frame pair)
-  const float eps4 = 4.f * p.eps;
+  // clamp gate; never below the smallest normal, so that eps = 0 (plain |X|) gets d|X|/dX := 0 at X = 0 like torch.abs
+  const float eps4 = fmaxf(4.f * p.eps, 1.17549435e-38f);
   for (int base = (block * wpc + warp) * FPW; base < total; base += grid * wpc * FPW) {
     const int item = base + h;
     const bool active = item < total;
@@ -962,6 +975,146 @@ SPL_DEVICE void specgrad_body(const SpecGradParams& q, float* smem, int block, i
     }
     __syncwarp();          // column reads done before the next item's pass-A store
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Waveform shape loss (losses/waveform_loss.py:15-75, the third switch of TrainerGAN._metric_loss,
+// trainer/trainerGAN.py:235-239): mean over window lengths of L1(maxpool_w |y_hat|, maxpool_w |y|), MaxPool1d(w) =
+// disjoint windows [j w, (j+1) w), j < T / w.  HBM-bound: the forward reads both signals ONCE (a warp walks a span of
+// the row through every window length while the span is in L1) and leaves, per window, a 4-byte record
+// {argmax of |y_hat| (first maximum, as max_pool1d) << 2 | sign(pool(y_hat) - pool(y)) sign(y_hat[argmax]) + 1};
+// the backward writes dx once from the records.  Algorithmic bytes: 8 per sample forward + 4 backward.
+// ---------------------------------------------------------------------------------------------
+constexpr int kShapeMaxWin = 8;
+constexpr int kShapeSpan = 2048;          // samples per warp work item
+
+struct ShapeParams {
+  const float* x;        // prediction (rows, T)
+  const float* y;        // target     (rows, T)
+  int rows, T;
+  int n;                 // window lengths
+  int span;              // forward: samples per warp work item (the host shrinks it until every SM has work)
+  int win[kShapeMaxWin];
+  long long rec_ofs[kShapeMaxWin];   // first record of window length r; records of r are [rows][T / win[r]]
+  int* records;
+  double* partials;      // forward: [grid * warps per CTA][n], one row per warp
+  // backward
+  float coef[kShapeMaxWin];          // 1 / (n * rows_global * (T / win[r]))
+  const float* g;        // upstream gradient (device scalar)
+  float* dx;             // (rows, T)
+};
+
+// windows of length w that START inside [s0, s1): j in [ceil(s0 / w), ceil(s1 / w)), clipped to T / w
+SPL_DEVICE void shape_window_range(int s0, int s1, int w, int T, int& j0, int& j1) {
+  j0 = (s0 + w - 1) / w;
+  j1 = min((s1 + w - 1) / w, T / w);
+}
+
+// [region: shape forward]
+// A warp walks the windows that start inside its span, lanes across the samples of a window.  The per-window reduction
+// is three redux.sync instructions: the maximum of |x| as an unsigned (non-negative floats order like their bit
+// patterns), the smallest index that attains it (max_pool1d routes the gradient to the first maximum), the maximum of
+// |y|.  The lane that owns the argmax writes the record.
+SPL_DEVICE void shape_forward_body(const ShapeParams& p, int block, int tid, int grid, int wpc) {
+  const int warp = tid >> 5, lane = tid & 31;
+  const int span = p.span;
+  const int spans = (p.T + span - 1) / span;
+  const long long items = (long long)p.rows * spans;
+  double acc[kShapeMaxWin];
+#pragma unroll
+  for (int r = 0; r < kShapeMaxWin; ++r) acc[r] = 0.0;
+  for (long long it = (long long)block * wpc + warp; it < items; it += (long long)grid * wpc) {
+    const int row = (int)(it / spans), s0 = (int)(it - (long long)row * spans) * span;
+    const int s1 = min(s0 + span, p.T);
+    const float* __restrict__ xr = p.x + (size_t)row * p.T;
+    const float* __restrict__ yr = p.y + (size_t)row * p.T;
+#pragma unroll
+    for (int r = 0; r < kShapeMaxWin; ++r) {
+      if (r >= p.n) continue;                          // fully unrolled: acc[] stays in registers
+      const int w = p.win[r], nw = p.T / w;
+      int j0, j1;
+      shape_window_range(s0, s1, w, p.T, j0, j1);
+      int* rec = p.records + p.rec_ofs[r] + (long long)row * nw;
+      float sum = 0.f;
+      for (int j = j0; j < j1; ++j) {
+        const int base = j * w;
+        float mx = 0.f, my = 0.f, sx = 0.f;
+        int ix = 0x7fffffff;
+        for (int i = lane; i < w; i += 32) {                 // ascending i: strict > keeps the first maximum per lane
+          const float xv = __ldg(xr + base + i), yv = __ldg(yr + base + i);
+          const float ax = fabsf(xv);
+          if (ax > mx || ix == 0x7fffffff) { mx = ax; ix = base + i; sx = xv; }
+          my = fmaxf(my, fabsf(yv));
+        }
+        const unsigned mxu = __reduce_max_sync(0xffffffffu, float_bits(mx));
+        const unsigned myu = __reduce_max_sync(0xffffffffu, float_bits(my));
+        const int first = (int)__reduce_min_sync(0xffffffffu, (ix != 0x7fffffff && float_bits(mx) == mxu) ? (unsigned)ix : 0x7fffffffu);
+        const float d = bits_to_float((int)mxu) - bits_to_float((int)myu);
+        sum += fabsf(d);
+        if (ix == first) {
+          const int sd = (d > 0.f) - (d < 0.f), ss = (sx > 0.f) - (sx < 0.f);
+          rec[j] = (ix << 2) | (sd * ss + 1);
+        }
+      }
+      acc[r] += (double)sum;
+    }
+  }
+  if (lane == 0) {
+    double* o = p.partials + (size_t)(block * wpc + warp) * p.n;
+#pragma unroll
+    for (int r = 0; r < kShapeMaxWin; ++r)
+      if (r < p.n) o[r] = acc[r];
+  }
+}
+
+// [region: shape backward]
+// one warp per span: the span of dx is assembled in the warp's shared-memory tile (window lengths one after the
+// other: within one length every sample is hit at most once, so there are no conflicts and no atomics) and written
+// out with coalesced 16-byte stores.
+SPL_DEVICE void shape_backward_body(const ShapeParams& p, float* smem, int block, int tid, int grid, int wpc) {
+  const int warp = tid >> 5, lane = tid & 31;
+  float* tile = smem + warp * kShapeSpan;
+  const int spans = (p.T + kShapeSpan - 1) / kShapeSpan;
+  const long long items = (long long)p.rows * spans;
+  const float g = *p.g;
+  for (long long it = (long long)block * wpc + warp; it < items; it += (long long)grid * wpc) {
+    const int row = (int)(it / spans), s0 = (int)(it - (long long)row * spans) * kShapeSpan;
+    const int s1 = min(s0 + kShapeSpan, p.T);
+    for (int i = lane; i < kShapeSpan; i += 32) tile[i] = 0.f;
+    __syncwarp();
+    for (int r = 0; r < p.n; ++r) {
+      const int w = p.win[r], nw = p.T / w;
+      const int j0 = s0 / w, j1 = min((s1 + w - 1) / w, nw);          // windows that OVERLAP the span
+      const float c = g * p.coef[r];
+      for (int j = j0 + lane; j < j1; j += 32) {
+        const int rec = __ldg(p.records + p.rec_ofs[r] + (long long)row * nw + j);
+        const int ix = rec >> 2, sg = (rec & 3) - 1;
+        if (ix >= s0 && ix < s1) tile[ix - s0] += c * (float)sg;
+      }
+      __syncwarp();
+    }
+    float* out = p.dx + (size_t)row * p.T + s0;
+    if ((p.T & 3) == 0) {
+      for (int i = 4 * lane; i < s1 - s0; i += 128)
+        *reinterpret_cast<float4*>(out + i) = make_float4(tile[i], tile[i + 1], tile[i + 2], tile[i + 3]);
+    } else {
+      for (int i = lane; i < s1 - s0; i += 32) out[i] = tile[i];
+    }
+    __syncwarp();
+  }
+}
+
+// loss = mean over window lengths of S_r / (rows_global * (T / w_r)); one thread
+struct ShapeFinalizeParams {
+  int n;
+  double count[kShapeMaxWin];
+  const double* sums;
+  float* loss;
+};
+SPL_DEVICE void shape_finalize_body(const ShapeFinalizeParams& p) {
+  double l = 0.0;
+  for (int r = 0; r < p.n; ++r) l += __ldcg(&p.sums[r]) / p.count[r];
+  *p.loss = (float)(l / p.n);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1179,6 +1332,16 @@ __global__ void __launch_bounds__(MaxWarps<NFFT>::value * 32, 1) specgrad_kernel
   cta_load_tables<NFFT, KIND>(q.t, smem_dyn, threadIdx.x, blockDim.x);
   __syncthreads();
   specgrad_body<NFFT, KIND>(q, smem_dyn, blockIdx.x, threadIdx.x, gridDim.x, blockDim.x >> 5);
+}
+__global__ void __launch_bounds__(256) shape_forward_kernel(const ShapeParams p) {
+  shape_forward_body(p, blockIdx.x, threadIdx.x, gridDim.x, blockDim.x >> 5);
+}
+__global__ void __launch_bounds__(256) shape_backward_kernel(const ShapeParams p) {
+  extern __shared__ __align__(16) float smem_dyn[];
+  shape_backward_body(p, smem_dyn, blockIdx.x, threadIdx.x, gridDim.x, blockDim.x >> 5);
+}
+__global__ void shape_finalize_kernel(const ShapeFinalizeParams p) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) shape_finalize_body(p);
 }
 __global__ void __launch_bounds__(256) reduce_kernel(const ReduceParams p) {
   __shared__ double sh[256];

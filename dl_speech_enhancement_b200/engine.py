@@ -413,6 +413,47 @@ class Engine:
         self.launches += 2
         return dx
 
+    # -- waveform shape loss ---------------------------------------------------------------------
+    def shape_forward(self, x: torch.Tensor, y: torch.Tensor, winlens: Sequence[int], group=None,
+                      global_rows: Optional[int] = None):
+        """x, y: (rows, T) fp32 contiguous.  Returns (loss 0-dim, records, rows_global): MultiWindowShapeLoss.forward
+        (waveform_loss.py:59-75).  Launches: forward + reduce [+ all-reduce] + finalize."""
+        rows, t_len = x.shape
+        dev = x.device
+        n = len(winlens)
+        wl = (ctypes.c_int32 * n)(*[int(w) for w in winlens])
+        n_rec, n_part = ctypes.c_int64(), ctypes.c_int64()
+        _abi.check(self.lib, self.lib.spl_shape_geometry(rows, t_len, wl, n, ctypes.byref(n_rec), ctypes.byref(n_part)))
+        records = torch.empty(max(1, n_rec.value), dtype=torch.int32, device=dev)
+        partials = torch.empty(n_part.value, dtype=torch.float64, device=dev)
+        sums = torch.empty(n, dtype=torch.float64, device=dev)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        stream = self._stream(x)
+        _abi.check(self.lib, self.lib.spl_shape_forward(x.data_ptr(), y.data_ptr(), rows, t_len, wl, n, records.data_ptr(),
+                                                        partials.data_ptr(), sums.data_ptr(), stream))
+        if group is not None:
+            import torch.distributed as dist
+            dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+            if global_rows is None:
+                global_rows = rows * dist.get_world_size(group)
+        rows_global = int(global_rows) if global_rows is not None else rows
+        _abi.check(self.lib, self.lib.spl_shape_finalize(sums.data_ptr(), rows_global, t_len, wl, n, loss.data_ptr(), stream))
+        self.launches += 3
+        return loss, records, rows_global
+
+    def shape_backward(self, records: torch.Tensor, rows: int, rows_global: int, t_len: int, winlens: Sequence[int],
+                       g: torch.Tensor) -> torch.Tensor:
+        dev = records.device
+        n = len(winlens)
+        wl = (ctypes.c_int32 * n)(*[int(w) for w in winlens])
+        if g.dtype != torch.float32 or g.device != dev or g.dim() != 0:
+            g = g.detach().to(device=dev, dtype=torch.float32).reshape(())
+        dx = torch.empty(rows, t_len, dtype=torch.float32, device=dev)
+        _abi.check(self.lib, self.lib.spl_shape_backward(records.data_ptr(), rows, rows_global, t_len, wl, n, g.data_ptr(),
+                                                         dx.data_ptr(), self._stream(dx)))
+        self.launches += 1
+        return dx
+
     # -- backward --------------------------------------------------------------------------------
     def backward(self, st: ForwardState, g_sc: Optional[torch.Tensor], g_mag: Optional[torch.Tensor],
                  g_mel: Optional[torch.Tensor]) -> torch.Tensor:

@@ -129,3 +129,33 @@ def spectrogram(x: torch.Tensor, plan: TransformPlan, engine: Optional[Engine] =
 def log_mel_spectrogram(x: torch.Tensor, plan: TransformPlan, w_hi, w_lo, ld: int, log_scale: float,
                         engine: Optional[Engine] = None) -> torch.Tensor:
     return _LogMelFn.apply(x, plan, w_hi, w_lo, ld, log_scale, engine or cuda_engine())
+
+
+class _ShapeLossFn(torch.autograd.Function):
+    """MultiWindowShapeLoss.forward (waveform_loss.py:59-75) over the C ABI (spl_shape_*)."""
+
+    @staticmethod
+    def forward(ctx, x, y, winlens, engine, group):
+        x2, y2 = _as_2d(x, "prediction"), _as_2d(y, "target")
+        loss, records, rows_global = engine.shape_forward(x2.detach(), y2.detach(), winlens, group)
+        ctx.engine, ctx.winlens, ctx.x_shape = engine, winlens, x.shape
+        ctx.rows, ctx.t_len, ctx.rows_global = x2.shape[0], x2.shape[1], rows_global
+        ctx.records = records if ctx.needs_input_grad[0] else None
+        return loss
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        if ctx.needs_input_grad[1]:
+            raise NotImplementedError("gradient w.r.t. the target is not implemented (no reference caller needs it)")
+        dx = ctx.engine.shape_backward(ctx.records, ctx.rows, ctx.rows_global, ctx.t_len, ctx.winlens, g)
+        ctx.records = None
+        return dx.view(ctx.x_shape), None, None, None, None
+
+
+def shape_loss(x: torch.Tensor, y: torch.Tensor, winlens: Sequence[int], group=None,
+               engine: Optional[Engine] = None) -> torch.Tensor:
+    if engine is None:
+        _check_inputs(x, y)
+        engine = cuda_engine()
+    return _ShapeLossFn.apply(x, y, tuple(int(w) for w in winlens), engine, group)

@@ -21,7 +21,8 @@ import torch
 from . import melfb
 from ._abi import SPL_KIND_MEL, SPL_KIND_STFT
 from .engine import TransformPlan, fft_geometry, mel_gemm_weights, mel_tables, twiddle_table
-from .functional import log_mel_spectrogram, spectral_losses, spectrogram
+from .functional import log_mel_spectrogram, shape_loss, spectral_losses
+from .functional import spectrogram as _spectrogram_fn
 
 
 def _cached_plans(owner, children) -> List[TransformPlan]:
@@ -71,7 +72,26 @@ def stft(x, fft_size, hop_size, win_length, window, eps=1e-7):
     window = window.detach().to(device=x.device, dtype=torch.float32).contiguous()
     plan = TransformPlan(SPL_KIND_STFT, fft_size, hop_size, win_length, eps, window, _twiddle_on(fft_size, x.device))
     plan.validate_explicit()
-    return spectrogram(x, plan)
+    return _spectrogram_fn(x, plan)
+
+
+def spectrogram(waveform, pad, window, n_fft, hop_length, win_length, power, normalized, center=True,
+                pad_mode="reflect", onesided=True, return_complex=None):
+    """torchaudio.functional.spectrogram for the case the UnivNet multi-resolution spectral discriminator uses
+    (models/vocoder/modules/discriminator.py:556-565: pad=win_length // 2, power=1.0, normalized=False): zero-pad the
+    waveform by `pad` on both sides, then |STFT| (reflect-centred, onesided, no clamp).  waveform (..., T) fp32 CUDA ->
+    (..., n_fft // 2 + 1, #frames), differentiable w.r.t. the waveform.  Runs on the sm_100a spectrogram kernels
+    (spl_spectrogram / spl_spectrogram_backward with eps = 0); anything outside this case raises."""
+    if power != 1.0 or normalized or not center or pad_mode != "reflect" or not onesided or return_complex:
+        raise NotImplementedError("spectrogram(): only power=1.0, normalized=False, center=True, pad_mode='reflect', "
+                                  "onesided=True (the UnivNet discriminator front-end) is implemented")
+    x = _explicit_input(waveform, "spectrogram()")
+    lead = x.shape[:-1]
+    x = x.reshape(-1, x.shape[-1])
+    if pad > 0:
+        x = torch.nn.functional.pad(x, (pad, pad), "constant")
+    mag = stft(x, n_fft, hop_length, win_length, window, eps=0.0)          # (B, F, K)
+    return mag.reshape(lead + mag.shape[1:]).transpose(-1, -2)
 
 
 class SpectralConvergenceLoss(torch.nn.Module):
@@ -228,3 +248,32 @@ class SpectralLoss(torch.nn.Module):
 
     def forward(self, y_hat, y):
         return spectral_losses(y_hat, y, self.stft.plans() + self.mel.plans(), group=self.process_group)
+
+
+class WaveformShapeLoss(torch.nn.Module):
+    """L1 between the max-pooled magnitudes of prediction and target (losses/waveform_loss.py:15-38): same ctor and
+    forward(y_hat (B, 1, T), y (B, 1, T)) -> 0-dim loss, on the sm_100a shape-loss kernels (both signals read once,
+    one 4-byte record per window for the backward)."""
+
+    def __init__(self, winlen):
+        super().__init__()
+        self.winlen = winlen
+        self.process_group = None
+
+    def forward(self, y_hat, y):
+        return shape_loss(y_hat, y, [self.winlen], group=self.process_group)
+
+
+class MultiWindowShapeLoss(torch.nn.Module):
+    """Mean over window lengths of WaveformShapeLoss (losses/waveform_loss.py:41-75; criterion["shape"] of
+    trainer/trainerGAN.py:235-239).  All window lengths run in ONE pass over the two signals."""
+
+    def __init__(self, winlen=[300, 200, 100]):
+        super().__init__()
+        self.shape_losses = torch.nn.ModuleList()
+        for wl in winlen:
+            self.shape_losses += [WaveformShapeLoss(wl)]
+        self.process_group = None
+
+    def forward(self, y_hat, y):
+        return shape_loss(y_hat, y, [m.winlen for m in self.shape_losses], group=self.process_group)

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SPL_ABI_VERSION 8
+#define SPL_ABI_VERSION 9
 
 #define SPL_OK 0
 #define SPL_E_INVALID (-1)   /* bad argument / outside the supported envelope */
@@ -133,6 +133,32 @@ int32_t spl_spectrogram_backward(const spl_transform* t, const float* x, int32_t
 int32_t spl_mel_project(const float* amp_hi, const float* amp_lo, int64_t rows, int32_t ld,
                         const float* w_hi, const float* w_lo, int32_t n_mels, int32_t n_pad, int32_t frames,
                         float eps, float log_scale, float* out, void* stream);
+
+/* ---- Waveform shape loss: WaveformShapeLoss / MultiWindowShapeLoss (losses/waveform_loss.py:15-75), the third metric
+ * loss of TrainerGAN._metric_loss (trainer/trainerGAN.py:235-239):
+ *     loss = mean over r of mean |maxpool_{w_r}(|x|) - maxpool_{w_r}(|y|)|,   MaxPool1d(w) = disjoint windows, T / w of them.
+ * x, y: device (rows, T) fp32 (rows = B * C).  winlens: HOST array of n <= 8 window lengths, 1 <= w <= T.
+ * Forward leaves one 4-byte record per window (argmax of |x| and the sign of the gradient) for the backward. */
+#define SPL_SHAPE_MAX_WINDOWS 8
+
+/* Workspace sizes: records (int32) and partials (double). */
+int32_t spl_shape_geometry(int32_t rows, int32_t T, const int32_t* winlens, int32_t n, int64_t* record_count,
+                           int64_t* partial_count);
+
+/* Per-window maxima and records, then sums[r] = sum over (row, window) of |pool(x) - pool(y)| (device doubles, fixed
+ * order).  Multi-GPU: all-reduce sums (SUM) before spl_shape_finalize(). */
+int32_t spl_shape_forward(const float* x, const float* y, int32_t rows, int32_t T, const int32_t* winlens, int32_t n,
+                          int32_t* records, double* partials, double* sums, void* stream);
+
+/* loss = (1/n) sum_r sums[r] / (rows_global * (T / w_r)): L1Loss means (waveform_loss.py:21,37) and the mean over the
+ * window lengths (waveform_loss.py:70-73). */
+int32_t spl_shape_finalize(const double* sums, int64_t rows_global, int32_t T, const int32_t* winlens, int32_t n,
+                           float* loss, void* stream);
+
+/* dx (rows, T) = g * dloss/dx: the gradient autograd derives (L1 sign -> max_pool1d argmax routing -> abs sign).
+ * g: device scalar.  dx is overwritten. */
+int32_t spl_shape_backward(const int32_t* records, int32_t rows, int64_t rows_global, int32_t T, const int32_t* winlens,
+                           int32_t n, const float* g, float* dx, void* stream);
 
 #ifdef __cplusplus
 }

@@ -350,3 +350,33 @@ def synth_pair(batch: int, t_len: int, seed: int = 0) -> Tuple[torch.Tensor, tor
     y = 0.1 * torch.randn(batch, 1, t_len, generator=g)
     y_hat = y + 0.05 * torch.randn(batch, 1, t_len, generator=g)
     return y_hat, y
+
+
+# --------------------------------------------------------------------------------------
+# waveform shape loss: losses/waveform_loss.py:15-75 (WaveformShapeLoss / MultiWindowShapeLoss)
+# --------------------------------------------------------------------------------------
+def shape_loss_and_grad(y_hat, y, winlens: Sequence[int], dtype=np.float64):
+    """numpy restatement of MultiWindowShapeLoss.forward and of what autograd derives for it.
+
+    waveform_loss.py:36-38: ys = MaxPool1d(w)(|y|) (kernel = stride = w, no padding, floor mode: T // w disjoint
+    windows), loss_w = L1Loss()(ys_hat, ys) = mean |ys_hat - ys|;  :70-73: mean over the window lengths.
+    Gradient: sign(ys_hat - ys) / count routed to the first maximum of |y_hat| in the window (max_pool1d backward),
+    times sign(y_hat) there (abs backward)."""
+    x = np.asarray(y_hat, dtype=dtype)
+    shape = x.shape
+    x = x.reshape(-1, shape[-1])
+    t = np.asarray(y, dtype=dtype).reshape(x.shape)
+    rows, t_len = x.shape
+    loss = 0.0
+    grad = np.zeros_like(x)
+    for w in winlens:
+        n = t_len // w
+        ax = np.abs(x[:, :n * w]).reshape(rows, n, w)
+        ay = np.abs(t[:, :n * w]).reshape(rows, n, w)
+        px, py = ax.max(-1), ay.max(-1)
+        loss += np.abs(px - py).mean() / len(winlens)
+        arg = ax.argmax(-1)                                       # first maximum
+        idx = arg + np.arange(n)[None, :] * w
+        r = np.repeat(np.arange(rows)[:, None], n, axis=1)
+        np.add.at(grad, (r, idx), np.sign(px - py) * np.sign(x[r, idx]) / (rows * n * len(winlens)))
+    return float(loss), grad.reshape(shape)

@@ -17,8 +17,26 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
-def golden_names():
+def _all_golden():
     return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+
+
+def golden_names():
+    """Spectral-loss fixtures (tests/golden/make_golden.py)."""
+    return [n for n in _all_golden() if not n.startswith("shape_")]
+
+
+def shape_golden_names():
+    """Waveform-shape-loss fixtures (tests/golden/make_golden_shape.py)."""
+    return [n for n in _all_golden() if n.startswith("shape_")]
+
+
+def load_shape_golden(name):
+    import torch
+
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    return dict(y_hat=torch.from_numpy(z["y_hat"]), y=torch.from_numpy(z["y"]), winlens=[int(w) for w in z["winlens"]],
+                loss32=float(z["loss32"]), loss64=float(z["loss64"]), grad32=z["grad32"], grad64=z["grad64"])
 
 
 def load_golden(name):

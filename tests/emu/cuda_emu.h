@@ -51,6 +51,29 @@ static inline double __shfl_xor_sync(unsigned, double v, int lane_mask) {
   emu_warp->bar.arrive_and_wait();
   return r;
 }
+static inline unsigned __shfl_xor_sync(unsigned, unsigned v, int lane_mask) {
+  emu_warp->votes[emu_lane] = v;
+  emu_warp->bar.arrive_and_wait();
+  const unsigned r = emu_warp->votes[emu_lane ^ lane_mask];
+  emu_warp->bar.arrive_and_wait();
+  return r;
+}
+static inline unsigned __reduce_max_sync(unsigned, unsigned v) {
+  emu_warp->votes[emu_lane] = v;
+  emu_warp->bar.arrive_and_wait();
+  unsigned r = 0;
+  for (int i = 0; i < 32; ++i) r = std::max(r, emu_warp->votes[i]);
+  emu_warp->bar.arrive_and_wait();
+  return r;
+}
+static inline unsigned __reduce_min_sync(unsigned, unsigned v) {
+  emu_warp->votes[emu_lane] = v;
+  emu_warp->bar.arrive_and_wait();
+  unsigned r = 0xffffffffu;
+  for (int i = 0; i < 32; ++i) r = std::min(r, emu_warp->votes[i]);
+  emu_warp->bar.arrive_and_wait();
+  return r;
+}
 static inline unsigned __ballot_sync(unsigned, bool pred) {
   emu_warp->votes[emu_lane] = pred ? 1u : 0u;
   emu_warp->bar.arrive_and_wait();

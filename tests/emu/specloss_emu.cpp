@@ -125,6 +125,29 @@ int spl_launch_reduce_finalize(const spl::ReduceFinalizeParams& rf, void*) {
   return SPL_OK;
 }
 
+int spl_shape_dims(long long items, int* grid, int* wpc) {
+  *wpc = 3;
+  *grid = (int)std::max<long long>(1, std::min<long long>((items + 2) / 3, 5));
+  return SPL_OK;
+}
+
+int spl_launch_shape_forward(const spl::ShapeParams& p, int grid, int wpc, void*) {
+  run_grid(grid, wpc, 0, [](float*, int) {},
+           [&](float*, int block, int tid) { spl::shape_forward_body(p, block, tid, grid, wpc); });
+  return SPL_OK;
+}
+
+int spl_launch_shape_backward(const spl::ShapeParams& p, int grid, int wpc, void*) {
+  run_grid(grid, wpc, (size_t)wpc * spl::kShapeSpan * 4, [](float*, int) {},
+           [&](float* sm, int block, int tid) { spl::shape_backward_body(p, sm, block, tid, grid, wpc); });
+  return SPL_OK;
+}
+
+int spl_launch_shape_finalize(const spl::ShapeFinalizeParams& fp, void*) {
+  spl::shape_finalize_body(fp);
+  return SPL_OK;
+}
+
 int spl_launch_combine(const spl::CombineParams& cp, void*) {
   const long long total = (long long)cp.B * ((cp.T + 3) / 4);
   for (long long g = 0; g < total; ++g) spl::combine_body(cp, g);

@@ -159,3 +159,71 @@ def test_emulated_logmel_backward_matches_autograd(emu_engine, kw, t_len):
     logmel = torch.log(mel) / (1.0 if mod.log_base is None else math.log(mod.log_base))
     (logmel.transpose(1, 2) * g.double()).sum().backward()
     assert rel_l2(dx.numpy(), xr.grad.numpy()) <= 1e-5
+
+
+def test_emulated_plain_magnitude_eps0(emu_engine):
+    """eps = 0 (torchaudio power=1.0, the UnivNet discriminator front-end, discriminator.py:556-565): |X| exactly 0 and
+    a zero gradient on silent input (torch.abs backward at 0), no NaN from rsqrt(0)."""
+    from dl_speech_enhancement_b200._abi import SPL_KIND_STFT
+    from dl_speech_enhancement_b200.engine import TransformPlan, twiddle_table
+    from dl_speech_enhancement_b200.functional import spectrogram
+
+    gen = torch.Generator().manual_seed(5)
+    x = 0.1 * torch.randn(3, 1300, generator=gen)
+    x[1] = 0.0
+    window = torch.hann_window(600)
+    plan = TransformPlan(SPL_KIND_STFT, 1024, 120, 600, 0.0, window, twiddle_table(1024))
+    xg = x.clone().requires_grad_(True)
+    out = spectrogram(xg, plan, engine=emu_engine)
+    gout = torch.randn(out.shape, generator=gen)
+    (out * gout).sum().backward()
+    xr = x.double().requires_grad_(True)
+    ref = torch.stft(xr, 1024, 120, 600, window.double(), return_complex=True).abs().transpose(2, 1)
+    (ref * gout.double()).sum().backward()
+    assert torch.count_nonzero(out[1]) == 0 and torch.count_nonzero(xg.grad[1]) == 0
+    assert bool(torch.isfinite(out).all()) and bool(torch.isfinite(xg.grad).all())
+    assert rel_l2(out.detach().numpy(), ref.detach().numpy()) <= 2e-6
+    assert rel_l2(xg.grad.numpy(), xr.grad.numpy()) <= 1e-5
+
+
+def _ref_shape_loss(y_hat, y, winlens):
+    """losses/waveform_loss.py:15-75 restated with the same torch ops (MaxPool1d of |.|, L1Loss, mean over windows)."""
+    loss = 0.0
+    for w in winlens:
+        pool = torch.nn.MaxPool1d(w)
+        loss = loss + torch.nn.functional.l1_loss(pool(torch.abs(y_hat)), pool(torch.abs(y)))
+    return loss / len(winlens)
+
+
+@pytest.mark.parametrize("winlens,shape", [([300, 200, 100], (3, 1, 5003)), ([64], (2, 1, 2048)), ([7, 2500], (2, 2, 4100)),
+                                           ([1], (1, 1, 300))])
+def test_emulated_shape_loss_matches_reference_ops(emu_engine, winlens, shape):
+    from dl_speech_enhancement_b200.functional import shape_loss
+
+    gen = torch.Generator().manual_seed(sum(winlens))
+    y = 0.1 * torch.randn(*shape, generator=gen)
+    y_hat = y + 0.05 * torch.randn(*shape, generator=gen)
+    y_hat[0, 0, :600] = y[0, 0, :600]                       # equal windows: sign(0) = 0
+    y_hat[-1, -1, 700:1400] = 0.0                           # silent prediction: abs'(0) = 0, first index is the argmax
+    xg = y_hat.clone().requires_grad_(True)
+    loss = shape_loss(xg, y, winlens, engine=emu_engine)
+    (3.0 * loss).backward()
+    xr = y_hat.double().requires_grad_(True)
+    ref = _ref_shape_loss(xr, y.double(), winlens)
+    (3.0 * ref).backward()
+    assert abs(float(loss.detach()) - float(ref.detach())) <= 1e-6 * abs(float(ref.detach()))
+    assert xg.grad.shape == xg.shape
+    np.testing.assert_allclose(xg.grad.numpy(), xr.grad.numpy(), rtol=1e-6, atol=1e-12)
+
+
+@pytest.mark.parametrize("name", __import__("conftest").shape_golden_names())
+def test_emulated_shape_loss_matches_golden(emu_engine, name):
+    from conftest import load_shape_golden
+    from dl_speech_enhancement_b200.functional import shape_loss
+
+    g = load_shape_golden(name)
+    x = g["y_hat"].clone().requires_grad_(True)
+    loss = shape_loss(x, g["y"], g["winlens"], engine=emu_engine)
+    loss.backward()
+    assert abs(float(loss.detach()) - g["loss64"]) <= 1e-6 * abs(g["loss64"])
+    np.testing.assert_allclose(x.grad.numpy(), g["grad32"], rtol=1e-6, atol=1e-9)

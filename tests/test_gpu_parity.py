@@ -320,6 +320,37 @@ def test_explicit_mel_l1_equals_fused(dev):
     assert rel_l2(x2.grad.cpu().numpy(), x1.grad.cpu().numpy()) <= 1e-3      # sign flips where |dL| ~ GEMM rounding
 
 
+@pytest.mark.parametrize("fft,hop,win", [(1024, 120, 600), (2048, 240, 1200), (512, 50, 240)])
+def test_univnet_frontend_matches_torchaudio(dev, fft, hop, win):
+    """spectrogram(x, pad=win // 2, power=1.0, normalized=False).transpose(-1, -2): the front-end of the UnivNet
+    multi-resolution spectral discriminator (models/vocoder/modules/discriminator.py:556-565), forward and backward
+    against torchaudio in fp64."""
+    import torchaudio
+
+    import dl_speech_enhancement_b200 as pkg
+    g = torch.Generator().manual_seed(fft)
+    x = 0.1 * torch.randn(3, 1, 12000, generator=g)
+    x[1] = 0.0                                            # silence: |X| = 0 exactly, zero gradient, no NaN
+    window = torch.hann_window(win)
+    xg = x.to(dev).requires_grad_(True)
+    out = pkg.spectrogram(xg, pad=win // 2, window=window.to(dev), n_fft=fft, hop_length=hop, win_length=win,
+                          power=1.0, normalized=False).transpose(-1, -2)
+    xr = x.double().requires_grad_(True)
+    ref = torchaudio.functional.spectrogram(xr, pad=win // 2, window=window.double(), n_fft=fft, hop_length=hop,
+                                            win_length=win, power=1.0, normalized=False).transpose(-1, -2)
+    assert out.shape == ref.shape and out.is_contiguous()
+    gout = torch.randn(ref.shape, generator=g)
+    (out * gout.to(dev)).sum().backward()
+    (ref * gout.double()).sum().backward()
+    assert torch.count_nonzero(out[1]) == 0 and torch.count_nonzero(xg.grad[1]) == 0
+    assert bool(torch.isfinite(xg.grad).all())
+    assert rel_l2(out.detach().cpu().numpy(), ref.detach().numpy()) <= 2e-6
+    assert rel_l2(xg.grad.cpu().numpy(), xr.grad.numpy()) <= 2e-5
+    with pytest.raises(NotImplementedError):
+        pkg.spectrogram(xg, pad=0, window=window.to(dev), n_fft=fft, hop_length=hop, win_length=win, power=2.0,
+                        normalized=False)
+
+
 def test_explicit_spectrogram_errors(dev):
     import dl_speech_enhancement_b200 as pkg
     with pytest.raises(RuntimeError, match="CUDA"):
@@ -412,3 +443,43 @@ def test_two_gpu_sharded_equals_single(dev):
     plans = pkg.MultiResolutionSTFTLoss().to(dev).plans() + pkg.MultiMelSpectrogramLoss(**MEL48).to(dev).plans()
     full = eng.forward(plans, y_hat[:, 0].to(dev).contiguous(), y[:, 0].to(dev).contiguous(), False).sums.cpu()
     np.testing.assert_allclose((sums[0] + sums[1]).numpy(), full.numpy(), rtol=1e-12)
+
+
+# ---- waveform shape loss (losses/waveform_loss.py) -------------------------------------------------
+@pytest.mark.parametrize("name", __import__("conftest").shape_golden_names())
+def test_shape_loss_golden_vectors(dev, name):
+    """MultiWindowShapeLoss on the GPU against the outputs of the reference's own module (tests/golden/shape_*.npz)."""
+    import dl_speech_enhancement_b200 as pkg
+    from conftest import load_shape_golden
+    g = load_shape_golden(name)
+    crit = pkg.MultiWindowShapeLoss(winlen=g["winlens"]).to(dev)
+    x = g["y_hat"].to(dev).requires_grad_(True)
+    loss = crit(x, g["y"].to(dev))
+    loss.backward()
+    assert abs(float(loss.detach()) - g["loss64"]) <= 1e-6 * abs(g["loss64"])
+    np.testing.assert_allclose(x.grad.cpu().numpy(), g["grad32"], rtol=1e-6, atol=1e-9)
+
+
+def test_shape_loss_config2_against_oracle(dev):
+    """BASELINE configs[1] shape (16 x 1 s @ 48 kHz), default window lengths, scaled upstream gradient
+    (lambda_shape_loss, trainerGAN.py:236-237), single WaveformShapeLoss, no_grad, determinism."""
+    import dl_speech_enhancement_b200 as pkg
+    from oracle import spectral_oracle as so
+    y_hat, y = so.synth_pair(16, 48000, seed=5)
+    ref_loss, ref_grad = so.shape_loss_and_grad(y_hat.numpy(), y.numpy(), [300, 200, 100])
+    crit = pkg.MultiWindowShapeLoss().to(dev)
+    x = y_hat.to(dev).requires_grad_(True)
+    loss = crit(x, y.to(dev))
+    (45.0 * loss).backward()
+    assert abs(float(loss.detach()) - ref_loss) <= 1e-6 * ref_loss
+    np.testing.assert_allclose(x.grad.cpu().numpy(), 45.0 * ref_grad, rtol=1e-5, atol=1e-9)
+    g1 = x.grad.clone()
+    x.grad = None
+    (45.0 * crit(x, y.to(dev))).backward()
+    assert torch.equal(g1, x.grad)
+    one = pkg.WaveformShapeLoss(200).to(dev)
+    l1, _ = so.shape_loss_and_grad(y_hat.numpy(), y.numpy(), [200])
+    with torch.no_grad():
+        assert abs(float(one(y_hat.to(dev), y.to(dev))) - l1) <= 1e-6 * l1
+    with pytest.raises(RuntimeError):
+        pkg.WaveformShapeLoss(50000).to(dev)(y_hat.to(dev), y.to(dev))       # window longer than the signal

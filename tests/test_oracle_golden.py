@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import golden_names, load_golden, rel_l2
+from conftest import golden_names, load_golden, load_shape_golden, rel_l2, shape_golden_names
 from oracle import spectral_oracle as so
 
 
@@ -49,3 +49,15 @@ def test_anchor_values_config1():
     assert g["y_hat"].shape == (1, 1, 123008)
     np.testing.assert_allclose(g["loss32"], [3.015629768, 3.128701448, 3.465816498], rtol=2e-7)
     np.testing.assert_allclose(g["loss64"], [3.015577380260, 3.128702007808, 3.465816607950], rtol=1e-10)
+
+
+@pytest.mark.parametrize("name", shape_golden_names())
+def test_shape_oracle_matches_reference_module(name):
+    """oracle.shape_loss_and_grad against the outputs of the reference's own MultiWindowShapeLoss."""
+    from oracle import spectral_oracle as so
+
+    g = load_shape_golden(name)
+    loss, grad = so.shape_loss_and_grad(g["y_hat"].numpy(), g["y"].numpy(), g["winlens"])
+    assert abs(loss - g["loss64"]) <= 1e-12 * abs(g["loss64"])
+    np.testing.assert_allclose(grad, g["grad64"], rtol=1e-6, atol=1e-12)   # atol: cancelling window lengths
+    assert abs(loss - g["loss32"]) <= 1e-6 * abs(g["loss32"])
