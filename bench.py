@@ -431,8 +431,16 @@ def run_ours(args, rank, local_rank, world):
     achieved = alg_bytes / (dom["ms"] * 1e-3) / 1e9
     step_bytes = 20.0 * BATCH * T_LEN                         # bytes_min of the whole fwd+bwd
     flops = nominal_flops(BATCH, T_LEN)
+    # DRAM traffic of that kernel from the committed `ncu --set full` capture (profiles/traffic.json), per launch
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath) and dom["name"].startswith("mel_2048"):
+        with open(tpath) as f:
+            tj = json.load(f)
+        traffic, traffic_src = float(tj["dram_bytes_per_launch"]), tj["source"].split(":")[0]
     roofline = {"bound": "hbm", "kernel": "transform_kernel<" + dom["name"] + ">", "achieved": achieved, "peak": hbm_peak,
-                "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic, "traffic_source": traffic_src,
+                "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes,
                 "step_hbm_frac": step_bytes / (ms_per_step * 1e-3) / 1e9 / hbm_peak,
                 "binding_roof": "fp32 CUDA-core pipe, not HBM (SURVEY 8d: ~217 FLOP/B vs ridge ~11)",
