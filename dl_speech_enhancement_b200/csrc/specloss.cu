@@ -256,7 +256,12 @@ int spl_shape_dims(long long items, int* grid, int* wpc) {
 }
 
 int spl_launch_shape_forward(const spl::ShapeParams& p, int grid, int wpc, void* stream) {
-  spl::shape_forward_kernel<<<grid, wpc * 32, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  // 16-byte loads when blocks, rows and base pointers are 16-byte aligned
+  const bool vec = p.block > 0 && p.block % 4 == 0 && p.T % 4 == 0 &&
+                   ((reinterpret_cast<uintptr_t>(p.x) | reinterpret_cast<uintptr_t>(p.y)) & 15) == 0;
+  if (vec && p.block <= 128) spl::shape_forward_vec_kernel<1><<<grid, wpc * 32, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  else if (vec)              spl::shape_forward_vec_kernel<2><<<grid, wpc * 32, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  else                       spl::shape_forward_kernel<<<grid, wpc * 32, 0, static_cast<cudaStream_t>(stream)>>>(p);
   SPL_CUDA(cudaGetLastError());
   return SPL_OK;
 }

@@ -404,19 +404,39 @@ static int shape_params(int rows, int T, const int32_t* winlens, int n, spl::Sha
 
 static long long shape_items(int rows, int T, int span = spl::kShapeSpan) { return (long long)rows * ((T + span - 1) / span); }
 
-// forward span: halve from kShapeSpan down to 128 samples until there are at least `want` warp work items
-static int shape_forward_span(int rows, int T, long long want) {
-  int span = spl::kShapeSpan;
-  while (span > 128 && shape_items(rows, T, span) < want) span >>= 1;
-  return span;
+static long long gcd_ll(long long a, long long b) { while (b) { const long long t = a % b; a = b; b = t; } return a; }
+
+// Forward launch plan.  One-pass path: block = gcd of the window lengths when it is in [32, 256] and the least common multiple
+// fits a span; the span is then a multiple of the lcm (windows never straddle spans) holding <= kShapeMaxBlocks
+// blocks, shrunk (in lcm steps) until the device has `want` warp work items.  Otherwise: pass per window length, span
+// halved from kShapeSpan down to 128 samples.
+static void shape_forward_plan(int rows, int T, const int32_t* winlens, int n, long long want, int* span, int* block) {
+  long long g = 0, l = 1;
+  for (int r = 0; r < n; ++r) {
+    g = gcd_ll(g, winlens[r]);
+    l = l / gcd_ll(l, winlens[r]) * winlens[r];
+    if (l > spl::kShapeSpan) l = spl::kShapeSpan + 1;
+  }
+  if (g >= 32 && g <= 256 && l <= spl::kShapeSpan && l / g <= spl::kShapeMaxBlocks) {
+    long long k = spl::kShapeSpan / l;
+    if (k * (l / g) > spl::kShapeMaxBlocks) k = spl::kShapeMaxBlocks / (l / g);
+    while (k > 1 && shape_items(rows, T, (int)(k * l)) < want) --k;
+    *span = (int)(k * l);
+    *block = (int)g;
+    return;
+  }
+  int sp = spl::kShapeSpan;
+  while (sp > 128 && shape_items(rows, T, sp) < want) sp >>= 1;
+  *span = sp;
+  *block = 0;
 }
 
-// grid, warps per CTA and span of the forward launch (geometry and forward must agree: one partial row per warp)
-static int shape_forward_dims(int rows, int T, int* grid, int* wpc, int* span) {
+// grid, warps per CTA, span and block of the forward launch (geometry and forward must agree: one partial row per warp)
+static int shape_forward_dims(int rows, int T, const int32_t* winlens, int n, int* grid, int* wpc, int* span, int* block) {
   int g0 = 0, w0 = 0;
   int rc = spl_shape_dims(1LL << 40, &g0, &w0);          // the device's full complement of warps
   if (rc) return rc;
-  *span = shape_forward_span(rows, T, (long long)g0 * w0);
+  shape_forward_plan(rows, T, winlens, n, (long long)g0 * w0, span, block);
   return spl_shape_dims(shape_items(rows, T, *span), grid, wpc);
 }
 
@@ -426,8 +446,8 @@ int32_t spl_shape_geometry(int32_t rows, int32_t T, const int32_t* winlens, int3
   long long recs = 0;
   int rc = shape_params(rows, T, winlens, n, &p, &recs);
   if (rc) return rc;
-  int grid = 0, wpc = 0, span = 0;
-  rc = shape_forward_dims(rows, T, &grid, &wpc, &span);
+  int grid = 0, wpc = 0, span = 0, block = 0;
+  rc = shape_forward_dims(rows, T, winlens, n, &grid, &wpc, &span, &block);
   if (rc) return rc;
   if (record_count) *record_count = recs;
   if (partial_count) *partial_count = (int64_t)grid * wpc * n;
@@ -441,10 +461,10 @@ int32_t spl_shape_forward(const float* x, const float* y, int32_t rows, int32_t 
   long long recs = 0;
   int rc = shape_params(rows, T, winlens, n, &p, &recs);
   if (rc) return rc;
-  int grid = 0, wpc = 0, span = 0;
-  rc = shape_forward_dims(rows, T, &grid, &wpc, &span);
+  int grid = 0, wpc = 0, span = 0, block = 0;
+  rc = shape_forward_dims(rows, T, winlens, n, &grid, &wpc, &span, &block);
   if (rc) return rc;
-  p.x = x; p.y = y; p.records = records; p.partials = partials; p.span = span;
+  p.x = x; p.y = y; p.records = records; p.partials = partials; p.span = span; p.block = block;
   rc = spl_launch_shape_forward(p, grid, wpc, stream);
   if (rc) return rc;
   spl::ReduceParams rp;

@@ -987,6 +987,7 @@ SPL_DEVICE void specgrad_body(const SpecGradParams& q, float* smem, int block, i
 // ---------------------------------------------------------------------------------------------
 constexpr int kShapeMaxWin = 8;
 constexpr int kShapeSpan = 2048;          // samples per warp work item
+constexpr int kShapeMaxBlocks = 64;       // one-pass forward: blocks per span (block >= 32 samples)
 
 struct ShapeParams {
   const float* x;        // prediction (rows, T)
@@ -994,6 +995,7 @@ struct ShapeParams {
   int rows, T;
   int n;                 // window lengths
   int span;              // forward: samples per warp work item (the host shrinks it until every SM has work)
+  int block;             // forward: common divisor of the window lengths for the one-pass path, 0 = pass per length
   int win[kShapeMaxWin];
   long long rec_ofs[kShapeMaxWin];   // first record of window length r; records of r are [rows][T / win[r]]
   int* records;
@@ -1011,15 +1013,137 @@ SPL_DEVICE void shape_window_range(int s0, int s1, int w, int T, int& j0, int& j
 }
 
 // [region: shape forward]
-// A warp walks the windows that start inside its span, lanes across the samples of a window.  The per-window reduction
-// is three redux.sync instructions: the maximum of |x| as an unsigned (non-negative floats order like their bit
-// patterns), the smallest index that attains it (max_pool1d routes the gradient to the first maximum), the maximum of
-// |y|.  The lane that owns the argmax writes the record.
-SPL_DEVICE void shape_forward_body(const ShapeParams& p, int block, int tid, int grid, int wpc) {
+// Per-window reduction of one warp, lanes across the samples [base, base + w): three redux.sync instructions -- the
+// maximum of |x| as an unsigned (non-negative floats order like their bit patterns), the smallest index that attains
+// it (max_pool1d routes the gradient to the first maximum) and the maximum of |y|.  Returns (max |x|, max |y|) to
+// every lane; the lane owning the argmax gets own = true with its sample in sx and its index in ix.
+template <int NS>
+SPL_DEVICE void shape_load(const float* __restrict__ xr, const float* __restrict__ yr, int base, int w, int lane,
+                           float (&xv)[NS], float (&yv)[NS]) {
+#pragma unroll
+  for (int u = 0; u < NS; ++u) {
+    xv[u] = 0.f;
+    yv[u] = 0.f;
+    if (32 * u < w) {                                      // warp-uniform: unused slots cost one branch
+      const int i = lane + 32 * u;
+      if (i < w) { xv[u] = __ldg(xr + base + i); yv[u] = __ldg(yr + base + i); }
+    }
+  }
+}
+
+// running (max |x|, first index, sample there) and max |y| of this lane; mx starts at -1 so that the first sample
+// always takes over
+template <int NS>
+SPL_DEVICE void shape_fold(const float (&xv)[NS], const float (&yv)[NS], int base, int w, int lane, float& mx, float& my,
+                           float& sx, int& ix) {
+#pragma unroll
+  for (int u = 0; u < NS; ++u) {                           // ascending i: strict > keeps the first maximum per lane
+    if (32 * u < w) {
+      const int i = lane + 32 * u;
+      const float ax = fabsf(xv[u]);
+      if (i < w && ax > mx) { mx = ax; ix = base + i; sx = xv[u]; }
+      my = fmaxf(my, fabsf(yv[u]));
+    }
+  }
+}
+
+SPL_DEVICE void shape_finish(float mx, float my, int ix, float& mxo, float& myo, bool& own) {
+  const unsigned mine = float_bits(fmaxf(mx, 0.f));
+  const unsigned mxu = __reduce_max_sync(0xffffffffu, mine);
+  const unsigned myu = __reduce_max_sync(0xffffffffu, float_bits(my));
+  const int first = (int)__reduce_min_sync(0xffffffffu, (ix != 0x7fffffff && mine == mxu) ? (unsigned)ix : 0x7fffffffu);
+  own = ix == first;
+  mxo = bits_to_float((int)mxu);
+  myo = bits_to_float((int)myu);
+}
+
+// any window length: chunks of 256 samples, the 16 loads of a lane issued before the first compare
+SPL_DEVICE void shape_scan(const float* __restrict__ xr, const float* __restrict__ yr, int base, int w, int lane,
+                           float& mxo, float& myo, float& sx, int& ix, bool& own) {
+  float mx = -1.f, my = 0.f;
+  sx = 0.f;
+  ix = 0x7fffffff;
+  for (int c = 0; c < w; c += 256) {
+    float xv[8], yv[8];
+    shape_load<8>(xr, yr, base + c, w - c, lane, xv, yv);
+    shape_fold<8>(xv, yv, base + c, w - c, lane, mx, my, sx, ix);
+  }
+  shape_finish(mx, my, ix, mxo, myo, own);
+}
+
+SPL_DEVICE int shape_record(int ix, float d, float sx) {
+  const int sd = (d > 0.f) - (d < 0.f), ss = (sx > 0.f) - (sx < 0.f);
+  return (ix << 2) | (sd * ss + 1);
+}
+
+// one-pass path, second half: every window of every length that starts in the span [s0, s1) is combined from its
+// blocks (blk[b] = {max |x|, max |y|, x at argmax, bits(argmax)}), one window per lane
+SPL_DEVICE void shape_window_pass(const ShapeParams& p, const float4* blk, int row, int s0, int s1, int lane,
+                                  double (&acc)[kShapeMaxWin]) {
+  const int g = p.block;
+#pragma unroll
+  for (int r = 0; r < kShapeMaxWin; ++r) {
+    if (r >= p.n) continue;                                // fully unrolled: acc[] stays in registers
+    const int w = p.win[r], nw = p.T / w, m = w / g;
+    const int j0 = s0 / w, j1 = min((s1 + w - 1) / w, nw);            // s0 is a multiple of w
+    int* rec = p.records + p.rec_ofs[r] + (long long)row * nw;
+    float sum = 0.f;
+    for (int j = j0 + lane; j < j1; j += 32) {
+      const int b0 = (j * w - s0) / g;
+      float4 best = blk[b0];
+      float my = best.y;
+      for (int q = 1; q < m; ++q) {                        // ascending blocks: strict > keeps the first maximum
+        const float4 c = blk[b0 + q];
+        if (c.x > best.x) best = c;
+        my = fmaxf(my, c.y);
+      }
+      const float d = best.x - my;
+      sum += fabsf(d);
+      rec[j] = shape_record((int)float_bits(best.w), d, best.z);
+    }
+    acc[r] += (double)sum;
+  }
+}
+
+// one row of partial sums per warp (fixed span -> warp -> lane assignment: deterministic)
+SPL_DEVICE void shape_write_partials(const ShapeParams& p, double (&acc)[kShapeMaxWin], int prow, int lane) {
+#pragma unroll
+  for (int r = 0; r < kShapeMaxWin; ++r)
+    if (r < p.n) acc[r] = warp_sum(acc[r]);
+  if (lane == 0) {
+    double* o = p.partials + (size_t)prow * p.n;
+#pragma unroll
+    for (int r = 0; r < kShapeMaxWin; ++r)
+      if (r < p.n) o[r] = acc[r];
+  }
+}
+
+// [region: shape forward vec]
+// One-pass path when everything is a multiple of 4 samples (T, block): 16-byte loads, NV float4 per lane per block and
+// signal, the loads of block b+1 in flight while block b is reduced -- the kernel needs ~45 KB of loads in flight per
+// SM to keep HBM busy, which scalar loads consumed block by block do not provide.
+template <int NV>
+SPL_DEVICE void shape_load4(const float* __restrict__ xr, const float* __restrict__ yr, int base, int g4, int lane,
+                            float4 (&xv)[NV], float4 (&yv)[NV]) {
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const int q = lane + 32 * v;
+    xv[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    yv[v] = xv[v];
+    if (q < g4) {
+      xv[v] = __ldg(reinterpret_cast<const float4*>(xr + base) + q);
+      yv[v] = __ldg(reinterpret_cast<const float4*>(yr + base) + q);
+    }
+  }
+}
+
+template <int NV>
+SPL_DEVICE void shape_forward_vec_body(const ShapeParams& p, float* smem, int block, int tid, int grid, int wpc) {
   const int warp = tid >> 5, lane = tid & 31;
-  const int span = p.span;
+  const int span = p.span, g = p.block, g4 = g >> 2;
   const int spans = (p.T + span - 1) / span;
   const long long items = (long long)p.rows * spans;
+  float4* blk = reinterpret_cast<float4*>(smem) + warp * kShapeMaxBlocks;
   double acc[kShapeMaxWin];
 #pragma unroll
   for (int r = 0; r < kShapeMaxWin; ++r) acc[r] = 0.0;
@@ -1028,43 +1152,97 @@ SPL_DEVICE void shape_forward_body(const ShapeParams& p, int block, int tid, int
     const int s1 = min(s0 + span, p.T);
     const float* __restrict__ xr = p.x + (size_t)row * p.T;
     const float* __restrict__ yr = p.y + (size_t)row * p.T;
+    const int nb = (s1 - s0) / g;
+    float4 xa[NV], ya[NV], xb[NV], yb[NV];
+    if (nb > 0) shape_load4<NV>(xr, yr, s0, g4, lane, xa, ya);
+    for (int bi = 0; bi < nb; ++bi) {
+      if (bi + 1 < nb) shape_load4<NV>(xr, yr, s0 + (bi + 1) * g, g4, lane, xb, yb);
+      float mx = -1.f, my = 0.f, sx = 0.f;
+      int ix = 0x7fffffff;
 #pragma unroll
-    for (int r = 0; r < kShapeMaxWin; ++r) {
-      if (r >= p.n) continue;                          // fully unrolled: acc[] stays in registers
-      const int w = p.win[r], nw = p.T / w;
-      int j0, j1;
-      shape_window_range(s0, s1, w, p.T, j0, j1);
-      int* rec = p.records + p.rec_ofs[r] + (long long)row * nw;
-      float sum = 0.f;
-      for (int j = j0; j < j1; ++j) {
-        const int base = j * w;
-        float mx = 0.f, my = 0.f, sx = 0.f;
-        int ix = 0x7fffffff;
-        for (int i = lane; i < w; i += 32) {                 // ascending i: strict > keeps the first maximum per lane
-          const float xv = __ldg(xr + base + i), yv = __ldg(yr + base + i);
-          const float ax = fabsf(xv);
-          if (ax > mx || ix == 0x7fffffff) { mx = ax; ix = base + i; sx = xv; }
-          my = fmaxf(my, fabsf(yv));
-        }
-        const unsigned mxu = __reduce_max_sync(0xffffffffu, float_bits(mx));
-        const unsigned myu = __reduce_max_sync(0xffffffffu, float_bits(my));
-        const int first = (int)__reduce_min_sync(0xffffffffu, (ix != 0x7fffffff && float_bits(mx) == mxu) ? (unsigned)ix : 0x7fffffffu);
-        const float d = bits_to_float((int)mxu) - bits_to_float((int)myu);
-        sum += fabsf(d);
-        if (ix == first) {
-          const int sd = (d > 0.f) - (d < 0.f), ss = (sx > 0.f) - (sx < 0.f);
-          rec[j] = (ix << 2) | (sd * ss + 1);
+      for (int v = 0; v < NV; ++v) {                       // ascending index: strict > keeps the first maximum per lane
+        const int q = lane + 32 * v;
+        if (q < g4) {
+          const int i0 = s0 + bi * g + 4 * q;
+          const float xs[4] = {xa[v].x, xa[v].y, xa[v].z, xa[v].w};
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const float ax = fabsf(xs[c]);
+            if (ax > mx) { mx = ax; ix = i0 + c; sx = xs[c]; }
+          }
+          my = fmaxf(fmaxf(my, fmaxf(fabsf(ya[v].x), fabsf(ya[v].y))), fmaxf(fabsf(ya[v].z), fabsf(ya[v].w)));
         }
       }
-      acc[r] += (double)sum;
+      float mxo, myo;
+      bool own;
+      shape_finish(mx, my, ix, mxo, myo, own);
+      if (own) blk[bi] = make_float4(mxo, myo, sx, bits_to_float(ix));
+#pragma unroll
+      for (int v = 0; v < NV; ++v) { xa[v] = xb[v]; ya[v] = yb[v]; }
+    }
+    __syncwarp();
+    shape_window_pass(p, blk, row, s0, s1, lane, acc);
+    __syncwarp();
+  }
+  shape_write_partials(p, acc, block * wpc + warp, lane);
+}
+
+// A warp takes the windows that start inside its span.
+//   p.block > 0 (every window length is a multiple of p.block in [32, 256] and the span a multiple of every window length):
+//     ONE pass over the samples in blocks of p.block -- per block (max |x|, its first index, the sample there, max |y|)
+//     into the warp's shared-memory scratch -- then every window of every length is combined from its blocks, one
+//     window per lane.  Each sample is loaded once.
+//   p.block == 0 (window lengths without a usable common divisor): one pass per window length, lanes across the
+//     samples of a window (the span stays in L1 between the passes).
+SPL_DEVICE void shape_forward_body(const ShapeParams& p, float* smem, int block, int tid, int grid, int wpc) {
+  const int warp = tid >> 5, lane = tid & 31;
+  const int span = p.span;
+  const int spans = (p.T + span - 1) / span;
+  const long long items = (long long)p.rows * spans;
+  float4* blk = reinterpret_cast<float4*>(smem) + warp * kShapeMaxBlocks;     // {max|x|, max|y|, x at argmax, bits(argmax)}
+  double acc[kShapeMaxWin];
+#pragma unroll
+  for (int r = 0; r < kShapeMaxWin; ++r) acc[r] = 0.0;
+  for (long long it = (long long)block * wpc + warp; it < items; it += (long long)grid * wpc) {
+    const int row = (int)(it / spans), s0 = (int)(it - (long long)row * spans) * span;
+    const int s1 = min(s0 + span, p.T);
+    const float* __restrict__ xr = p.x + (size_t)row * p.T;
+    const float* __restrict__ yr = p.y + (size_t)row * p.T;
+    if (p.block > 0) {
+      const int g = p.block, nb = (s1 - s0) / g;           // whole blocks inside the span (windows never use a partial one)
+      for (int bi = 0; bi < nb; ++bi) {
+        float mx, my, sx;
+        int ix;
+        bool own;
+        shape_scan(xr, yr, s0 + bi * g, g, lane, mx, my, sx, ix, own);
+        if (own) blk[bi] = make_float4(mx, my, sx, bits_to_float(ix));
+      }
+      __syncwarp();
+      shape_window_pass(p, blk, row, s0, s1, lane, acc);
+      __syncwarp();
+    } else {
+#pragma unroll
+      for (int r = 0; r < kShapeMaxWin; ++r) {
+        if (r >= p.n) continue;
+        const int w = p.win[r], nw = p.T / w;
+        int j0, j1;
+        shape_window_range(s0, s1, w, p.T, j0, j1);
+        int* rec = p.records + p.rec_ofs[r] + (long long)row * nw;
+        float sum = 0.f;
+        for (int j = j0; j < j1; ++j) {
+          float mx, my, sx;
+          int ix;
+          bool own;
+          shape_scan(xr, yr, j * w, w, lane, mx, my, sx, ix, own);
+          const float d = mx - my;
+          if (lane == 0) sum += fabsf(d);
+          if (own) rec[j] = shape_record(ix, d, sx);
+        }
+        acc[r] += (double)sum;
+      }
     }
   }
-  if (lane == 0) {
-    double* o = p.partials + (size_t)(block * wpc + warp) * p.n;
-#pragma unroll
-    for (int r = 0; r < kShapeMaxWin; ++r)
-      if (r < p.n) o[r] = acc[r];
-  }
+  shape_write_partials(p, acc, block * wpc + warp, lane);
 }
 
 // [region: shape backward]
@@ -1333,8 +1511,14 @@ __global__ void __launch_bounds__(MaxWarps<NFFT>::value * 32, 1) specgrad_kernel
   __syncthreads();
   specgrad_body<NFFT, KIND>(q, smem_dyn, blockIdx.x, threadIdx.x, gridDim.x, blockDim.x >> 5);
 }
+template <int NV>
+__global__ void __launch_bounds__(256) shape_forward_vec_kernel(const ShapeParams p) {
+  __shared__ __align__(16) float scratch[8 * kShapeMaxBlocks * 4];          // 8 warps per CTA (spl_shape_dims)
+  shape_forward_vec_body<NV>(p, scratch, blockIdx.x, threadIdx.x, gridDim.x, blockDim.x >> 5);
+}
 __global__ void __launch_bounds__(256) shape_forward_kernel(const ShapeParams p) {
-  shape_forward_body(p, blockIdx.x, threadIdx.x, gridDim.x, blockDim.x >> 5);
+  __shared__ __align__(16) float scratch[8 * kShapeMaxBlocks * 4];          // 8 warps per CTA (spl_shape_dims)
+  shape_forward_body(p, scratch, blockIdx.x, threadIdx.x, gridDim.x, blockDim.x >> 5);
 }
 __global__ void __launch_bounds__(256) shape_backward_kernel(const ShapeParams p) {
   extern __shared__ __align__(16) float smem_dyn[];

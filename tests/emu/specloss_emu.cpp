@@ -132,8 +132,14 @@ int spl_shape_dims(long long items, int* grid, int* wpc) {
 }
 
 int spl_launch_shape_forward(const spl::ShapeParams& p, int grid, int wpc, void*) {
-  run_grid(grid, wpc, 0, [](float*, int) {},
-           [&](float*, int block, int tid) { spl::shape_forward_body(p, block, tid, grid, wpc); });
+  const bool vec = p.block > 0 && p.block % 4 == 0 && p.T % 4 == 0 &&
+                   ((reinterpret_cast<uintptr_t>(p.x) | reinterpret_cast<uintptr_t>(p.y)) & 15) == 0;
+  run_grid(grid, wpc, (size_t)wpc * spl::kShapeMaxBlocks * 16, [](float*, int) {},
+           [&](float* sm, int block, int tid) {
+             if (vec && p.block <= 128) spl::shape_forward_vec_body<1>(p, sm, block, tid, grid, wpc);
+             else if (vec)              spl::shape_forward_vec_body<2>(p, sm, block, tid, grid, wpc);
+             else                       spl::shape_forward_body(p, sm, block, tid, grid, wpc);
+           });
   return SPL_OK;
 }
 

@@ -196,7 +196,8 @@ def _ref_shape_loss(y_hat, y, winlens):
 
 
 @pytest.mark.parametrize("winlens,shape", [([300, 200, 100], (3, 1, 5003)), ([64], (2, 1, 2048)), ([7, 2500], (2, 2, 4100)),
-                                           ([1], (1, 1, 300))])
+                                           ([1], (1, 1, 300)), ([300, 200, 100], (2, 1, 6000)), ([400, 200], (2, 1, 4800)),
+                                           ([96, 36], (1, 2, 3001))])
 def test_emulated_shape_loss_matches_reference_ops(emu_engine, winlens, shape):
     from dl_speech_enhancement_b200.functional import shape_loss
 
@@ -213,7 +214,7 @@ def test_emulated_shape_loss_matches_reference_ops(emu_engine, winlens, shape):
     (3.0 * ref).backward()
     assert abs(float(loss.detach()) - float(ref.detach())) <= 1e-6 * abs(float(ref.detach()))
     assert xg.grad.shape == xg.shape
-    np.testing.assert_allclose(xg.grad.numpy(), xr.grad.numpy(), rtol=1e-6, atol=1e-12)
+    np.testing.assert_allclose(xg.grad.numpy(), xr.grad.numpy(), rtol=1e-6, atol=1e-8)   # atol: fp32 cancellation between window lengths
 
 
 @pytest.mark.parametrize("name", __import__("conftest").shape_golden_names())

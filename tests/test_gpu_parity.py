@@ -483,3 +483,18 @@ def test_shape_loss_config2_against_oracle(dev):
         assert abs(float(one(y_hat.to(dev), y.to(dev))) - l1) <= 1e-6 * l1
     with pytest.raises(RuntimeError):
         pkg.WaveformShapeLoss(50000).to(dev)(y_hat.to(dev), y.to(dev))       # window longer than the signal
+
+
+@pytest.mark.parametrize("winlens,t_len", [([400, 200], 48000), ([96, 36], 30001), ([7, 2500], 20000), ([256], 8192)])
+def test_shape_loss_kernel_variants(dev, winlens, t_len):
+    """Every forward variant (16-byte one-pass with 1 / 2 vectors per lane, scalar one-pass, pass per window length)
+    against the oracle."""
+    import dl_speech_enhancement_b200 as pkg
+    from oracle import spectral_oracle as so
+    y_hat, y = so.synth_pair(5, t_len, seed=len(winlens) + t_len)
+    ref_loss, ref_grad = so.shape_loss_and_grad(y_hat.numpy(), y.numpy(), winlens)
+    x = y_hat.to(dev).requires_grad_(True)
+    loss = pkg.MultiWindowShapeLoss(winlen=winlens).to(dev)(x, y.to(dev))
+    loss.backward()
+    assert abs(float(loss.detach()) - ref_loss) <= 1e-6 * ref_loss
+    np.testing.assert_allclose(x.grad.cpu().numpy(), ref_grad, rtol=1e-5, atol=1e-9)
