@@ -252,11 +252,17 @@ def run_ours(args, rank, local_rank, world):
             vec = torch.stack([sc.detach(), mag.detach(), ml.detach()])
         return dict(sx=sx, sy=sy, graph=graph, losses=(sc, mag, ml), vec=vec, launches=eng.launches - n_before)
 
-    # Variants of the captured step: the trainer's literal call sequence on one stream, and -- single GPU only --
-    # the same two criterion calls with the mel criterion on a second stream (no module/API change; NCCL all-reduces
-    # of the sharded path stay on one stream).
+    # Variants of the captured step: the trainer's literal call sequence on one stream, and the same two criterion calls
+    # with the mel criterion on a second stream (no module/API change).  Sharded runs take the second variant only when
+    # the exchange step is the in-kernel peer-memory one: NCCL collectives of one communicator stay on one stream.
+    # sharded: is the exchange step the in-kernel NVLink peer-memory one on EVERY rank (then the step holds no NCCL call)?
+    peer = 1 if (world > 1 and eng._exchanges and all(v is not None for v in eng._exchanges.values())) else 0
+    if world > 1:
+        pf = torch.tensor([peer], device=dev)
+        dist.all_reduce(pf, op=dist.ReduceOp.MIN)
+        peer = int(pf.item())
     variants = [("1 stream", losses_and_backward)]
-    if world == 1 and not args.one_stream:
+    if (world == 1 or peer) and not args.one_stream:
         variants.append(("mel criterion on a 2nd stream", losses_and_backward_2s))
     graph_ms, sets, graph_variant, graph_times = None, None, None, {}
     for vname, vfn in ([] if args.no_graph else variants):
@@ -466,7 +472,10 @@ def run_ours(args, rank, local_rank, world):
                        "eager_ms_per_step": eager_ms, "graph_ms_per_step": graph_ms,
                        "graph_variants_ms_per_step": graph_times,
                        "l2": f"inputs rotate through a pool of {n_pool} pairs = {n_pool * pair_bytes >> 20} MB > 126 MB L2",
-                       "parallelism": f"batch-sharded x{world}, one all-reduce of 10 fp64 partial sums per criterion"},
+                       "parallelism": (f"batch-sharded x{world}; the 10 fp64 partial sums are exchanged "
+                                       + ("over NVLink peer memory inside the reduce+finalize kernel of each criterion "
+                                          "(no NCCL call in the step)" if peer else
+                                          "with one NCCL all-reduce per criterion") if world > 1 else "single GPU")},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": pair_bytes, "d2h_bytes_per_step": 12,
                     "steps": e_steps, "timing": "wall clock; per step: pinned H2D of the NEXT step's inputs on a copy stream, fwd+bwd ("
                                                 + e2e_mode + "), D2H of the 3 losses + stream sync; max over ranks"},

@@ -15,7 +15,7 @@ from ctypes import POINTER, c_char_p, c_double, c_float, c_int32, c_int64, c_voi
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libspecloss.so")
 CSRC = os.path.join(_HERE, "csrc")
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 SPL_KIND_STFT = 0
 SPL_KIND_MEL = 1
@@ -47,7 +47,7 @@ class SplGeometry(ctypes.Structure):
 
 
 EXPORTS = ("spl_abi_version", "spl_last_error", "spl_fill_twiddle", "spl_geometry_of", "spl_forward",
-           "spl_reduce", "spl_finalize", "spl_reduce_finalize", "spl_backward", "spl_spectrogram", "spl_spectrogram_backward", "spl_mel_project",
+           "spl_reduce", "spl_finalize", "spl_reduce_finalize", "spl_exchange_buffer_bytes", "spl_reduce_exchange_finalize", "spl_backward", "spl_spectrogram", "spl_spectrogram_backward", "spl_mel_project",
            "spl_shape_geometry", "spl_shape_forward", "spl_shape_finalize", "spl_shape_backward")
 
 
@@ -75,6 +75,12 @@ def bind(lib: ctypes.CDLL) -> ctypes.CDLL:
     lib.spl_reduce_finalize.restype = c_int32
     lib.spl_reduce_finalize.argtypes = [POINTER(SplTransform), c_int32, c_int32, c_int32, c_void_p,
                                         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.spl_exchange_buffer_bytes.restype = c_int64
+    lib.spl_exchange_buffer_bytes.argtypes = []
+    lib.spl_reduce_exchange_finalize.restype = c_int32
+    lib.spl_reduce_exchange_finalize.argtypes = [POINTER(SplTransform), c_int32, c_int32, c_int32, c_int64, c_void_p, c_void_p,
+                                                 c_int32, c_int32, POINTER(c_void_p), c_void_p,
+                                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.spl_backward.restype = c_int32
     lib.spl_backward.argtypes = [POINTER(SplTransform), c_int32, c_int32, c_int32, c_void_p,
                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]

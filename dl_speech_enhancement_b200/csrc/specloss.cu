@@ -281,6 +281,12 @@ int spl_launch_shape_finalize(const spl::ShapeFinalizeParams& fp, void* stream) 
   return SPL_OK;
 }
 
+int spl_launch_reduce_exchange(const spl::ExchangeParams& ep, void* stream) {
+  spl::reduce_exchange_finalize_kernel<<<ep.r.n_sums, 256, 0, static_cast<cudaStream_t>(stream)>>>(ep);
+  SPL_CUDA(cudaGetLastError());
+  return SPL_OK;
+}
+
 int spl_launch_combine(const spl::CombineParams& cp, void* stream) {
   const long long total = (long long)cp.B * ((cp.T + 3) / 4);
   const unsigned grid = (unsigned)((total + 127) / 128);

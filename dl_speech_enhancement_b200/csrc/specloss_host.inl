@@ -16,6 +16,7 @@
 //   int spl_launch_finalize(const spl::FinalizeParams&, void* stream);
 //   int spl_launch_reduce_finalize(const spl::ReduceFinalizeParams&, void* stream);
 //   int spl_launch_combine(const spl::CombineParams&, void* stream);
+//   int spl_launch_reduce_exchange(const spl::ExchangeParams&, void* stream);
 //   int spl_shape_dims(long long items, int* grid, int* wpc);      -- CTAs x warps of the shape-loss kernels
 //   int spl_launch_shape_forward(const spl::ShapeParams&, int grid, int wpc, void* stream);
 //   int spl_launch_shape_backward(const spl::ShapeParams&, int grid, int wpc, void* stream);
@@ -363,6 +364,31 @@ int32_t spl_reduce_finalize(const spl_transform* ts, int32_t n, int32_t B, int32
   if (rc) return rc;
   rf.counter = counter;
   return spl_launch_reduce_finalize(rf, stream);
+}
+
+int64_t spl_exchange_buffer_bytes(void) { return (int64_t)spl::kExchangeBytes; }
+
+int32_t spl_reduce_exchange_finalize(const spl_transform* ts, int32_t n, int32_t B, int32_t T, int64_t B_global,
+                                     double* sums_local, double* sums_global, int32_t rank, int32_t world,
+                                     void* const* peer_bufs, uint32_t* state,
+                                     float* sc, float* mag, float* mel, float* coefs, void* stream) {
+  if (n < 1 || n > SPL_MAX_TRANSFORMS || !sums_local || !sums_global || !coefs || !state || !peer_bufs)
+    return fail(SPL_E_INVALID, "spl_reduce_exchange_finalize: bad n or null pointer");
+  if (world < 1 || world > spl::kMaxRanks || rank < 0 || rank >= world)
+    return fail(SPL_E_INVALID, "rank %d / world %d outside [0, %d]", rank, world, spl::kMaxRanks);
+  spl::ExchangeParams ep;
+  std::memset(&ep, 0, sizeof(ep));
+  int rc = build_reduce(ts, n, B, T, sums_local, &ep.r);
+  if (rc) return rc;
+  if (ep.r.n_sums > spl::kExchangeSums) return fail(SPL_E_INVALID, "%d sums exceed the exchange slot", ep.r.n_sums);
+  rc = build_finalize(ts, n, sums_global, B_global, T, sc, mag, mel, coefs, &ep.f);
+  if (rc) return rc;
+  ep.gsums = sums_global; ep.state = state; ep.rank = rank; ep.world = world;
+  for (int r = 0; r < world; ++r) {
+    if (!peer_bufs[r]) return fail(SPL_E_INVALID, "null symmetric buffer of rank %d", r);
+    ep.peers[r] = peer_bufs[r];
+  }
+  return spl_launch_reduce_exchange(ep, stream);
 }
 
 int32_t spl_backward(const spl_transform* ts, int32_t n, int32_t B, int32_t T, const float* coefs,

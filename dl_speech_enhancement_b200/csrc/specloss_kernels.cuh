@@ -195,6 +195,14 @@ SPL_DEVICE unsigned float_bits(float f) {
 #endif
 }
 
+SPL_DEVICE double __longlong_as_double_nan() {
+#ifdef SPECLOSS_EMU
+  return std::nan("");
+#else
+  return __longlong_as_double(0x7ff8000000000000LL);
+#endif
+}
+
 SPL_DEVICE float bits_to_float(int b) {
 #ifdef SPECLOSS_EMU
   float f; memcpy(&f, &b, 4); return f;
@@ -1359,6 +1367,97 @@ SPL_DEVICE void finalize_body(const FinalizeParams& p) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Multi-GPU: reduce -> exchange over NVLink peer memory -> finalize in ONE kernel (the single exchange step
+// of the sharded loss).  Replaces spl_reduce + ncclAllReduce(10 doubles) + spl_finalize: for an 80-byte payload the
+// collective is pure latency (two launches + NCCL's own protocol), so the last CTA of the reduction pushes this rank's
+// sums straight into every peer's symmetric buffer (peer-mapped stores), raises a flag there, waits for the peers'
+// flags in its own buffer and adds the contributions in rank order -- every rank gets bit-identical global sums.
+//   symmetric buffer (one per rank, peer-mapped):  double slots[2][kMaxRanks][16];  unsigned flags[2][kMaxRanks];
+// Calls are numbered by an epoch kept in device memory (CUDA-graph replay safe); slot/flag sets alternate with the
+// epoch's parity: a rank can be at most one call ahead of the slowest peer, so the set being written is never the set a
+// peer still reads.
+// ---------------------------------------------------------------------------------------------
+constexpr int kMaxRanks = 8;
+constexpr int kExchangeSums = 16;
+constexpr size_t kExchangeBytes = 2 * kMaxRanks * kExchangeSums * sizeof(double) + 2 * kMaxRanks * sizeof(unsigned);
+
+struct ExchangeParams {
+  ReduceParams r;          // r.out = this rank's sums (local)
+  FinalizeParams f;        // f.sums = gsums
+  double* gsums;           // local: receives the global sums
+  unsigned* state;         // local: [0] CTA ticket (self-resetting), [1] epoch of the last completed call
+  int rank, world;
+  void* peers[kMaxRanks];  // symmetric buffers of all ranks, peers[rank] = own
+};
+
+#ifdef SPECLOSS_EMU
+static inline void st_release_sys(unsigned* p, unsigned v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+static inline unsigned ld_acquire_sys(const unsigned* p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+static inline double ld_volatile_f64(const double* p) { return *reinterpret_cast<const volatile double*>(p); }
+static inline void threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+static inline long long spin_clock() { static thread_local long long c = 0; return c += 64; }
+#else
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ double ld_volatile_f64(const double* p) {
+  double v;
+  asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void threadfence_system() { __threadfence_system(); }
+__device__ __forceinline__ long long spin_clock() { return clock64(); }
+#endif
+
+// [region: exchange]
+// one warp (the first warp of the last CTA of the reduction); `lane` in [0, 32)
+SPL_DEVICE void exchange_body(const ExchangeParams& p, int lane) {
+  const int n = p.r.n_sums, world = p.world;
+  const unsigned epoch = __ldcg(&p.state[1]) + 1u;
+  const int parity = (int)(epoch & 1u);
+  // publish this rank's sums in every rank's buffer (own included)
+  for (int t = lane; t < world * n; t += 32) {
+    const int peer = t / n, j = t - peer * n;
+    double* slots = reinterpret_cast<double*>(p.peers[peer]);
+    slots[(parity * kMaxRanks + p.rank) * kExchangeSums + j] = __ldcg(&p.r.out[j]);
+  }
+  threadfence_system();
+  __syncwarp();
+  if (lane < world) {
+    unsigned* flags = reinterpret_cast<unsigned*>(reinterpret_cast<double*>(p.peers[lane]) + 2 * kMaxRanks * kExchangeSums);
+    st_release_sys(&flags[parity * kMaxRanks + p.rank], epoch);
+  }
+  // wait for every rank's contribution to this call (bounded: a missing peer poisons the result instead of hanging)
+  bool ok = true;
+  if (lane < world) {
+    const unsigned* flags = reinterpret_cast<const unsigned*>(reinterpret_cast<const double*>(p.peers[p.rank]) + 2 * kMaxRanks * kExchangeSums);
+    const long long t0 = spin_clock();
+    while (ld_acquire_sys(&flags[parity * kMaxRanks + lane]) != epoch) {
+      if (spin_clock() - t0 > 8000000000LL) { ok = false; break; }        // ~4 s at 2 GHz
+    }
+  }
+  threadfence_system();
+  ok = __ballot_sync(0xffffffffu, !ok) == 0u;
+  if (lane < n) {
+    const double* slots = reinterpret_cast<const double*>(p.peers[p.rank]);
+    double acc = 0.0;
+    for (int r = 0; r < world; ++r) acc += ld_volatile_f64(&slots[(parity * kMaxRanks + r) * kExchangeSums + lane]);   // rank order
+    p.gsums[lane] = ok ? acc : acc * __longlong_as_double_nan();
+  }
+  __syncwarp();
+  if (lane == 0) {
+    p.state[1] = epoch;
+    __threadfence();
+    finalize_body(p.f);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // backward: dx[b, i] = sum over transforms of coef * (overlap-added frame gradients), gathered
 // from the per-frame slots (no atomics: every slot has one writer, every dx sample one reader)
 // and folded over the reflect-padding margins.
@@ -1546,6 +1645,20 @@ __global__ void __launch_bounds__(256) reduce_finalize_kernel(const ReduceFinali
   if (last && threadIdx.x == 0) {
     __threadfence();
     finalize_body(p.f);
+  }
+}
+__global__ void __launch_bounds__(256) reduce_exchange_finalize_kernel(const ExchangeParams p) {
+  __shared__ double sh[256];
+  __shared__ bool last;
+  reduce_body(p.r, sh, blockIdx.x, threadIdx.x, 256);
+  if (threadIdx.x == 0) {
+    __threadfence();
+    last = atomicInc(&p.state[0], gridDim.x - 1) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (last && threadIdx.x < 32) {
+    __threadfence();
+    exchange_body(p, threadIdx.x);
   }
 }
 __global__ void __launch_bounds__(128) combine_kernel(const CombineParams p) {

@@ -214,7 +214,7 @@ class _Recipe:
     """Everything about a (plan list, batch shape, grad mode) that does not change from call to call:
     the filled ctypes transform array and the carve-up of the single per-call workspace buffer."""
     __slots__ = ("template", "nbytes", "n", "off_partials", "off_gframes", "off_sums", "off_coefs", "ws_bytes",
-                 "n_sums", "has_stft", "has_mel", "keep")
+                 "n_sums", "has_stft", "has_mel", "keep", "off_lsums", "serial")
 
 
 class Engine:
@@ -222,6 +222,8 @@ class Engine:
         self.lib = lib
         self._recipes = {}
         self._counters = {}
+        self._exchanges = {}
+        self._recipe_serial = 0
         self.launches = 0          # kernels launched so far (bench.py reports the per-step count)
 
     # -- helpers ---------------------------------------------------------------------------------
@@ -242,6 +244,38 @@ class Engine:
         if c is None:
             c = self._counters[key] = torch.zeros(1, dtype=torch.int32, device=dev)
         return c
+
+    def _exchange(self, group, dev, owner):
+        """Peer-mapped exchange buffers of one recipe for `group` (torch symmetric memory over NVLink), or None when the
+        group cannot use them (not NCCL / more than 8 ranks / SPECLOSS_NCCL_ALLREDUCE=1): the caller then all-reduces the
+        sums with NCCL.  The first call per recipe is collective (every rank builds its recipes in the same order)."""
+        key = (id(group), str(dev), owner)
+        ex = self._exchanges.get(key)
+        if ex is not None or key in self._exchanges:
+            return ex
+        ex = None
+        import torch.distributed as dist
+        world = dist.get_world_size(group)
+        usable = (dev.type == "cuda" and os.environ.get("SPECLOSS_NCCL_ALLREDUCE", "0") != "1" and 1 < world <= 8
+                  and dist.get_backend(group) == "nccl")
+        if usable:
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                nbytes = int(self.lib.spl_exchange_buffer_bytes())
+                buf = symm_mem.empty(nbytes, dtype=torch.uint8, device=dev)
+                buf.zero_()
+                hdl = symm_mem.rendezvous(buf, group)
+                torch.cuda.synchronize(dev)
+                dist.barrier(group)                    # every buffer is zero before any peer writes into it
+                ptrs = (ctypes.c_void_p * world)(*[int(p) for p in hdl.buffer_ptrs])
+                ex = dict(buf=buf, hdl=hdl, ptrs=ptrs, rank=dist.get_rank(group), world=world,
+                          state=torch.zeros(2, dtype=torch.int32, device=dev))
+            except Exception as exc:          # peer mapping unavailable (no NVLink/IPC): NCCL does the exchange instead
+                import warnings
+                warnings.warn(f"specloss: symmetric-memory exchange unavailable ({exc!r}); using NCCL all-reduce")
+                ex = None
+        self._exchanges[key] = ex
+        return ex
 
     def _recipe(self, plans: Sequence[TransformPlan], batch: int, t_len: int, need_grad: bool, dev) -> _Recipe:
         key = (tuple((p.kind, p.n_fft, p.hop, p.win, p.eps, p.n_mels, p.inv_ln_base, p.window.data_ptr(),
@@ -288,12 +322,16 @@ class Engine:
             rec.keep.extend([pl.window, pl.twiddle] + list(pl.tables.values()))
         rec.off_sums = off
         off = _align(off + 8 * n_sums)
+        rec.off_lsums = off                    # this rank's sums when the global ones come from the peer exchange
+        off = _align(off + 8 * n_sums)
         rec.off_coefs = off
         off = _align(off + 4 * 2 * n)
         rec.ws_bytes, rec.n_sums = off, n_sums
         rec.has_stft = any(p.kind == SPL_KIND_STFT for p in plans)
         rec.has_mel = any(p.kind == SPL_KIND_MEL for p in plans)
         rec.template, rec.nbytes = arr, ctypes.sizeof(arr)
+        self._recipe_serial += 1
+        rec.serial = self._recipe_serial       # same on every rank (SPMD): names the recipe's peer-exchange buffers
         if len(self._recipes) > 64:
             self._recipes.clear()
             self._counters.clear()
@@ -334,15 +372,27 @@ class Engine:
                                                     _ptr(st.mel), coefs_ptr, self._counter(dev, id(rec)).data_ptr(), stream))
             st.n_launches = n + 1
         else:
-            _abi.check(lib, lib.spl_reduce(arr, n, batch, t_len, sums_ptr, stream))
-            if group is not None:
-                import torch.distributed as dist
-                dist.all_reduce(st.sums, op=dist.ReduceOp.SUM, group=group)   # the single exchange step
+            ex = self._exchange(group, dev, rec.serial) if group is not None else None
+            if ex is not None:
+                # reduce + NVLink peer-memory exchange + finalize in one launch (spl_reduce_exchange_finalize)
                 if global_batch is None:
-                    global_batch = batch * dist.get_world_size(group)
-            _abi.check(lib, lib.spl_finalize(arr, n, sums_ptr, int(global_batch), t_len, _ptr(st.sc), _ptr(st.mag),
-                                             _ptr(st.mel), coefs_ptr, stream))
-            st.n_launches = n + 2
+                    global_batch = batch * ex["world"]
+                lsums = ws[rec.off_lsums:rec.off_lsums + 8 * rec.n_sums]
+                _abi.check(lib, lib.spl_reduce_exchange_finalize(
+                    arr, n, batch, t_len, int(global_batch), lsums.data_ptr(), sums_ptr, ex["rank"], ex["world"],
+                    ex["ptrs"], ex["state"].data_ptr(), _ptr(st.sc), _ptr(st.mag), _ptr(st.mel), coefs_ptr, stream))
+                st.keep = st.keep + (ex,)
+                st.n_launches = n + 1
+            else:
+                _abi.check(lib, lib.spl_reduce(arr, n, batch, t_len, sums_ptr, stream))
+                if group is not None:
+                    import torch.distributed as dist
+                    dist.all_reduce(st.sums, op=dist.ReduceOp.SUM, group=group)   # the single exchange step
+                    if global_batch is None:
+                        global_batch = batch * dist.get_world_size(group)
+                _abi.check(lib, lib.spl_finalize(arr, n, sums_ptr, int(global_batch), t_len, _ptr(st.sc), _ptr(st.mag),
+                                                 _ptr(st.mel), coefs_ptr, stream))
+                st.n_launches = n + 2
         self.launches += st.n_launches
         return st
 

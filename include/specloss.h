@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SPL_ABI_VERSION 9
+#define SPL_ABI_VERSION 10
 
 #define SPL_OK 0
 #define SPL_E_INVALID (-1)   /* bad argument / outside the supported envelope */
@@ -99,6 +99,22 @@ int32_t spl_finalize(const spl_transform* ts, int32_t n, const double* sums, int
  * and is left at zero by every call (it may be shared by successive calls on one stream). */
 int32_t spl_reduce_finalize(const spl_transform* ts, int32_t n, int32_t B, int32_t T, double* sums,
                             float* sc, float* mag, float* mel, float* coefs, uint32_t* counter, void* stream);
+
+/* Sharded batch (one process per GPU), the single exchange step without a collective library:
+ * spl_reduce + all-reduce(SUM) of the sums + spl_finalize in ONE launch.  The last CTA of the reduction stores this rank's
+ * sums into every rank's symmetric buffer (peer-mapped device memory: NVLink stores), raises a flag, waits for the peers'
+ * flags in its own buffer and adds the contributions in rank order, so every rank finalizes bit-identical global losses.
+ *   peer_bufs : HOST array of `world` (<= 8) device pointers, peer_bufs[r] = rank r's buffer of
+ *               spl_exchange_buffer_bytes() bytes as mapped in THIS process, zero before the first call; one buffer set
+ *               per sequence of calls that all ranks issue in the same order
+ *   state     : local device uint32[2], zero before the first call (CTA ticket, call epoch)
+ *   sums_local / sums_global : local device doubles [sum of n_sums] (this rank's sums / the global sums)
+ * A peer that does not arrive within ~4 s poisons the losses with NaN instead of hanging the stream. */
+int64_t spl_exchange_buffer_bytes(void);
+int32_t spl_reduce_exchange_finalize(const spl_transform* ts, int32_t n, int32_t B, int32_t T, int64_t B_global,
+                                     double* sums_local, double* sums_global, int32_t rank, int32_t world,
+                                     void* const* peer_bufs, uint32_t* state,
+                                     float* sc, float* mag, float* mel, float* coefs, void* stream);
 
 /* Backward: dx (B, T) = g_sc * dsc/dx + g_mag * dmag/dx + g_mel * dmel/dx -- what autograd derives for
  * the reference modules.  g_* are device scalars (NULL = 0). */

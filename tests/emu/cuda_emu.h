@@ -82,6 +82,7 @@ static inline unsigned __ballot_sync(unsigned, bool pred) {
   emu_warp->bar.arrive_and_wait();
   return r;
 }
+static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 template <typename T> static inline T __ldg(const T* p) { return *p; }
 template <typename T> static inline T __ldcg(const T* p) { return *p; }
 static inline float rsqrtf(float x) { return 1.0f / std::sqrt(x); }

@@ -154,6 +154,13 @@ int spl_launch_shape_finalize(const spl::ShapeFinalizeParams& fp, void*) {
   return SPL_OK;
 }
 
+// "ranks" of the emulated exchange are host threads of one process calling in concurrently (tests/test_distributed_gloo.py)
+int spl_launch_reduce_exchange(const spl::ExchangeParams& ep, void*) {
+  spl_launch_reduce(ep.r, nullptr);
+  run_warp([&](int lane) { spl::exchange_body(ep, lane); });
+  return SPL_OK;
+}
+
 int spl_launch_combine(const spl::CombineParams& cp, void*) {
   const long long total = (long long)cp.B * ((cp.T + 3) / 4);
   for (long long g = 0; g < total; ++g) spl::combine_body(cp, g);

@@ -56,3 +56,59 @@ def test_two_rank_sharded_equals_full_batch(emu_engine, tmp_path):
     # and both agree with the reference on the full batch
     np.testing.assert_allclose(r0["losses"], g["loss64"], rtol=1e-4)
     assert rel_l2(np.concatenate([r0["grad"], r1["grad"]]), g["grad64"].reshape(4, 6000)) <= 1e-3
+
+
+def test_peer_exchange_protocol_three_ranks(emu_engine):
+    """spl_reduce_exchange_finalize (reduce + peer-memory exchange + finalize in one launch, the NVLink path of the
+    sharded loss): three "ranks" = three host threads of this process that call into the emulated kernels concurrently,
+    their symmetric buffers being plain host arrays mapped into each other's pointer tables.  Three calls in a row
+    exercise the epoch / parity alternation.  Every rank must end with the full-batch losses, bit-identical."""
+    import ctypes
+    import threading
+
+    from conftest import load_golden, plans_for, run_losses
+
+    eng, lib = emu_engine, emu_engine.lib
+    g = load_golden("ragged_b3_t5003_2d")                     # (3, 5003): one utterance per rank
+    yh, y = g["y_hat"].reshape(3, -1), g["y"].reshape(3, -1)
+    t_len, world = yh.shape[1], 3
+    plans = plans_for(g)
+    nbytes = int(lib.spl_exchange_buffer_bytes())
+    bufs = [np.zeros(nbytes, dtype=np.uint8) for _ in range(world)]
+    results = [[None] * 3 for _ in range(world)]
+    errors = []
+
+    def rank_main(rank):
+        try:
+            ptrs = (ctypes.c_void_p * world)(*[b.ctypes.data for b in bufs])
+            state = np.zeros(2, dtype=np.uint32)
+            for call in range(3):
+                st = eng.forward(plans, yh[rank:rank + 1].contiguous(), y[rank:rank + 1].contiguous(), need_grad=False)
+                n_sums = st.sums.numel()
+                lsums, gsums = np.zeros(n_sums), np.zeros(n_sums)
+                sc, mag, mel = (np.zeros(1, dtype=np.float32) for _ in range(3))
+                coefs = np.zeros(2 * st.n, dtype=np.float32)
+                rc = lib.spl_reduce_exchange_finalize(st.transforms, st.n, 1, t_len, world, lsums.ctypes.data,
+                                                      gsums.ctypes.data, rank, world, ptrs, state.ctypes.data,
+                                                      sc.ctypes.data, mag.ctypes.data, mel.ctypes.data, coefs.ctypes.data, None)
+                assert rc == 0, lib.spl_last_error()
+                assert int(state[1]) == call + 1 and int(state[0]) == 0
+                results[rank][call] = (float(sc[0]), float(mag[0]), float(mel[0]), gsums.copy(), coefs.copy())
+        except Exception as exc:   # surfaced in the main thread
+            errors.append(exc)
+
+    threads = [threading.Thread(target=rank_main, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=120)
+    assert not errors, errors
+    assert all(not t.is_alive() for t in threads)
+    full, _ = run_losses(eng, g)
+    for call in range(3):
+        for rank in range(world):
+            sc, mag, mel, gsums, coefs = results[rank][call]
+            np.testing.assert_allclose([sc, mag, mel], full, rtol=1e-6)
+            assert (sc, mag, mel) == results[0][call][:3]
+            np.testing.assert_array_equal(gsums, results[0][call][3])
+            np.testing.assert_array_equal(coefs, results[0][call][4])
