@@ -150,14 +150,14 @@ def frames(x: torch.Tensor, n_fft: int, hop: int, win_length: int, window: str) 
         raise RuntimeError("reflect padding needs T > n_fft/2 (torch.stft raises likewise)")
     xp = torch.nn.functional.pad(x.unsqueeze(1), (half, half), mode="reflect").squeeze(1)
     fr = xp.unfold(-1, n_fft, hop)
-    return fr * padded_window(window, win_length, n_fft, x.dtype)
+    return fr * padded_window(window, win_length, n_fft, x.dtype).to(x.device)
 
 
 def spectrum(x: torch.Tensor, n_fft: int, hop: int, win_length: int, window: str,
              use_torch_stft: bool = False) -> torch.Tensor:
     """Complex one-sided STFT laid out (B, F, K)."""
     if use_torch_stft:
-        w = getattr(torch, window)(win_length, dtype=torch.float32).to(x.dtype)
+        w = getattr(torch, window)(win_length, dtype=torch.float32).to(device=x.device, dtype=x.dtype)
         return torch.stft(x, n_fft, hop, win_length, w, return_complex=True).transpose(1, 2)
     return torch.fft.rfft(frames(x, n_fft, hop, win_length, window), dim=-1)
 
@@ -224,7 +224,7 @@ def log_mel(x, r: MelRes, use_torch_stft=False) -> torch.Tensor:
     """(B, num_mels, F) log-mel spectrogram, losses/mel_loss.py:74-94."""
     x = _flat(x)
     amp = magnitude(x, r.fft_size, r.hop_size, r.win(), r.window, r.eps, use_torch_stft)
-    mel = torch.clamp(torch.matmul(amp, melmat(r, x.dtype)), min=r.eps)
+    mel = torch.clamp(torch.matmul(amp, melmat(r, x.dtype).to(x.device)), min=r.eps)
     return _logfn(r.log_base)(mel).transpose(1, 2)
 
 
@@ -240,7 +240,7 @@ def losses_and_grad(x, y, stft_res, mel_res, weights=(1.0, 1.0, 1.0), dtype=torc
     """Autograd route: returns (sc, mag, mel) as python floats and d(w.sc+w.mag+w.mel)/dx."""
     xx = x.detach().to(dtype).clone().requires_grad_(True)
     yy = y.detach().to(dtype)
-    zero = torch.zeros((), dtype=dtype)
+    zero = torch.zeros((), dtype=dtype, device=xx.device)
     sc, mag = mr_stft_loss(xx, yy, stft_res, use_torch_stft) if stft_res else (zero, zero)
     mel = multi_mel_loss(xx, yy, mel_res, use_torch_stft) if mel_res else zero
     total = weights[0] * sc + weights[1] * mag + weights[2] * mel
