@@ -498,3 +498,30 @@ def test_shape_loss_kernel_variants(dev, winlens, t_len):
     loss.backward()
     assert abs(float(loss.detach()) - ref_loss) <= 1e-6 * ref_loss
     np.testing.assert_allclose(x.grad.cpu().numpy(), ref_grad, rtol=1e-5, atol=1e-9)
+
+
+@pytest.mark.parametrize("tag,batch,t_len,mel_kw", [("configs[3]: 256 x 4 s @ 48 kHz", 256, 192000, MEL48),
+                                                    ("configs[4]: 64 x 60 s @ 24 kHz", 64, 1440000, MEL24)])
+def test_full_size_configs_tiled_batch_invariance(dev, tag, batch, t_len, mel_kw):
+    """BASELINE's largest configurations at FULL size on one GPU, through a size-independent property: a batch that
+    tiles two distinct utterances has the same losses as those two alone (ratios of norms and means do not see the
+    tiling) and per-row gradients scaled by 2 / batch -- so the fp64 oracle of the 2-utterance batch pins the losses of
+    the full-size run, row indexing and the 64-bit offsets of the multi-GB workspace included."""
+    from oracle import spectral_oracle as so
+    y_hat2, y2 = so.synth_pair(2, t_len, seed=batch)
+    ref, gref = so.losses_and_grad(y_hat2, y2, so.DEFAULT_STFT, so.mel_from_kwargs(**mel_kw), dtype=torch.float64)
+    stft, mel = _modules({}, mel_kw, dev)
+    reps = batch // 2
+    x = y_hat2.to(dev).repeat(reps, 1, 1).requires_grad_(True)          # rows 0,1,0,1,...
+    t = y2.to(dev).repeat(reps, 1, 1)
+    sc, mag = stft(x, t)
+    ml = mel(x, t)
+    (sc + mag + ml).backward()
+    vals = [float(sc.detach()), float(mag.detach()), float(ml.detach())]
+    print(tag, "ours", vals, "oracle (2 utterances, fp64)", ref)
+    np.testing.assert_allclose(vals, ref, rtol=LOSS_RTOL)
+    g = x.grad.reshape(reps, 2, t_len)
+    assert torch.equal(g[0], g[reps - 1]) and torch.equal(g[0], g[reps // 2])      # every tile gets the same rows, bit for bit
+    assert rel_l2((g[reps - 1] * reps).cpu().numpy(), gref.reshape(2, t_len).numpy()) <= GRAD_RTOL
+    del x, t, g
+    torch.cuda.empty_cache()
