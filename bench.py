@@ -145,11 +145,12 @@ def run_reference(args, rank, world):
     times, cores = cpu_reference_step_time(b, T_LEN, args.steps, args.warmup)
     ms = 1000.0 * sum(times) / len(times)
     value = b * T_LEN / FS / (ms / 1000.0)
-    sample = f"{b} x 1 s @ 48 kHz per step (of the 16 x 1 s workload), {args.steps} steps, mean"
+    sample = f"{b} x {T_LEN / FS:g} s @ 48 kHz per step (of the {BATCH} x {T_LEN / FS:g} s workload), {args.steps} steps, mean"
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "configs[1]: batch 16 x 1 s synthetic 48 kHz, MR-STFT(1024/2048/512) + 80-mel hop-300, fwd+bwd",
+            "config": {"workload": ("configs[1]: " if (BATCH, T_LEN) == (16, 48000) else "non-default size: ")
+                                   + f"batch {BATCH} x {T_LEN / FS:g} s synthetic 48 kHz, MR-STFT(1024/2048/512) + 80-mel hop-300, fwd+bwd",
                        "reference_path": "torch.stft + ATen elementwise/norm/matmul + autograd on CPU (oracle port of losses/stft_loss.py, losses/mel_loss.py)"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -475,7 +476,7 @@ def run_ours(args, rank, local_rank, world):
     # DRAM traffic of that kernel from the committed `ncu --set full` capture (profiles/traffic.json), per launch
     traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath) and dom["name"].startswith("mel_2048"):
+    if os.path.exists(tpath) and dom["name"].startswith("mel_2048") and (BATCH, T_LEN) == (16, 48000):
         with open(tpath) as f:
             tj = json.load(f)
         traffic, traffic_src = float(tj["dram_bytes_per_launch"]), tj["source"].split(":")[0]
@@ -492,10 +493,11 @@ def run_ours(args, rank, local_rank, world):
     # ---- CPU baseline beside it (rank 0, N=1 only): bounded sample of the same workload -------------
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        times, cores = cpu_reference_step_time(BATCH, T_LEN, 10, 1)
+        cpu_steps = 10 if BATCH * T_LEN <= 16 * 48000 else 3        # bounded: ~1.3 s at configs[1], a few seconds beyond
+        times, cores = cpu_reference_step_time(BATCH, T_LEN, cpu_steps, 1)
         best = min(times)
         cpu = {"value": BATCH * T_LEN / FS / best, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"the full 16 x 1 s workload, 10 steps after 1 warm-up, best step {best * 1e3:.1f} ms "
+               "sample": f"the full {BATCH} x {T_LEN / FS:g} s workload, {cpu_steps} steps after 1 warm-up, best step {best * 1e3:.1f} ms "
                          f"(mean {1e3 * sum(times) / len(times):.1f} ms); torch {torch.__version__} CPU ops, {os.cpu_count()} host cores"}
 
         try:
@@ -510,7 +512,8 @@ def run_ours(args, rank, local_rank, world):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "configs[1]: batch 16 x 1 s synthetic 48 kHz per GPU, MR-STFT(1024/2048/512) + 80-mel hop-300, fwd+bwd",
+            "config": {"workload": ("configs[1]: " if (BATCH, T_LEN) == (16, 48000) else "non-default size: ")
+                                   + f"batch {BATCH} x {T_LEN / FS:g} s synthetic 48 kHz per GPU, MR-STFT(1024/2048/512) + 80-mel hop-300, fwd+bwd",
                        "global_batch": world * BATCH, "samples_per_utterance": T_LEN, "fs": FS,
                        "api": "drop-in nn.Modules (MultiResolutionSTFTLoss + MultiMelSpectrogramLoss), " + mode,
                        "eager_ms_per_step": eager_ms, "graph_ms_per_step": graph_ms,
@@ -530,18 +533,22 @@ def run_ours(args, rank, local_rank, world):
 
 
 def main():
+    global BATCH, T_LEN
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--batch", type=int, default=BATCH, help="utterances per GPU (default: BASELINE configs[1], 16)")
+    ap.add_argument("--seconds", type=float, default=T_LEN / FS, help="utterance length in seconds at 48 kHz (default 1)")
     ap.add_argument("--no-graph", action="store_true", help="skip the CUDA-graph replay measurement")
     ap.add_argument("--one-stream", action="store_true",
                     help="do not try the captured step with the mel criterion on a second stream")
     ap.add_argument("--verbose", action="store_true", help="stage-by-stage progress on stderr")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    BATCH, T_LEN = int(args.batch), int(round(args.seconds * FS))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
