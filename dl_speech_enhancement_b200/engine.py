@@ -192,18 +192,27 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
 
 class ForwardState:
     """What backward needs: the ctypes transform array (pointers into the workspace kept alive here)."""
-    __slots__ = ("transforms", "n", "keep", "coefs", "batch", "t_len", "has_grad", "sc", "mag", "mel", "sums",
-                 "n_launches")
+    __slots__ = ("transforms", "n", "keep", "batch", "t_len", "has_grad", "sc", "mag", "mel", "n_launches",
+                 "ws", "off_sums", "off_coefs", "n_sums", "coefs_ptr", "device")
 
     def __init__(self):
         self.transforms = None
         self.n = 0
         self.keep = None
-        self.coefs = self.sums = None
+        self.ws = None
         self.batch = self.t_len = 0
         self.has_grad = False
         self.sc = self.mag = self.mel = None
         self.n_launches = 0
+
+    # views into the workspace, made on demand (the hot path only needs their addresses)
+    @property
+    def sums(self) -> torch.Tensor:
+        return self.ws[self.off_sums:self.off_sums + 8 * self.n_sums].view(torch.float64)
+
+    @property
+    def coefs(self) -> torch.Tensor:
+        return self.ws[self.off_coefs:self.off_coefs + 8 * self.n].view(torch.float32)
 
 
 def _align(n: int, a: int = 256) -> int:
@@ -214,13 +223,14 @@ class _Recipe:
     """Everything about a (plan list, batch shape, grad mode) that does not change from call to call:
     the filled ctypes transform array and the carve-up of the single per-call workspace buffer."""
     __slots__ = ("template", "nbytes", "n", "off_partials", "off_gframes", "off_sums", "off_coefs", "ws_bytes",
-                 "n_sums", "has_stft", "has_mel", "keep", "off_lsums", "serial")
+                 "n_sums", "has_stft", "has_mel", "keep", "off_lsums", "serial", "plan_refs")
 
 
 class Engine:
     def __init__(self, lib: ctypes.CDLL):
         self.lib = lib
         self._recipes = {}
+        self._recipes_by_id = {}
         self._counters = {}
         self._exchanges = {}
         self._recipe_serial = 0
@@ -229,7 +239,13 @@ class Engine:
     # -- helpers ---------------------------------------------------------------------------------
     @staticmethod
     def _stream(ref: torch.Tensor):
-        return ctypes.c_void_p(torch.cuda.current_stream(ref.device).cuda_stream) if ref.is_cuda else None
+        """The caller's current CUDA stream as a raw handle (None for the CPU emulator of the test-suite)."""
+        if not ref.is_cuda:
+            return None
+        raw = getattr(torch._C, "_cuda_getCurrentRawStream", None)      # no Stream object: ~10x cheaper per call
+        if raw is not None:
+            return ctypes.c_void_p(raw(ref.device.index if ref.device.index is not None else torch.cuda.current_device()))
+        return ctypes.c_void_p(torch.cuda.current_stream(ref.device).cuda_stream)
 
     def geometry(self, tr: SplTransform, batch: int, t_len: int) -> SplGeometry:
         g = SplGeometry()
@@ -278,11 +294,21 @@ class Engine:
         return ex
 
     def _recipe(self, plans: Sequence[TransformPlan], batch: int, t_len: int, need_grad: bool, dev) -> _Recipe:
+        # fast path: the same plan OBJECTS as last time (modules cache their plans until a buffer moves; the recipe keeps
+        # them alive, so an id cannot be recycled while its entry exists)
+        fast = (tuple(map(id, plans)), batch, t_len, need_grad, dev)
+        rec = self._recipes_by_id.get(fast)
+        if rec is not None:
+            return rec
         key = (tuple((p.kind, p.n_fft, p.hop, p.win, p.eps, p.n_mels, p.inv_ln_base, p.window.data_ptr(),
                       p.twiddle.data_ptr()) + tuple(t.data_ptr() for t in p.tables.values()) for p in plans),
                batch, t_len, need_grad, str(dev))
         rec = self._recipes.get(key)
         if rec is not None:
+            if len(self._recipes_by_id) > 256:
+                self._recipes_by_id.clear()
+            self._recipes_by_id[fast] = rec
+            rec.plan_refs.append(tuple(plans))
             return rec
         if len(plans) < 1 or len(plans) > _abi.SPL_MAX_TRANSFORMS:
             raise RuntimeError(f"{len(plans)} resolutions: supported range is 1..{_abi.SPL_MAX_TRANSFORMS}")
@@ -334,8 +360,11 @@ class Engine:
         rec.serial = self._recipe_serial       # same on every rank (SPMD): names the recipe's peer-exchange buffers
         if len(self._recipes) > 64:
             self._recipes.clear()
+            self._recipes_by_id.clear()
             self._counters.clear()
         self._recipes[key] = rec
+        rec.plan_refs = [tuple(plans)]
+        self._recipes_by_id[fast] = rec
         return rec
 
     # -- forward ---------------------------------------------------------------------------------
@@ -361,8 +390,8 @@ class Engine:
         st.sc = torch.empty((), dtype=torch.float32, device=dev) if rec.has_stft else None
         st.mag = torch.empty((), dtype=torch.float32, device=dev) if rec.has_stft else None
         st.mel = torch.empty((), dtype=torch.float32, device=dev) if rec.has_mel else None
-        st.sums = ws[rec.off_sums:rec.off_sums + 8 * rec.n_sums].view(torch.float64)
-        st.coefs = ws[rec.off_coefs:rec.off_coefs + 8 * n].view(torch.float32)
+        st.ws, st.off_sums, st.off_coefs, st.n_sums, st.device = ws, rec.off_sums, rec.off_coefs, rec.n_sums, dev
+        st.coefs_ptr = base + rec.off_coefs
         stream = self._stream(x)
         lib = self.lib
         _abi.check(lib, lib.spl_forward(arr, n, x.data_ptr(), y.data_ptr(), batch, t_len, stream))
@@ -509,7 +538,7 @@ class Engine:
                  g_mel: Optional[torch.Tensor]) -> torch.Tensor:
         if not st.has_grad:
             raise RuntimeError("backward requested but forward ran without gradient workspace")
-        dev = st.coefs.device
+        dev = st.device
         dx = torch.empty(st.batch, st.t_len, dtype=torch.float32, device=dev)
 
         def scalar(g):
@@ -520,7 +549,7 @@ class Engine:
             return g
 
         gs = (scalar(g_sc), scalar(g_mag), scalar(g_mel))
-        _abi.check(self.lib, self.lib.spl_backward(st.transforms, st.n, st.batch, st.t_len, st.coefs.data_ptr(),
+        _abi.check(self.lib, self.lib.spl_backward(st.transforms, st.n, st.batch, st.t_len, st.coefs_ptr,
                                                    _ptr(gs[0]), _ptr(gs[1]), _ptr(gs[2]), dx.data_ptr(),
                                                    self._stream(dx)))
         self.launches += 1

@@ -82,8 +82,8 @@ def test_peer_exchange_protocol_three_ranks(emu_engine):
         try:
             ptrs = (ctypes.c_void_p * world)(*[b.ctypes.data for b in bufs])
             state = np.zeros(2, dtype=np.uint32)
-            for call in range(3):
-                st = eng.forward(plans, yh[rank:rank + 1].contiguous(), y[rank:rank + 1].contiguous(), need_grad=False)
+            st = eng.forward(plans, yh[rank:rank + 1].contiguous(), y[rank:rank + 1].contiguous(), need_grad=False)
+            for call in range(3):                                # the partial sums stay valid: three exchanges of them
                 n_sums = st.sums.numel()
                 lsums, gsums = np.zeros(n_sums), np.zeros(n_sums)
                 sc, mag, mel = (np.zeros(1, dtype=np.float32) for _ in range(3))
