@@ -90,3 +90,23 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_abi, "LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(_abi.SpecLossError):
         _abi.load_library()
+
+
+def test_new_entry_points_reject_bad_arguments(lib):
+    """Argument checks of the widened ABI (shape loss, spectrogram backward, peer exchange) run before any launch."""
+    wl = (ctypes.c_int32 * 3)(300, 200, 100)
+    n_rec, n_part = ctypes.c_int64(), ctypes.c_int64()
+    assert lib.spl_shape_geometry(2, 250, wl, 3, ctypes.byref(n_rec), ctypes.byref(n_part)) == -1      # window > T
+    assert "window length" in lib.spl_last_error().decode()
+    assert lib.spl_shape_geometry(2, 9000, wl, 9, ctypes.byref(n_rec), ctypes.byref(n_part)) == -1     # > 8 windows
+    assert lib.spl_shape_forward(None, None, 2, 9000, wl, 3, None, None, None, None) == -1
+    assert lib.spl_shape_backward(None, 2, 2, 9000, wl, 3, None, None, None) == -1
+    assert lib.spl_spectrogram_backward(ctypes.byref(_tr()), None, 2, 9000, None, 513, None, None) == -1
+    assert "null" in lib.spl_last_error().decode()
+    assert lib.spl_exchange_buffer_bytes() == 2 * 8 * 16 * 8 + 2 * 8 * 4
+    dummy = (ctypes.c_double * 16)()
+    state = (ctypes.c_uint32 * 2)()
+    ptrs = (ctypes.c_void_p * 2)(ctypes.addressof(dummy), ctypes.addressof(dummy))
+    rc = lib.spl_reduce_exchange_finalize(ctypes.byref(_tr()), 1, 2, 9000, 4, ctypes.addressof(dummy), ctypes.addressof(dummy),
+                                          5, 2, ptrs, ctypes.addressof(state), None, None, None, ctypes.addressof(dummy), None)
+    assert rc == -1 and "rank" in lib.spl_last_error().decode()
