@@ -1,5 +1,6 @@
 """Host-side driver of the C ABI: builds the per-resolution constant tables, sizes the per-call
-workspace and issues spl_forward / spl_reduce / [all-reduce] / spl_finalize / spl_backward.
+workspace and issues spl_forward / spl_reduce_finalize (one GPU) or spl_reduce_exchange_finalize (sharded: the
+partial sums cross NVLink inside that kernel; NCCL all-reduce as fallback) / spl_backward.
 
 All buffers are torch tensors (device memory, caching allocator, current stream); the library
 itself never allocates or synchronises.  Nothing here computes losses or gradients in Python.
