@@ -15,7 +15,7 @@ from ctypes import POINTER, c_char_p, c_double, c_float, c_int32, c_int64, c_voi
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libspecloss.so")
 CSRC = os.path.join(_HERE, "csrc")
-ABI_VERSION = 10
+ABI_VERSION = 11
 
 SPL_KIND_STFT = 0
 SPL_KIND_MEL = 1
@@ -48,7 +48,8 @@ class SplGeometry(ctypes.Structure):
 
 EXPORTS = ("spl_abi_version", "spl_last_error", "spl_fill_twiddle", "spl_geometry_of", "spl_forward",
            "spl_reduce", "spl_finalize", "spl_reduce_finalize", "spl_exchange_buffer_bytes", "spl_reduce_exchange_finalize", "spl_backward", "spl_spectrogram", "spl_spectrogram_backward", "spl_mel_project",
-           "spl_shape_geometry", "spl_shape_forward", "spl_shape_finalize", "spl_shape_backward")
+           "spl_shape_geometry", "spl_shape_forward", "spl_shape_finalize", "spl_shape_backward",
+           "spl_mag_loss_geometry", "spl_mag_loss_forward", "spl_mag_loss_backward")
 
 
 class SpecLossError(RuntimeError):
@@ -103,6 +104,13 @@ def bind(lib: ctypes.CDLL) -> ctypes.CDLL:
     lib.spl_shape_backward.restype = c_int32
     lib.spl_shape_backward.argtypes = [c_void_p, c_int32, c_int64, c_int32, POINTER(c_int32), c_int32,
                                        c_void_p, c_void_p, c_void_p]
+    lib.spl_mag_loss_geometry.restype = c_int32
+    lib.spl_mag_loss_geometry.argtypes = [c_int64, POINTER(c_int64)]
+    lib.spl_mag_loss_forward.restype = c_int32
+    lib.spl_mag_loss_forward.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.spl_mag_loss_backward.restype = c_int32
+    lib.spl_mag_loss_backward.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                          c_void_p]
     ver = lib.spl_abi_version()
     if ver != ABI_VERSION:
         raise SpecLossError(f"libspecloss ABI version {ver}, expected {ABI_VERSION}")

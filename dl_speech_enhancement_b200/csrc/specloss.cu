@@ -287,6 +287,27 @@ int spl_launch_reduce_exchange(const spl::ExchangeParams& ep, void* stream) {
   return SPL_OK;
 }
 
+int spl_launch_mag_sums(const spl::MagLossParams& p, int grid, int wpc, void* stream) {
+  spl::mag_sums_kernel<<<grid, wpc * 32, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  SPL_CUDA(cudaGetLastError());
+  return SPL_OK;
+}
+
+int spl_launch_mag_backward(const spl::MagLossParams& p, void* stream) {
+  int grid = 0, wpc = 0;
+  int rc = spl_shape_dims((p.n + 2047) / 2048, &grid, &wpc);      // persistent: at most 8 CTAs of 8 warps per SM
+  if (rc) return rc;
+  spl::mag_backward_kernel<<<grid, wpc * 32, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  SPL_CUDA(cudaGetLastError());
+  return SPL_OK;
+}
+
+int spl_launch_mag_finalize(const spl::MagFinalizeParams& fp, void* stream) {
+  spl::mag_finalize_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(fp);
+  SPL_CUDA(cudaGetLastError());
+  return SPL_OK;
+}
+
 int spl_launch_combine(const spl::CombineParams& cp, void* stream) {
   const long long total = (long long)cp.B * ((cp.T + 3) / 4);
   const unsigned grid = (unsigned)((total + 127) / 128);

@@ -17,6 +17,9 @@
 //   int spl_launch_reduce_finalize(const spl::ReduceFinalizeParams&, void* stream);
 //   int spl_launch_combine(const spl::CombineParams&, void* stream);
 //   int spl_launch_reduce_exchange(const spl::ExchangeParams&, void* stream);
+//   int spl_launch_mag_sums(const spl::MagLossParams&, int grid, int wpc, void* stream);      -- grid/wpc from spl_shape_dims
+//   int spl_launch_mag_backward(const spl::MagLossParams&, void* stream);
+//   int spl_launch_mag_finalize(const spl::MagFinalizeParams&, void* stream);
 //   int spl_shape_dims(long long items, int* grid, int* wpc);      -- CTAs x warps of the shape-loss kernels
 //   int spl_launch_shape_forward(const spl::ShapeParams&, int grid, int wpc, void* stream);
 //   int spl_launch_shape_backward(const spl::ShapeParams&, int grid, int wpc, void* stream);
@@ -531,6 +534,54 @@ int32_t spl_shape_backward(const int32_t* records, int32_t rows, int64_t rows_gl
   p.records = const_cast<int32_t*>(records); p.g = g; p.dx = dx;
   for (int r = 0; r < n; ++r) p.coef[r] = (float)(1.0 / ((double)n * (double)rows_global * (double)(T / winlens[r])));
   return spl_launch_shape_backward(p, grid, wpc, stream);
+}
+
+// ---- losses on explicit magnitude tensors (stft_loss.py:38-77) ------------------------------------------------------
+static int mag_dims(long long n, int* grid, int* wpc) { return spl_shape_dims((n + 4095) / 4096, grid, wpc); }
+
+int32_t spl_mag_loss_geometry(int64_t n, int64_t* partial_count) {
+  if (n < 1 || !partial_count) return fail(SPL_E_INVALID, "spl_mag_loss_geometry: n %lld < 1 or null output", (long long)n);
+  int grid = 0, wpc = 0;
+  int rc = mag_dims(n, &grid, &wpc);
+  if (rc) return rc;
+  *partial_count = (int64_t)grid * wpc * 3;
+  return SPL_OK;
+}
+
+int32_t spl_mag_loss_forward(const float* x_mag, const float* y_mag, int64_t n, double* partials, double* sums,
+                             float* sc, float* mag, void* stream) {
+  if (!x_mag || !y_mag || !partials || !sums) return fail(SPL_E_INVALID, "spl_mag_loss_forward: null pointer");
+  if (n < 1) return fail(SPL_E_INVALID, "spl_mag_loss_forward: n %lld < 1", (long long)n);
+  int grid = 0, wpc = 0;
+  int rc = mag_dims(n, &grid, &wpc);
+  if (rc) return rc;
+  spl::MagLossParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.x = x_mag; p.y = y_mag; p.n = n; p.partials = partials;
+  p.vec = (((uintptr_t)x_mag | (uintptr_t)y_mag) & 15) == 0;
+  rc = spl_launch_mag_sums(p, grid, wpc, stream);
+  if (rc) return rc;
+  spl::ReduceParams rp;
+  std::memset(&rp, 0, sizeof(rp));
+  rp.n_sums = 3;
+  for (int j = 0; j < 3; ++j) { rp.base[j] = partials + j; rp.stride[j] = 3; rp.count[j] = grid * wpc; }
+  rp.out = sums;
+  rc = spl_launch_reduce(rp, stream);
+  if (rc) return rc;
+  spl::MagFinalizeParams fp;
+  fp.sums = sums; fp.n = (double)n; fp.sc = sc; fp.mag = mag;
+  return spl_launch_mag_finalize(fp, stream);
+}
+
+int32_t spl_mag_loss_backward(const float* x_mag, const float* y_mag, int64_t n, const double* sums,
+                              const float* g_sc, const float* g_mag, float* gx, float* gy, void* stream) {
+  if (!x_mag || !y_mag || !sums || (!gx && !gy)) return fail(SPL_E_INVALID, "spl_mag_loss_backward: null pointer");
+  if (n < 1) return fail(SPL_E_INVALID, "spl_mag_loss_backward: n %lld < 1", (long long)n);
+  spl::MagLossParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.x = x_mag; p.y = y_mag; p.n = n; p.sums = sums; p.g_sc = g_sc; p.g_mag = g_mag; p.gx = gx; p.gy = gy;
+  p.vec = (((uintptr_t)x_mag | (uintptr_t)y_mag | (uintptr_t)gx | (uintptr_t)gy) & 15) == 0;
+  return spl_launch_mag_backward(p, stream);
 }
 
 }  // extern "C"

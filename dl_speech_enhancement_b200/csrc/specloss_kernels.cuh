@@ -1304,6 +1304,124 @@ SPL_DEVICE void shape_finalize_body(const ShapeFinalizeParams& p) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Losses on EXPLICIT magnitude tensors: SpectralConvergenceLoss.forward(x_mag, y_mag) = ||y - x||_F / ||y||_F
+// (losses/stft_loss.py:38-56) and LogSTFTMagnitudeLoss.forward = mean |ln y - ln x| (stft_loss.py:59-77), for callers
+// that compose them with stft() themselves (STFTLoss.forward does, stft_loss.py:112-116).  HBM-bound streaming:
+// forward reads both tensors once (8 B per element), backward reads both and writes one or two gradients.
+// ---------------------------------------------------------------------------------------------
+struct MagLossParams {
+  const float* x;          // x_mag, n elements
+  const float* y;          // y_mag
+  long long n;
+  int vec;                 // 1: both tensors (and the gradients) are 16-byte aligned -> float4 body + scalar tail
+  double* partials;        // forward: [grid * warps per CTA][3]  (S1 = sum (y-x)^2, S2 = sum y^2, S3 = sum |ln y - ln x|)
+  // backward
+  const double* sums;      // [6]: S1, S2, S3 and the three backward coefficients
+  const float* g_sc;       // upstream gradients (device scalars, null = 0)
+  const float* g_mag;
+  float* gx;               // d/dx_mag (null = skip)
+  float* gy;               // d/dy_mag (null = skip)
+};
+
+// [region: mag loss]
+SPL_DEVICE void mag_accumulate(float xv, float yv, float& s1, float& s2, float& s3) {
+  const float d = yv - xv;
+  s1 = fmaf(d, d, s1);
+  s2 = fmaf(yv, yv, s2);
+  s3 += fabsf(spl_fast_log2(yv) - spl_fast_log2(xv));               // x ln 2 once, at the end
+}
+
+// 16-byte loads over the aligned body (vec: n / 4 float4 per tensor), scalar loads over the tail
+SPL_DEVICE void mag_sums_body(const MagLossParams& p, int block, int tid, int grid, int wpc) {
+  const int warp = tid >> 5, lane = tid & 31;
+  const long long stride = (long long)grid * wpc * 32, first = ((long long)block * wpc + warp) * 32 + lane;
+  double d1 = 0.0, d2 = 0.0, d3 = 0.0;
+  float s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int pending = 0;
+  const long long nv = p.vec ? p.n >> 2 : 0;
+  const float4* x4 = reinterpret_cast<const float4*>(p.x);
+  const float4* y4 = reinterpret_cast<const float4*>(p.y);
+  for (long long i = first; i < nv; i += stride) {
+    const float4 xv = __ldg(x4 + i), yv = __ldg(y4 + i);
+    mag_accumulate(xv.x, yv.x, s1, s2, s3);
+    mag_accumulate(xv.y, yv.y, s1, s2, s3);
+    mag_accumulate(xv.z, yv.z, s1, s2, s3);
+    mag_accumulate(xv.w, yv.w, s1, s2, s3);
+    if (++pending == 16) { d1 += (double)s1; d2 += (double)s2; d3 += (double)s3; s1 = s2 = s3 = 0.f; pending = 0; }
+  }
+  for (long long i = 4 * nv + first; i < p.n; i += stride) mag_accumulate(__ldg(p.x + i), __ldg(p.y + i), s1, s2, s3);
+  d1 = warp_sum(d1 + (double)s1);
+  d2 = warp_sum(d2 + (double)s2);
+  d3 = warp_sum(d3 + (double)s3);
+  if (lane == 0) {
+    double* o = p.partials + (size_t)(block * wpc + warp) * 3;
+    o[0] = d1; o[1] = d2; o[2] = 0.69314718055994531 * d3;
+  }
+}
+
+// gradients of  g_sc * sqrt(S1)/sqrt(S2) + g_mag * S3/n  (what autograd derives: torch.norm backward gives 0 at D = 0,
+// sign(0) = 0).  sums[3..5] = {1/(D Ny) (0 at D = 0), D/Ny^3, 1/n} from the finalize step.  For positive magnitudes
+// sign(ln x - ln y) = sign(x - y): no logarithm on this path.
+SPL_DEVICE void mag_grad(float xv, float yv, float a, float b, float c, float& gx, float& gy) {
+  const float d = xv - yv;
+  const float sg = (d > 0.f) ? c : ((d < 0.f) ? -c : 0.f);
+  gx = fmaf(a, d, sg / xv);
+  gy = -fmaf(a, d, fmaf(b, yv, sg / yv));
+}
+
+// persistent grid-stride loop (one float4 per thread per CTA would spend its time launching 200 k tiny CTAs)
+SPL_DEVICE void mag_backward_body(const MagLossParams& p, long long first, long long stride) {
+  const float gsc = p.g_sc ? *p.g_sc : 0.f, gmag = p.g_mag ? *p.g_mag : 0.f;
+  const float a = gsc * (float)__ldcg(&p.sums[3]), b = gsc * (float)__ldcg(&p.sums[4]), c = gmag * (float)__ldcg(&p.sums[5]);
+  const long long nv = p.vec ? p.n >> 2 : 0;
+  const float4* x4 = reinterpret_cast<const float4*>(p.x);
+  const float4* y4 = reinterpret_cast<const float4*>(p.y);
+  for (long long i = first; i < nv; i += 2 * stride) {         // two independent float4 pairs in flight per thread
+    const long long i2 = i + stride;
+    const bool two = i2 < nv;
+    const float4 xa = __ldg(x4 + i), ya = __ldg(y4 + i);
+    const float4 xb = two ? __ldg(x4 + i2) : xa, yb = two ? __ldg(y4 + i2) : ya;
+    float4 gx, gy;
+    mag_grad(xa.x, ya.x, a, b, c, gx.x, gy.x);
+    mag_grad(xa.y, ya.y, a, b, c, gx.y, gy.y);
+    mag_grad(xa.z, ya.z, a, b, c, gx.z, gy.z);
+    mag_grad(xa.w, ya.w, a, b, c, gx.w, gy.w);
+    if (p.gx) reinterpret_cast<float4*>(p.gx)[i] = gx;
+    if (p.gy) reinterpret_cast<float4*>(p.gy)[i] = gy;
+    if (two) {
+      mag_grad(xb.x, yb.x, a, b, c, gx.x, gy.x);
+      mag_grad(xb.y, yb.y, a, b, c, gx.y, gy.y);
+      mag_grad(xb.z, yb.z, a, b, c, gx.z, gy.z);
+      mag_grad(xb.w, yb.w, a, b, c, gx.w, gy.w);
+      if (p.gx) reinterpret_cast<float4*>(p.gx)[i2] = gx;
+      if (p.gy) reinterpret_cast<float4*>(p.gy)[i2] = gy;
+    }
+  }
+  for (long long i = 4 * nv + first; i < p.n; i += stride) {   // scalar tail (or everything when not 16-byte aligned)
+    float gx, gy;
+    mag_grad(__ldg(p.x + i), __ldg(p.y + i), a, b, c, gx, gy);
+    if (p.gx) p.gx[i] = gx;
+    if (p.gy) p.gy[i] = gy;
+  }
+}
+
+struct MagFinalizeParams {
+  double* sums;            // [6]: in S1, S2, S3; out [3..5] = backward coefficients 1/(D Ny), D/Ny^3, 1/n
+  double n;
+  float* sc;               // null = skip
+  float* mag;
+};
+SPL_DEVICE void mag_finalize_body(const MagFinalizeParams& p) {
+  const double S2 = __ldcg(&p.sums[1]);
+  const double D = sqrt(__ldcg(&p.sums[0])), Ny = sqrt(S2);
+  if (p.sc) *p.sc = (float)(D / Ny);
+  if (p.mag) *p.mag = (float)(__ldcg(&p.sums[2]) / p.n);
+  p.sums[3] = D > 0.0 ? 1.0 / (D * Ny) : 0.0;
+  p.sums[4] = D / (Ny * S2);
+  p.sums[5] = 1.0 / p.n;
+}
+
+// ---------------------------------------------------------------------------------------------
 // deterministic reduction of the per-warp partial sums: one CTA per output sum
 // ---------------------------------------------------------------------------------------------
 struct ReduceParams {
@@ -1625,6 +1743,15 @@ __global__ void __launch_bounds__(256) shape_backward_kernel(const ShapeParams p
 }
 __global__ void shape_finalize_kernel(const ShapeFinalizeParams p) {
   if (threadIdx.x == 0 && blockIdx.x == 0) shape_finalize_body(p);
+}
+__global__ void __launch_bounds__(256) mag_sums_kernel(const MagLossParams p) {
+  mag_sums_body(p, blockIdx.x, threadIdx.x, gridDim.x, blockDim.x >> 5);
+}
+__global__ void __launch_bounds__(256) mag_backward_kernel(const MagLossParams p) {
+  mag_backward_body(p, (long long)blockIdx.x * blockDim.x + threadIdx.x, (long long)gridDim.x * blockDim.x);
+}
+__global__ void mag_finalize_kernel(const MagFinalizeParams p) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) mag_finalize_body(p);
 }
 __global__ void __launch_bounds__(256) reduce_kernel(const ReduceParams p) {
   __shared__ double sh[256];

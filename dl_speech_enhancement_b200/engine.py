@@ -534,6 +534,41 @@ class Engine:
         self.launches += 1
         return dx
 
+    # -- losses on explicit magnitude tensors ----------------------------------------------------
+    def mag_loss_forward(self, x_mag: torch.Tensor, y_mag: torch.Tensor, want_sc: bool, want_mag: bool):
+        """x_mag, y_mag: fp32 contiguous, same shape.  Returns (sc or None, mag or None, sums): SpectralConvergenceLoss /
+        LogSTFTMagnitudeLoss.forward (stft_loss.py:38-77) on the streaming kernels."""
+        n = x_mag.numel()
+        dev = x_mag.device
+        n_part = ctypes.c_int64()
+        _abi.check(self.lib, self.lib.spl_mag_loss_geometry(n, ctypes.byref(n_part)))
+        partials = torch.empty(n_part.value, dtype=torch.float64, device=dev)
+        sums = torch.empty(6, dtype=torch.float64, device=dev)
+        sc = torch.empty((), dtype=torch.float32, device=dev) if want_sc else None
+        mag = torch.empty((), dtype=torch.float32, device=dev) if want_mag else None
+        _abi.check(self.lib, self.lib.spl_mag_loss_forward(x_mag.data_ptr(), y_mag.data_ptr(), n, partials.data_ptr(),
+                                                           sums.data_ptr(), _ptr(sc), _ptr(mag), self._stream(x_mag)))
+        self.launches += 3
+        return sc, mag, sums
+
+    def mag_loss_backward(self, x_mag, y_mag, sums, g_sc, g_mag, need_x: bool, need_y: bool):
+        dev = x_mag.device
+
+        def scalar(g):
+            if g is None:
+                return None
+            if g.dtype != torch.float32 or g.device != dev or g.dim() != 0:
+                g = g.detach().to(device=dev, dtype=torch.float32).reshape(())
+            return g
+
+        g_sc, g_mag = scalar(g_sc), scalar(g_mag)
+        gx = torch.empty_like(x_mag) if need_x else None
+        gy = torch.empty_like(y_mag) if need_y else None
+        _abi.check(self.lib, self.lib.spl_mag_loss_backward(x_mag.data_ptr(), y_mag.data_ptr(), x_mag.numel(), sums.data_ptr(),
+                                                            _ptr(g_sc), _ptr(g_mag), _ptr(gx), _ptr(gy), self._stream(x_mag)))
+        self.launches += 1
+        return gx, gy
+
     # -- backward --------------------------------------------------------------------------------
     def backward(self, st: ForwardState, g_sc: Optional[torch.Tensor], g_mag: Optional[torch.Tensor],
                  g_mel: Optional[torch.Tensor]) -> torch.Tensor:

@@ -159,3 +159,31 @@ def shape_loss(x: torch.Tensor, y: torch.Tensor, winlens: Sequence[int], group=N
         _check_inputs(x, y)
         engine = cuda_engine()
     return _ShapeLossFn.apply(x, y, tuple(int(w) for w in winlens), engine, group)
+
+
+class _MagLossFn(torch.autograd.Function):
+    """SpectralConvergenceLoss (which = 0) / LogSTFTMagnitudeLoss (which = 1) on explicit magnitude tensors
+    (stft_loss.py:38-77), differentiable w.r.t. both arguments like the reference."""
+
+    @staticmethod
+    def forward(ctx, x_mag, y_mag, which, engine):
+        xd, yd = x_mag.detach().contiguous(), y_mag.detach().contiguous()
+        sc, mag, sums = engine.mag_loss_forward(xd, yd, which == 0, which == 1)
+        ctx.engine, ctx.which, ctx.sums = engine, which, sums
+        ctx.save_for_backward(xd, yd)
+        return sc if which == 0 else mag
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        xd, yd = ctx.saved_tensors
+        gx, gy = ctx.engine.mag_loss_backward(xd, yd, ctx.sums, g if ctx.which == 0 else None, g if ctx.which == 1 else None,
+                                              ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+        return gx, gy, None, None
+
+
+def magnitude_loss(x_mag: torch.Tensor, y_mag: torch.Tensor, which: int, engine: Optional[Engine] = None) -> torch.Tensor:
+    if engine is None:
+        _check_inputs(x_mag, y_mag)
+        engine = cuda_engine()
+    return _MagLossFn.apply(x_mag, y_mag, which, engine)

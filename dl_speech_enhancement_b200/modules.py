@@ -21,7 +21,7 @@ import torch
 from . import melfb
 from ._abi import SPL_KIND_MEL, SPL_KIND_STFT
 from .engine import TransformPlan, fft_geometry, mel_gemm_weights, mel_tables, twiddle_table
-from .functional import log_mel_spectrogram, shape_loss, spectral_losses
+from .functional import log_mel_spectrogram, magnitude_loss, shape_loss, spectral_losses
 from .functional import spectrogram as _spectrogram_fn
 
 
@@ -95,18 +95,19 @@ def spectrogram(waveform, pad, window, n_fft, hop_length, win_length, power, nor
 
 
 class SpectralConvergenceLoss(torch.nn.Module):
-    """||y_mag - x_mag||_F / ||y_mag||_F on explicit magnitudes (stft_loss.py:38-56); kept for
-    `from losses import *` compatibility -- the fused STFTLoss does not call it."""
+    """||y_mag - x_mag||_F / ||y_mag||_F on explicit magnitudes (stft_loss.py:38-56), on the sm_100a streaming kernels
+    (spl_mag_loss_*), differentiable w.r.t. both arguments.  The fused STFTLoss never materialises the magnitudes and
+    does not call this; it is for callers that compose stft() + losses themselves."""
 
     def forward(self, x_mag, y_mag):
-        return torch.norm(y_mag - x_mag, p="fro") / torch.norm(y_mag, p="fro")
+        return magnitude_loss(x_mag, y_mag, 0)
 
 
 class LogSTFTMagnitudeLoss(torch.nn.Module):
-    """mean |log y_mag - log x_mag| on explicit magnitudes (stft_loss.py:59-77); compatibility only."""
+    """mean |log y_mag - log x_mag| on explicit magnitudes (stft_loss.py:59-77), same kernels."""
 
     def forward(self, x_mag, y_mag):
-        return torch.nn.functional.l1_loss(torch.log(y_mag), torch.log(x_mag))
+        return magnitude_loss(x_mag, y_mag, 1)
 
 
 class STFTLoss(torch.nn.Module):

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SPL_ABI_VERSION 10
+#define SPL_ABI_VERSION 11
 
 #define SPL_OK 0
 #define SPL_E_INVALID (-1)   /* bad argument / outside the supported envelope */
@@ -175,6 +175,21 @@ int32_t spl_shape_finalize(const double* sums, int64_t rows_global, int32_t T, c
  * g: device scalar.  dx is overwritten. */
 int32_t spl_shape_backward(const int32_t* records, int32_t rows, int64_t rows_global, int32_t T, const int32_t* winlens,
                            int32_t n, const float* g, float* dx, void* stream);
+
+/* ---- Losses on explicit magnitude tensors, for callers that compose them with stft() themselves (STFTLoss.forward,
+ * stft_loss.py:112-116): SpectralConvergenceLoss.forward(x_mag, y_mag) = ||y - x||_F / ||y||_F (stft_loss.py:38-56) and
+ * LogSTFTMagnitudeLoss.forward = mean |ln y - ln x| (stft_loss.py:59-77).  x_mag, y_mag: device, n fp32 elements. */
+int32_t spl_mag_loss_geometry(int64_t n, int64_t* partial_count);
+
+/* sums: device doubles [6]; [0..2] = {sum (y-x)^2, sum y^2, sum |ln y - ln x|} (fixed order), [3..5] = coefficients the
+ * backward consumes.  sc / mag: device scalars, NULL to skip.  Magnitudes must be positive (stft() output is). */
+int32_t spl_mag_loss_forward(const float* x_mag, const float* y_mag, int64_t n, double* partials, double* sums,
+                             float* sc, float* mag, void* stream);
+
+/* gx / gy (n fp32 each, NULL to skip one) = g_sc * d sc + g_mag * d mag w.r.t. x_mag / y_mag; g_sc, g_mag: device scalars
+ * (NULL = 0). */
+int32_t spl_mag_loss_backward(const float* x_mag, const float* y_mag, int64_t n, const double* sums,
+                              const float* g_sc, const float* g_mag, float* gx, float* gy, void* stream);
 
 #ifdef __cplusplus
 }

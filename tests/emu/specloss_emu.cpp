@@ -161,6 +161,22 @@ int spl_launch_reduce_exchange(const spl::ExchangeParams& ep, void*) {
   return SPL_OK;
 }
 
+int spl_launch_mag_sums(const spl::MagLossParams& p, int grid, int wpc, void*) {
+  run_grid(grid, wpc, 0, [](float*, int) {},
+           [&](float*, int block, int tid) { spl::mag_sums_body(p, block, tid, grid, wpc); });
+  return SPL_OK;
+}
+
+int spl_launch_mag_backward(const spl::MagLossParams& p, void*) {
+  for (long long t = 0; t < 96; ++t) spl::mag_backward_body(p, t, 96);       // 96 "threads" stride over the elements
+  return SPL_OK;
+}
+
+int spl_launch_mag_finalize(const spl::MagFinalizeParams& fp, void*) {
+  spl::mag_finalize_body(fp);
+  return SPL_OK;
+}
+
 int spl_launch_combine(const spl::CombineParams& cp, void*) {
   const long long total = (long long)cp.B * ((cp.T + 3) / 4);
   for (long long g = 0; g < total; ++g) spl::combine_body(cp, g);

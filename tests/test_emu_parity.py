@@ -228,3 +228,26 @@ def test_emulated_shape_loss_matches_golden(emu_engine, name):
     loss.backward()
     assert abs(float(loss.detach()) - g["loss64"]) <= 1e-6 * abs(g["loss64"])
     np.testing.assert_allclose(x.grad.numpy(), g["grad32"], rtol=1e-6, atol=1e-9)
+
+
+def test_emulated_explicit_magnitude_losses(emu_engine):
+    """SpectralConvergenceLoss / LogSTFTMagnitudeLoss on explicit tensors (stft_loss.py:38-77): values and the gradients
+    w.r.t. BOTH arguments against torch autograd in fp64."""
+    from dl_speech_enhancement_b200.functional import magnitude_loss
+
+    gen = torch.Generator().manual_seed(8)
+    x = torch.rand(3, 37, 129, generator=gen) + 0.05
+    y = torch.rand(3, 37, 129, generator=gen) + 0.05
+    y[0, :5] = x[0, :5]                                      # equal entries: sign(0) = 0
+    for which in (0, 1):
+        xg, yg = x.clone().requires_grad_(True), y.clone().requires_grad_(True)
+        loss = magnitude_loss(xg, yg, which, engine=emu_engine)
+        (2.5 * loss).backward()
+        xr, yr = x.double().requires_grad_(True), y.double().requires_grad_(True)
+        ref = (torch.norm(yr - xr, p="fro") / torch.norm(yr, p="fro")) if which == 0 else \
+            torch.nn.functional.l1_loss(torch.log(yr), torch.log(xr))
+        (2.5 * ref).backward()
+        assert abs(float(loss.detach()) - float(ref.detach())) <= 1e-6 * float(ref.detach())
+        assert rel_l2(xg.grad.numpy(), xr.grad.numpy()) <= 1e-6 and rel_l2(yg.grad.numpy(), yr.grad.numpy()) <= 1e-6
+    same = magnitude_loss(x.clone().requires_grad_(True), x, 0, engine=emu_engine)
+    assert float(same.detach()) == 0.0

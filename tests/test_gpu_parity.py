@@ -525,3 +525,23 @@ def test_full_size_configs_tiled_batch_invariance(dev, tag, batch, t_len, mel_kw
     assert rel_l2((g[reps - 1] * reps).cpu().numpy(), gref.reshape(2, t_len).numpy()) <= GRAD_RTOL
     del x, t, g
     torch.cuda.empty_cache()
+
+
+def test_explicit_magnitude_losses_both_gradients(dev):
+    """SpectralConvergenceLoss / LogSTFTMagnitudeLoss on explicit tensors (stft_loss.py:38-77) at the config-2 shape of
+    the 1024-point resolution: values and gradients w.r.t. both arguments against fp64 autograd."""
+    import dl_speech_enhancement_b200 as pkg
+    g = torch.Generator().manual_seed(3)
+    x = torch.rand(16, 401, 513, generator=g) + 0.01
+    y = torch.rand(16, 401, 513, generator=g) + 0.01
+    for crit, ref_fn in ((pkg.SpectralConvergenceLoss(), lambda a, b: torch.norm(b - a, p="fro") / torch.norm(b, p="fro")),
+                         (pkg.LogSTFTMagnitudeLoss(), lambda a, b: torch.nn.functional.l1_loss(torch.log(b), torch.log(a)))):
+        xg, yg = x.to(dev).requires_grad_(True), y.to(dev).requires_grad_(True)
+        loss = crit(xg, yg)
+        loss.backward()
+        xr, yr = x.double().requires_grad_(True), y.double().requires_grad_(True)
+        ref = ref_fn(xr, yr)
+        ref.backward()
+        assert abs(float(loss.detach()) - float(ref.detach())) <= 1e-6 * float(ref.detach())
+        assert rel_l2(xg.grad.cpu().numpy(), xr.grad.numpy()) <= 1e-5
+        assert rel_l2(yg.grad.cpu().numpy(), yr.grad.numpy()) <= 1e-5
