@@ -63,3 +63,15 @@ us_ms = timeit(lambda: ms(x))
 us_fused = timeit(lambda: eng.forward(mel_loss.plans(), x, y, need_grad=False))
 print(f"  MelSpectrogram.forward(x) [spectrogram + GEMM]: {us_ms:7.1f} us;  x2 signals = {2 * us_ms:7.1f} us "
       f"(+ an L1 kernel) vs fused mel-loss forward (banded projection, both signals, no spectrogram in HBM): {us_fused:7.1f} us")
+
+# backward of the explicit tensors (specgrad_kernel + combine): gradient of stft() / MelSpectrogram.forward w.r.t. x
+print("  backward of the explicit tensors (recompute + adjoint transform, then the overlap-add gather):")
+for sl in stft.stft_losses:
+    plan = sl.plan()
+    frames = 1 + T // sl.hop_size
+    gout = torch.randn(B, frames, sl.fft_size // 2 + 1, device=dev)
+    us = timeit(lambda: eng.spectrogram_backward(plan, x, gout))
+    print(f"    stft {sl.fft_size}/{sl.hop_size}/{sl.win_length}: {us:7.1f} us")
+gmel = torch.randn(B, 80, 1 + T // 300, device=dev)
+us = timeit(lambda: eng.spectrogram_backward(ms.plan(), x, gmel))
+print(f"    log-mel 2048/300 (banded transposed projection in the kernel): {us:7.1f} us")
