@@ -285,7 +285,7 @@ def run_ours(args, rank, local_rank, world):
     # with the mel criterion on a second stream (no module/API change).  Sharded runs take the second variant only when
     # the exchange step is the in-kernel peer-memory one: NCCL collectives of one communicator stay on one stream.
     # sharded: is the exchange step the in-kernel NVLink peer-memory one on EVERY rank (then the step holds no NCCL call)?
-    peer = 1 if (world > 1 and eng._exchanges and all(v is not None for v in eng._exchanges.values())) else 0
+    peer = 1 if (world > 1 and eng.peer_exchange_active()) else 0
     if world > 1:
         pf = torch.tensor([peer], device=dev)
         dist.all_reduce(pf, op=dist.ReduceOp.MIN)

@@ -10,7 +10,7 @@ import ctypes
 import os
 import shutil
 import subprocess
-from ctypes import POINTER, c_char_p, c_double, c_float, c_int32, c_int64, c_void_p
+from ctypes import POINTER, c_char_p, c_float, c_int32, c_int64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libspecloss.so")

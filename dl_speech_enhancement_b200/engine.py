@@ -8,10 +8,9 @@ itself never allocates or synchronises.  Nothing here computes losses or gradien
 from __future__ import annotations
 
 import ctypes
-import math
 import os
 from dataclasses import dataclass, field
-from typing import List, Optional, Sequence
+from typing import Optional, Sequence
 
 import numpy as np
 import torch
@@ -293,6 +292,10 @@ class Engine:
                 ex = None
         self._exchanges[key] = ex
         return ex
+
+    def peer_exchange_active(self) -> bool:
+        """True when every sharded recipe used so far exchanges its sums over peer memory (no NCCL call per step)."""
+        return bool(self._exchanges) and all(v is not None for v in self._exchanges.values())
 
     def _recipe(self, plans: Sequence[TransformPlan], batch: int, t_len: int, need_grad: bool, dev) -> _Recipe:
         # fast path: the same plan OBJECTS as last time (modules cache their plans until a buffer moves; the recipe keeps

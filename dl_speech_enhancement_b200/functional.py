@@ -6,12 +6,11 @@ non-fp32 dtypes and missing libspecloss.so raise -- there is no fallback path.
 """
 from __future__ import annotations
 
-from typing import Optional, Sequence, Tuple
+from typing import Optional, Sequence
 
 import torch
 
-from .engine import Engine, ForwardState, TransformPlan, cuda_engine
-from ._abi import SPL_KIND_MEL, SPL_KIND_STFT
+from .engine import Engine, TransformPlan, cuda_engine
 
 
 def _as_2d(x: torch.Tensor, name: str) -> torch.Tensor:
@@ -49,7 +48,6 @@ class _SpectralLossFn(torch.autograd.Function):
         ctx.set_materialize_grads(False)
         outs = tuple(t for t in (st.sc, st.mag, st.mel) if t is not None)
         ctx.layout = (st.sc is not None, st.mel is not None)
-        ctx.mark_non_differentiable()  # nothing: all outputs differentiable w.r.t. x
         return outs
 
     @staticmethod

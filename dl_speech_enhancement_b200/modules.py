@@ -14,7 +14,7 @@ Differences from the reference, all raising rather than silently diverging:
 from __future__ import annotations
 
 import math
-from typing import List, Optional
+from typing import List
 
 import torch
 

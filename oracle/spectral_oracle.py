@@ -32,7 +32,7 @@ the authoring container by tests/golden/make_golden.py and committed as tests/go
 from __future__ import annotations
 
 import math
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
