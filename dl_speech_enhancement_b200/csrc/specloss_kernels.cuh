@@ -211,30 +211,57 @@ SPL_DEVICE float bits_to_float(int b) {
 #endif
 }
 
-// CTA prologue: every thread copies its share of the constant tables into shared memory.
+// CTA prologue: every thread copies its share of the constant tables into shared memory -- with cp.async, so that all
+// the copies of a thread are in flight together (as register-staged 4-byte loads the prologue cost one L2 round trip
+// per element and thread: 16 % of the stall samples of the mel kernel at configs[1], profiles r1v).
+#ifdef SPECLOSS_EMU
+static inline void cp_async4(void* d, const void* s) { memcpy(d, s, 4); }
+static inline void cp_async8(void* d, const void* s) { memcpy(d, s, 8); }
+static inline void cp_async16(void* d, const void* s) { memcpy(d, s, 16); }
+static inline void cp_async_wait_all() {}
+#else
+__device__ __forceinline__ void cp_async4(void* d, const void* s) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(d)), "l"(s) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* d, const void* s) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(d)), "l"(s) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* d, const void* s) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(d)), "l"(s) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+#endif
+
+// n 4-byte words, global -> shared (dst 16-byte aligned by construction of CtaTables): 16-byte chunks when the source
+// is 16-byte aligned, words otherwise and for the tail
+SPL_DEVICE void cta_copy_words(float* dst, const void* src, int n, int tid, int nthreads) {
+  const char* s8 = reinterpret_cast<const char*>(src);
+  const int n16 = ((reinterpret_cast<uintptr_t>(src) & 15) == 0) ? n >> 2 : 0;
+  for (int i = tid; i < n16; i += nthreads) cp_async16(dst + 4 * i, s8 + 16 * i);
+  for (int i = 4 * n16 + tid; i < n; i += nthreads) cp_async4(dst + i, s8 + 4 * i);
+}
+
 template <int NFFT>
 SPL_DEVICE void cta_load_fft_tables(const CtaTables& ct, const float2* twiddle, const float* window, int win,
                                     float* smem, int tid, int nthreads) {
   using G = Geo<NFFT>;
   float2* tw = reinterpret_cast<float2*>(smem + ct.tw);
-  for (int i = tid; i < NFFT; i += nthreads) tw[(i / G::L) * G::PITCH + (i % G::L)] = __ldg(&twiddle[i]);
-  for (int i = tid; i < win; i += nthreads) smem[ct.win + i] = __ldg(&window[i]);
+  for (int i = tid; i < NFFT; i += nthreads) cp_async8(&tw[(i / G::L) * G::PITCH + (i % G::L)], &twiddle[i]);
+  cta_copy_words(smem + ct.win, window, win, tid, nthreads);
 }
 
+// ends with the wait for this thread's copies; the caller's __syncthreads() publishes the tables
 template <int NFFT, int KIND>
 SPL_DEVICE void cta_load_tables(const TransformParams& p, float* smem, int tid, int nthreads) {
   constexpr int L = Geo<NFFT>::L;
   const CtaTables ct = cta_tables(NFFT, p.win, KIND, p.mel_rounds, p.mel_entry_rows);
   cta_load_fft_tables<NFFT>(ct, p.twiddle, p.window, p.win, smem, tid, nthreads);
   if (KIND == kKindMel) {
-    int* ism = reinterpret_cast<int*>(smem);
-    const int* a = reinterpret_cast<const int*>(p.mel_tasks);
-    const int* b = reinterpret_cast<const int*>(p.mel_entries);
-    const int* c = reinterpret_cast<const int*>(p.bin_tab);
-    for (int i = tid; i < 4 * p.mel_rounds * L; i += nthreads) ism[ct.tasks + i] = __ldg(&a[i]);
-    for (int i = tid; i < 2 * p.mel_entry_rows * L; i += nthreads) ism[ct.entries + i] = __ldg(&b[i]);
-    for (int i = tid; i < 4 * (NFFT / 2 + 1); i += nthreads) ism[ct.bintab + i] = __ldg(&c[i]);
+    cta_copy_words(smem + ct.tasks, p.mel_tasks, 4 * p.mel_rounds * L, tid, nthreads);
+    cta_copy_words(smem + ct.entries, p.mel_entries, 2 * p.mel_entry_rows * L, tid, nthreads);
+    cta_copy_words(smem + ct.bintab, p.bin_tab, 4 * (NFFT / 2 + 1), tid, nthreads);
   }
+  cp_async_wait_all();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1718,6 +1745,7 @@ __global__ void __launch_bounds__(MaxWarps<NFFT>::value * 32, 1) spec_kernel(con
   extern __shared__ __align__(16) float smem_dyn[];
   cta_load_fft_tables<NFFT>(cta_tables(NFFT, p.win, kKindStft, 0, 0), p.twiddle, p.window, p.win, smem_dyn, threadIdx.x,
                             blockDim.x);
+  cp_async_wait_all();
   __syncthreads();
   spec_body<NFFT>(p, smem_dyn, blockIdx.x, threadIdx.x, gridDim.x, blockDim.x >> 5);
 }

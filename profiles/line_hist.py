@@ -103,3 +103,6 @@ for reg, e in sorted(by_region.items(), key=lambda t: -t[1]):
 print(f"-- top {top} lines")
 for (f, ln), e in by_line.most_common(top):
     print(f"  {100 * e / tot:5.1f}% exec  {100 * s_line[(f, ln)] / max(tots, 1):5.1f}% samples  {f}:{ln}")
+print(f"-- top {top} lines by stall samples")
+for (f, ln), sm in s_line.most_common(top):
+    print(f"  {100 * sm / max(tots, 1):5.1f}% samples  {100 * by_line[(f, ln)] / tot:5.1f}% exec  {f}:{ln}")
