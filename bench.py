@@ -178,7 +178,19 @@ def run_ours(args, rank, local_rank, world):
     torch.cuda.set_device(dev)
     group = None
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # stdout carries exactly one JSON line: the version banner NCCL prints on stdout when the first communicator is
+        # created is sent to stderr (file descriptor 1 points at stderr while the communicator comes up)
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
         group = dist.group.WORLD
     cuda_engine()          # raises if libspecloss.so is missing -- no fallback
     log("process group + engine ready")
