@@ -41,7 +41,7 @@ def twiddle_table(n_fft: int) -> torch.Tensor:
     return torch.from_numpy(tab.reshape(-1).copy())
 
 
-MEL_ITER_TARGET = 16     # bins summed per lane per round of the projection schedule
+MEL_ITER_TARGET = int(os.environ.get("SPECLOSS_MEL_ITER", "16"))     # bins summed per lane per round of the projection schedule (tuning knob)
 
 
 def slot_offset(n_fft: int, k: int) -> int:
