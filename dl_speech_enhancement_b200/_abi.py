@@ -15,7 +15,7 @@ from ctypes import POINTER, c_char_p, c_float, c_int32, c_int64, c_void_p
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libspecloss.so")
 CSRC = os.path.join(_HERE, "csrc")
-ABI_VERSION = 11
+ABI_VERSION = 12
 
 SPL_KIND_STFT = 0
 SPL_KIND_MEL = 1
@@ -80,7 +80,7 @@ def bind(lib: ctypes.CDLL) -> ctypes.CDLL:
     lib.spl_exchange_buffer_bytes.argtypes = []
     lib.spl_reduce_exchange_finalize.restype = c_int32
     lib.spl_reduce_exchange_finalize.argtypes = [POINTER(SplTransform), c_int32, c_int32, c_int32, c_int64, c_void_p, c_void_p,
-                                                 c_int32, c_int32, POINTER(c_void_p), c_void_p,
+                                                 c_int32, c_int32, POINTER(c_void_p), c_void_p, c_int64, c_void_p,
                                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.spl_backward.restype = c_int32
     lib.spl_backward.argtypes = [POINTER(SplTransform), c_int32, c_int32, c_int32, c_void_p,

@@ -308,7 +308,7 @@ static int build_reduce(const spl_transform* ts, int n, int B, int T, double* su
     if (rc) return rc;
     const int n_sums = ts[r].kind == SPL_KIND_STFT ? 3 : 1;
     for (int j = 0; j < n_sums; ++j) {
-      if (k >= 16) return fail(SPL_E_INVALID, "too many sums");
+      if (k >= spl::kMaxSums) return fail(SPL_E_INVALID, "too many sums");
       rp->base[k] = ts[r].partials + j;
       rp->stride[k] = n_sums;
       rp->count[k] = grid * wpc;
@@ -373,7 +373,7 @@ int64_t spl_exchange_buffer_bytes(void) { return (int64_t)spl::kExchangeBytes; }
 
 int32_t spl_reduce_exchange_finalize(const spl_transform* ts, int32_t n, int32_t B, int32_t T, int64_t B_global,
                                      double* sums_local, double* sums_global, int32_t rank, int32_t world,
-                                     void* const* peer_bufs, uint32_t* state,
+                                     void* const* peer_bufs, uint32_t* state, int64_t timeout_ns, uint32_t* error_flag,
                                      float* sc, float* mag, float* mel, float* coefs, void* stream) {
   if (n < 1 || n > SPL_MAX_TRANSFORMS || !sums_local || !sums_global || !coefs || !state || !peer_bufs)
     return fail(SPL_E_INVALID, "spl_reduce_exchange_finalize: bad n or null pointer");
@@ -387,6 +387,7 @@ int32_t spl_reduce_exchange_finalize(const spl_transform* ts, int32_t n, int32_t
   rc = build_finalize(ts, n, sums_global, B_global, T, sc, mag, mel, coefs, &ep.f);
   if (rc) return rc;
   ep.gsums = sums_global; ep.state = state; ep.rank = rank; ep.world = world;
+  ep.timeout_ns = timeout_ns; ep.error_flag = error_flag;
   for (int r = 0; r < world; ++r) {
     if (!peer_bufs[r]) return fail(SPL_E_INVALID, "null symmetric buffer of rank %d", r);
     ep.peers[r] = peer_bufs[r];

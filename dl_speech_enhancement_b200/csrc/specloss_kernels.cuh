@@ -1451,12 +1451,13 @@ SPL_DEVICE void mag_finalize_body(const MagFinalizeParams& p) {
 // ---------------------------------------------------------------------------------------------
 // deterministic reduction of the per-warp partial sums: one CTA per output sum
 // ---------------------------------------------------------------------------------------------
+constexpr int kMaxSums = 24;   // 3 sums x SPL_MAX_TRANSFORMS resolutions
 struct ReduceParams {
   int n_sums;
-  const double* base[16];   // first element of the column
-  int stride[16];           // doubles between consecutive items
-  int count[16];            // items
-  double* out;              // [n_sums]
+  const double* base[kMaxSums];   // first element of the column
+  int stride[kMaxSums];           // doubles between consecutive items
+  int count[kMaxSums];            // items
+  double* out;                    // [n_sums]
 };
 
 SPL_DEVICE void reduce_body(const ReduceParams& p, double* sh, int block, int tid, int nthreads) {
@@ -1517,13 +1518,13 @@ SPL_DEVICE void finalize_body(const FinalizeParams& p) {
 // collective is pure latency (two launches + NCCL's own protocol), so the last CTA of the reduction pushes this rank's
 // sums straight into every peer's symmetric buffer (peer-mapped stores), raises a flag there, waits for the peers'
 // flags in its own buffer and adds the contributions in rank order -- every rank gets bit-identical global sums.
-//   symmetric buffer (one per rank, peer-mapped):  double slots[2][kMaxRanks][16];  unsigned flags[2][kMaxRanks];
+//   symmetric buffer (one per rank, peer-mapped):  double slots[2][kMaxRanks][kExchangeSums];  unsigned flags[2][kMaxRanks];
 // Calls are numbered by an epoch kept in device memory (CUDA-graph replay safe); slot/flag sets alternate with the
 // epoch's parity: a rank can be at most one call ahead of the slowest peer, so the set being written is never the set a
 // peer still reads.
 // ---------------------------------------------------------------------------------------------
 constexpr int kMaxRanks = 8;
-constexpr int kExchangeSums = 16;
+constexpr int kExchangeSums = kMaxSums;
 constexpr size_t kExchangeBytes = 2 * kMaxRanks * kExchangeSums * sizeof(double) + 2 * kMaxRanks * sizeof(unsigned);
 
 struct ExchangeParams {
@@ -1531,6 +1532,9 @@ struct ExchangeParams {
   FinalizeParams f;        // f.sums = gsums
   double* gsums;           // local: receives the global sums
   unsigned* state;         // local: [0] CTA ticket (self-resetting), [1] epoch of the last completed call
+  unsigned* error_flag;    // null, or a word the HOST can read without synchronising (mapped pinned memory): receives the
+                           // epoch of a call whose peers did not arrive in time
+  long long timeout_ns;    // how long to wait for the peers' flags; <= 0: wait for ever, like a collective
   int rank, world;
   void* peers[kMaxRanks];  // symmetric buffers of all ranks, peers[rank] = own
 };
@@ -1540,7 +1544,8 @@ static inline void st_release_sys(unsigned* p, unsigned v) { __atomic_store_n(p,
 static inline unsigned ld_acquire_sys(const unsigned* p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
 static inline double ld_volatile_f64(const double* p) { return *reinterpret_cast<const volatile double*>(p); }
 static inline void threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
-static inline long long spin_clock() { static thread_local long long c = 0; return c += 64; }
+static inline void st_relaxed_sys(unsigned* p, unsigned v) { __atomic_store_n(p, v, __ATOMIC_RELAXED); }
+static inline long long spin_clock() { static thread_local long long c = 0; return c += 64; }     // "ns" 
 #else
 __device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -1556,7 +1561,14 @@ __device__ __forceinline__ double ld_volatile_f64(const double* p) {
   return v;
 }
 __device__ __forceinline__ void threadfence_system() { __threadfence_system(); }
-__device__ __forceinline__ long long spin_clock() { return clock64(); }
+__device__ __forceinline__ long long spin_clock() {      // nanoseconds (globaltimer: independent of the SM clock)
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return (long long)t;
+}
+__device__ __forceinline__ void st_relaxed_sys(unsigned* p, unsigned v) {
+  asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 #endif
 
 // [region: exchange]
@@ -1577,17 +1589,21 @@ SPL_DEVICE void exchange_body(const ExchangeParams& p, int lane) {
     unsigned* flags = reinterpret_cast<unsigned*>(reinterpret_cast<double*>(p.peers[lane]) + 2 * kMaxRanks * kExchangeSums);
     st_release_sys(&flags[parity * kMaxRanks + p.rank], epoch);
   }
-  // wait for every rank's contribution to this call (bounded: a missing peer poisons the result instead of hanging)
+  // Wait for every rank's contribution to this call.  Like a collective this waits as long as it takes by default
+  // (rank skew of seconds is routine in training: checkpoints, validation, data stalls).  With a finite timeout_ns a
+  // missing peer does not hang the stream: the call's epoch goes to the host-visible error flag (the host raises on its
+  // next call) and the sums are poisoned with NaN so the step cannot be used by accident.
   bool ok = true;
   if (lane < world) {
     const unsigned* flags = reinterpret_cast<const unsigned*>(reinterpret_cast<const double*>(p.peers[p.rank]) + 2 * kMaxRanks * kExchangeSums);
     const long long t0 = spin_clock();
     while (ld_acquire_sys(&flags[parity * kMaxRanks + lane]) != epoch) {
-      if (spin_clock() - t0 > 8000000000LL) { ok = false; break; }        // ~4 s at 2 GHz
+      if (p.timeout_ns > 0 && spin_clock() - t0 > p.timeout_ns) { ok = false; break; }
     }
   }
   threadfence_system();
   ok = __ballot_sync(0xffffffffu, !ok) == 0u;
+  if (!ok && lane == 0 && p.error_flag) st_relaxed_sys(p.error_flag, epoch);
   if (lane < n) {
     const double* slots = reinterpret_cast<const double*>(p.peers[p.rank]);
     double acc = 0.0;

@@ -19,7 +19,52 @@ from . import _abi
 from ._abi import SPL_KIND_MEL, SPL_KIND_STFT, SplGeometry, SplTransform
 
 SUPPORTED_NFFT = (512, 1024, 2048)
-_SM_COUNT = 148          # B200
+MAX_MELS = 512           # check_transform() in csrc/specloss_host.inl enforces the same bound
+COUNTER_SLOTS = 1024     # reduce tickets per device, handed out by recipe serial (see Engine._counter)
+
+
+class _DeviceGuard:
+    """Makes the tensors' device current around a C-ABI call: the library sizes grids, picks side streams and opts in to
+    shared memory for cudaGetDevice()'s device, and the stream handle belongs to the tensors' device.  (The reference
+    modules work on cuda:1 tensors while cuda:0 is current; so must these.)  One integer compare in the common case."""
+    __slots__ = ("idx", "prev")
+
+    def __init__(self, dev):
+        self.idx = dev.index if dev.type == "cuda" else None
+
+    def __enter__(self):
+        if self.idx is not None:
+            self.prev = torch.cuda.current_device()
+            if self.prev != self.idx:
+                torch.cuda.set_device(self.idx)
+        return self
+
+    def __exit__(self, *exc):
+        if self.idx is not None and self.prev != self.idx:
+            torch.cuda.set_device(self.prev)
+        return False
+
+
+def _on_tensor_device(arg_index: int):
+    """Runs an Engine method with the device of its arg_index-th positional argument (a tensor) current."""
+    def deco(fn):
+        import functools
+
+        @functools.wraps(fn)
+        def wrapper(self, *args, **kwargs):
+            t = args[arg_index]
+            if t.device.type != "cuda" or t.device.index == torch.cuda.current_device():
+                return fn(self, *args, **kwargs)
+            with _DeviceGuard(t.device):
+                return fn(self, *args, **kwargs)
+        return wrapper
+    return deco
+
+
+def exchange_timeout_ns() -> int:
+    """How long the fused exchange waits for its peers: SPECLOSS_EXCHANGE_TIMEOUT_S seconds, default 0 = as long as it
+    takes (what a collective does; rank skew of many seconds is routine around checkpoints and validation)."""
+    return int(float(os.environ.get("SPECLOSS_EXCHANGE_TIMEOUT_S", "0")) * 1e9)
 
 
 def fft_geometry(n_fft: int):
@@ -65,8 +110,8 @@ def mel_tables(melmat: np.ndarray, n_fft: int):
     lanes, _ = fft_geometry(n_fft)
     k_bins, n_mels = melmat.shape
     assert k_bins == n_fft // 2 + 1
-    if not (2 <= n_mels <= 0xffe):
-        raise NotImplementedError("num_mels must be in [2, 4094] for the sm_100a kernels")
+    if not (2 <= n_mels <= MAX_MELS):
+        raise NotImplementedError(f"num_mels must be in [2, {MAX_MELS}] for the sm_100a kernels")
     rows = []
     for m in range(n_mels):
         nz = np.flatnonzero(melmat[:, m])
@@ -205,6 +250,14 @@ class ForwardState:
         self.sc = self.mag = self.mel = None
         self.n_launches = 0
 
+    def detach_workspace(self) -> torch.Tensor:
+        """Hands the workspace tensor over to the caller (the autograd function saves it with save_for_backward, which
+        ties its lifetime to the autograd graph); this object keeps only raw addresses into it."""
+        ws = self.ws
+        self.ws = None
+        self.keep = self.keep[1:]
+        return ws
+
     # views into the workspace, made on demand (the hot path only needs their addresses)
     @property
     def sums(self) -> torch.Tensor:
@@ -252,14 +305,15 @@ class Engine:
         _abi.check(self.lib, self.lib.spl_geometry_of(ctypes.byref(tr), batch, t_len, ctypes.byref(g)))
         return g
 
-    def _counter(self, dev, owner=0) -> torch.Tensor:
-        """Zero-initialised, self-resetting device counter of spl_reduce_finalize: one per recipe, so that two
-        criteria evaluated concurrently on different streams never share one."""
-        key = (str(dev), owner)
-        c = self._counters.get(key)
-        if c is None:
-            c = self._counters[key] = torch.zeros(1, dtype=torch.int32, device=dev)
-        return c
+    def _counter_ptr(self, dev, serial: int) -> int:
+        """Address of the zero-initialised, self-resetting ticket of spl_reduce_finalize for recipe `serial`: one per
+        recipe, so that two criteria evaluated concurrently on different streams never share one.  The tickets of a
+        device live in ONE buffer that is never freed or moved (captured CUDA graphs keep raw pointers into it); a slot is
+        reused only by the recipe created COUNTER_SLOTS recipes later."""
+        pool = self._counters.get(dev)
+        if pool is None:
+            pool = self._counters[dev] = torch.zeros(COUNTER_SLOTS, dtype=torch.int32, device=dev)
+        return pool.data_ptr() + 4 * (serial % COUNTER_SLOTS)
 
     def _exchange(self, group, dev, owner):
         """Peer-mapped exchange buffers of one recipe for `group` (torch symmetric memory over NVLink), or None when the
@@ -284,14 +338,36 @@ class Engine:
                 torch.cuda.synchronize(dev)
                 dist.barrier(group)                    # every buffer is zero before any peer writes into it
                 ptrs = (ctypes.c_void_p * world)(*[int(p) for p in hdl.buffer_ptrs])
+                # error word in pinned (mapped) host memory: the kernel stores to it, the host reads it without a sync
+                err = torch.zeros(1, dtype=torch.int32).pin_memory()
                 ex = dict(buf=buf, hdl=hdl, ptrs=ptrs, rank=dist.get_rank(group), world=world,
-                          state=torch.zeros(2, dtype=torch.int32, device=dev))
+                          state=torch.zeros(2, dtype=torch.int32, device=dev), err=err, timeout_ns=exchange_timeout_ns())
             except Exception as exc:          # peer mapping unavailable (no NVLink/IPC): NCCL does the exchange instead
                 import warnings
                 warnings.warn(f"specloss: symmetric-memory exchange unavailable ({exc!r}); using NCCL all-reduce")
                 ex = None
         self._exchanges[key] = ex
         return ex
+
+    def _evict(self):
+        """Drop every cached recipe together with its peer-exchange buffers (symmetric memory is returned only here, so
+        the caches cannot grow without bound when batch shapes keep changing).  Ranks evict at the same call, because
+        they build the same recipes in the same order."""
+        self._recipes.clear()
+        self._recipes_by_id.clear()
+        self._exchanges.clear()
+
+    def check_exchange_errors(self):
+        """Raises if a fused exchange gave up waiting for a peer (finite SPECLOSS_EXCHANGE_TIMEOUT_S only).  Reads mapped
+        host memory: no synchronisation.  Called at the start of every sharded forward."""
+        for key, ex in self._exchanges.items():
+            if ex is not None and int(ex["err"][0]) != 0:
+                epoch = int(ex["err"][0])
+                ex["err"][0] = 0
+                raise _abi.SpecLossError(
+                    f"specloss: peer exchange call #{epoch} of recipe {key[2]} timed out waiting for another rank "
+                    f"(SPECLOSS_EXCHANGE_TIMEOUT_S={os.environ.get('SPECLOSS_EXCHANGE_TIMEOUT_S')}); the losses of that "
+                    "step are NaN.  Every rank must call the criterion collectively.")
 
     def peer_exchange_active(self) -> bool:
         """True when every sharded recipe used so far exchanges its sums over peer memory (no NCCL call per step)."""
@@ -312,7 +388,10 @@ class Engine:
             if len(self._recipes_by_id) > 256:
                 self._recipes_by_id.clear()
             self._recipes_by_id[fast] = rec
-            rec.plan_refs.append(tuple(plans))
+            if len(rec.plan_refs) < 8:           # keeps the plan objects (hence their ids) alive; bounded
+                rec.plan_refs.append(tuple(plans))
+            else:
+                self._recipes_by_id.pop(fast)    # callers that build fresh plans per call take the keyed lookup
             return rec
         if len(plans) < 1 or len(plans) > _abi.SPL_MAX_TRANSFORMS:
             raise RuntimeError(f"{len(plans)} resolutions: supported range is 1..{_abi.SPL_MAX_TRANSFORMS}")
@@ -363,15 +442,14 @@ class Engine:
         self._recipe_serial += 1
         rec.serial = self._recipe_serial       # same on every rank (SPMD): names the recipe's peer-exchange buffers
         if len(self._recipes) > 64:
-            self._recipes.clear()
-            self._recipes_by_id.clear()
-            self._counters.clear()
+            self._evict()
         self._recipes[key] = rec
         rec.plan_refs = [tuple(plans)]
         self._recipes_by_id[fast] = rec
         return rec
 
     # -- forward ---------------------------------------------------------------------------------
+    @_on_tensor_device(1)
     def forward(self, plans: Sequence[TransformPlan], x: torch.Tensor, y: torch.Tensor, need_grad: bool,
                 group=None, global_batch: Optional[int] = None) -> ForwardState:
         """x, y: (B, T) fp32 contiguous on one device.  Launches on the current stream; one workspace
@@ -402,18 +480,21 @@ class Engine:
         sums_ptr, coefs_ptr = base + rec.off_sums, base + rec.off_coefs
         if group is None and (global_batch is None or global_batch == batch):
             _abi.check(lib, lib.spl_reduce_finalize(arr, n, batch, t_len, sums_ptr, _ptr(st.sc), _ptr(st.mag),
-                                                    _ptr(st.mel), coefs_ptr, self._counter(dev, id(rec)).data_ptr(), stream))
+                                                    _ptr(st.mel), coefs_ptr, self._counter_ptr(dev, rec.serial), stream))
             st.n_launches = n + 1
         else:
             ex = self._exchange(group, dev, rec.serial) if group is not None else None
             if ex is not None:
+                if ex["timeout_ns"] > 0:
+                    self.check_exchange_errors()
                 # reduce + NVLink peer-memory exchange + finalize in one launch (spl_reduce_exchange_finalize)
                 if global_batch is None:
                     global_batch = batch * ex["world"]
                 lsums = ws[rec.off_lsums:rec.off_lsums + 8 * rec.n_sums]
                 _abi.check(lib, lib.spl_reduce_exchange_finalize(
                     arr, n, batch, t_len, int(global_batch), lsums.data_ptr(), sums_ptr, ex["rank"], ex["world"],
-                    ex["ptrs"], ex["state"].data_ptr(), _ptr(st.sc), _ptr(st.mag), _ptr(st.mel), coefs_ptr, stream))
+                    ex["ptrs"], ex["state"].data_ptr(), ex["timeout_ns"], ex["err"].data_ptr(),
+                    _ptr(st.sc), _ptr(st.mag), _ptr(st.mel), coefs_ptr, stream))
                 st.keep = st.keep + (ex,)
                 st.n_launches = n + 1
             else:
@@ -430,6 +511,7 @@ class Engine:
         return st
 
     # -- explicit spectrogram / log-mel spectrogram -----------------------------------------------------
+    @_on_tensor_device(0)
     def spectrogram(self, x: torch.Tensor, n_fft: int, hop: int, win: int, window: torch.Tensor,
                     twiddle: torch.Tensor, eps: float, ld: Optional[int] = None, split: bool = False):
         """(B, T) fp32 -> magnitude spectrogram (B, 1 + T // hop, n_fft // 2 + 1), the tensor the reference's
@@ -450,6 +532,7 @@ class Engine:
             return out, lo
         return out if ld == n_bins else out[:, :, :n_bins]
 
+    @_on_tensor_device(0)
     def mel_project(self, amp_hi: torch.Tensor, amp_lo: torch.Tensor, w_hi: torch.Tensor, w_lo: torch.Tensor,
                     n_mels: int, eps: float, log_scale: float) -> torch.Tensor:
         """(B, F, ld) split amplitudes x (n_pad, ld) split melmat^T -> log-mel (B, n_mels, F) on the tensor cores:
@@ -462,6 +545,7 @@ class Engine:
         self.launches += 1
         return out
 
+    @_on_tensor_device(1)
     def spectrogram_backward(self, plan: TransformPlan, x: torch.Tensor, g: torch.Tensor) -> torch.Tensor:
         """dL/dx (B, T) from the gradient of an explicit spectrogram of x: g = dL/d stft(x) (B, F, K) for an STFT plan
         (stft_loss.py:19-35), g = dL/d MelSpectrogram(x) (B, n_mels, F) for a mel plan (mel_loss.py:74-94).  Two
@@ -497,6 +581,7 @@ class Engine:
         return dx
 
     # -- waveform shape loss ---------------------------------------------------------------------
+    @_on_tensor_device(0)
     def shape_forward(self, x: torch.Tensor, y: torch.Tensor, winlens: Sequence[int], group=None,
                       global_rows: Optional[int] = None):
         """x, y: (rows, T) fp32 contiguous.  Returns (loss 0-dim, records, rows_global): MultiWindowShapeLoss.forward
@@ -524,6 +609,7 @@ class Engine:
         self.launches += 3
         return loss, records, rows_global
 
+    @_on_tensor_device(0)
     def shape_backward(self, records: torch.Tensor, rows: int, rows_global: int, t_len: int, winlens: Sequence[int],
                        g: torch.Tensor) -> torch.Tensor:
         dev = records.device
@@ -538,6 +624,7 @@ class Engine:
         return dx
 
     # -- losses on explicit magnitude tensors ----------------------------------------------------
+    @_on_tensor_device(0)
     def mag_loss_forward(self, x_mag: torch.Tensor, y_mag: torch.Tensor, want_sc: bool, want_mag: bool):
         """x_mag, y_mag: fp32 contiguous, same shape.  Returns (sc or None, mag or None, sums): SpectralConvergenceLoss /
         LogSTFTMagnitudeLoss.forward (stft_loss.py:38-77) on the streaming kernels."""
@@ -554,6 +641,7 @@ class Engine:
         self.launches += 3
         return sc, mag, sums
 
+    @_on_tensor_device(0)
     def mag_loss_backward(self, x_mag, y_mag, sums, g_sc, g_mag, need_x: bool, need_y: bool):
         dev = x_mag.device
 
@@ -578,6 +666,9 @@ class Engine:
         if not st.has_grad:
             raise RuntimeError("backward requested but forward ran without gradient workspace")
         dev = st.device
+        if dev.type == "cuda" and dev.index != torch.cuda.current_device():
+            with _DeviceGuard(dev):
+                return self.backward(st, g_sc, g_mag, g_mel)
         dx = torch.empty(st.batch, st.t_len, dtype=torch.float32, device=dev)
 
         def scalar(g):

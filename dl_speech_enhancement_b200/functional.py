@@ -42,6 +42,11 @@ class _SpectralLossFn(torch.autograd.Function):
         x2, y2 = _as_2d(x, "prediction"), _as_2d(y, "target")
         need_grad = ctx.needs_input_grad[0]
         st = engine.forward(plans, x2.detach(), y2.detach(), need_grad, group, global_batch)
+        if need_grad:
+            # The gradient workspace travels as a SAVED TENSOR: autograd frees it right after backward() unless the
+            # caller asked for retain_graph=True (then a second backward works, as with the reference's graph), and a
+            # second backward without it raises torch's usual "backward through the graph a second time" error.
+            ctx.save_for_backward(st.detach_workspace())
         ctx.state = st
         ctx.engine = engine
         ctx.x_shape = x.shape
@@ -64,8 +69,9 @@ class _SpectralLossFn(torch.autograd.Function):
             raise NotImplementedError(
                 "gradient w.r.t. the target is not implemented (no caller in the reference needs it: "
                 "trainer/denoise.py:75, autoencoder.py:98, vocoder.py:76 pass a constant target)")
+        (ws,) = ctx.saved_tensors          # keeps the workspace alive across the launch; raises if already released
         dx = ctx.engine.backward(ctx.state, g_sc, g_mag, g_mel)
-        ctx.state = None   # release the gradient workspace
+        del ws
         return dx.view(ctx.x_shape), None, None, None, None, None
 
 

@@ -129,7 +129,7 @@ class STFTLoss(torch.nn.Module):
                              self.window, self._twiddle)
 
     def forward(self, x, y):
-        return spectral_losses(x, y, [self.plan()], group=getattr(self, "process_group", None))
+        return spectral_losses(x, y, _cached_plans(self, [self]), group=getattr(self, "process_group", None))
 
 
 class MultiResolutionSTFTLoss(torch.nn.Module):

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SPL_ABI_VERSION 11
+#define SPL_ABI_VERSION 12
 
 #define SPL_OK 0
 #define SPL_E_INVALID (-1)   /* bad argument / outside the supported envelope */
@@ -109,11 +109,15 @@ int32_t spl_reduce_finalize(const spl_transform* ts, int32_t n, int32_t B, int32
  *               per sequence of calls that all ranks issue in the same order
  *   state     : local device uint32[2], zero before the first call (CTA ticket, call epoch)
  *   sums_local / sums_global : local device doubles [sum of n_sums] (this rank's sums / the global sums)
- * A peer that does not arrive within ~4 s poisons the losses with NaN instead of hanging the stream. */
+ *   timeout_ns: <= 0 waits for the peers as long as it takes, like a collective (the default of the Python host);
+ *               > 0: a peer that has not arrived after timeout_ns nanoseconds (device globaltimer) ends the wait: the
+ *               call's epoch (>= 1) is stored to *error_flag and the losses are NaN, so the step cannot be used silently
+ *   error_flag: NULL, or a uint32 the host can read WITHOUT synchronising (pinned mapped host memory, or device memory
+ *               the host copies back), zero before the first call */
 int64_t spl_exchange_buffer_bytes(void);
 int32_t spl_reduce_exchange_finalize(const spl_transform* ts, int32_t n, int32_t B, int32_t T, int64_t B_global,
                                      double* sums_local, double* sums_global, int32_t rank, int32_t world,
-                                     void* const* peer_bufs, uint32_t* state,
+                                     void* const* peer_bufs, uint32_t* state, int64_t timeout_ns, uint32_t* error_flag,
                                      float* sc, float* mag, float* mel, float* coefs, void* stream);
 
 /* Backward: dx (B, T) = g_sc * dsc/dx + g_mag * dmag/dx + g_mel * dmel/dx -- what autograd derives for

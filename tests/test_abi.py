@@ -103,10 +103,10 @@ def test_new_entry_points_reject_bad_arguments(lib):
     assert lib.spl_shape_backward(None, 2, 2, 9000, wl, 3, None, None, None) == -1
     assert lib.spl_spectrogram_backward(ctypes.byref(_tr()), None, 2, 9000, None, 513, None, None) == -1
     assert "null" in lib.spl_last_error().decode()
-    assert lib.spl_exchange_buffer_bytes() == 2 * 8 * 16 * 8 + 2 * 8 * 4
-    dummy = (ctypes.c_double * 16)()
+    assert lib.spl_exchange_buffer_bytes() == 2 * 8 * 24 * 8 + 2 * 8 * 4     # 24 = 3 sums x SPL_MAX_TRANSFORMS
+    dummy = (ctypes.c_double * 24)()
     state = (ctypes.c_uint32 * 2)()
     ptrs = (ctypes.c_void_p * 2)(ctypes.addressof(dummy), ctypes.addressof(dummy))
     rc = lib.spl_reduce_exchange_finalize(ctypes.byref(_tr()), 1, 2, 9000, 4, ctypes.addressof(dummy), ctypes.addressof(dummy),
-                                          5, 2, ptrs, ctypes.addressof(state), None, None, None, ctypes.addressof(dummy), None)
+                                          5, 2, ptrs, ctypes.addressof(state), 0, None, None, None, None, ctypes.addressof(dummy), None)
     assert rc == -1 and "rank" in lib.spl_last_error().decode()

@@ -89,7 +89,7 @@ def test_peer_exchange_protocol_three_ranks(emu_engine):
                 sc, mag, mel = (np.zeros(1, dtype=np.float32) for _ in range(3))
                 coefs = np.zeros(2 * st.n, dtype=np.float32)
                 rc = lib.spl_reduce_exchange_finalize(st.transforms, st.n, 1, t_len, world, lsums.ctypes.data,
-                                                      gsums.ctypes.data, rank, world, ptrs, state.ctypes.data,
+                                                      gsums.ctypes.data, rank, world, ptrs, state.ctypes.data, 0, None,
                                                       sc.ctypes.data, mag.ctypes.data, mel.ctypes.data, coefs.ctypes.data, None)
                 assert rc == 0, lib.spl_last_error()
                 assert int(state[1]) == call + 1 and int(state[0]) == 0
@@ -112,3 +112,49 @@ def test_peer_exchange_protocol_three_ranks(emu_engine):
             assert (sc, mag, mel) == results[0][call][:3]
             np.testing.assert_array_equal(gsums, results[0][call][3])
             np.testing.assert_array_equal(coefs, results[0][call][4])
+
+
+def test_peer_exchange_timeout_sets_host_visible_error(emu_engine):
+    """A finite timeout with a peer that never arrives: the call ends, the error word receives the call's epoch (the host
+    reads it without synchronising and raises on its next sharded call) and the losses are NaN -- never silent."""
+    import ctypes
+
+    from conftest import load_golden, plans_for
+
+    eng, lib = emu_engine, emu_engine.lib
+    g = load_golden("ragged_b3_t5003_2d")
+    yh, y = g["y_hat"].reshape(3, -1), g["y"].reshape(3, -1)
+    world = 2
+    nbytes = int(lib.spl_exchange_buffer_bytes())
+    bufs = [np.zeros(nbytes, dtype=np.uint8) for _ in range(world)]
+    ptrs = (ctypes.c_void_p * world)(*[b.ctypes.data for b in bufs])
+    state = np.zeros(2, dtype=np.uint32)
+    err = np.zeros(1, dtype=np.uint32)
+    st = eng.forward(plans_for(g), yh[:1].contiguous(), y[:1].contiguous(), need_grad=False)
+    n_sums = st.sums.numel()
+    lsums, gsums = np.zeros(n_sums), np.zeros(n_sums)
+    sc, mag, mel = (np.zeros(1, dtype=np.float32) for _ in range(3))
+    coefs = np.zeros(2 * st.n, dtype=np.float32)
+    rc = lib.spl_reduce_exchange_finalize(st.transforms, st.n, 1, yh.shape[1], world, lsums.ctypes.data, gsums.ctypes.data,
+                                          0, world, ptrs, state.ctypes.data, 100000, err.ctypes.data,
+                                          sc.ctypes.data, mag.ctypes.data, mel.ctypes.data, coefs.ctypes.data, None)
+    assert rc == 0, lib.spl_last_error()
+    assert int(err[0]) == 1                       # epoch of the failed call
+    assert np.isnan(sc[0]) and np.isnan(mag[0]) and np.isnan(mel[0])
+    assert np.all(lsums != 0) and not np.any(np.isnan(lsums))     # the local sums are untouched
+
+
+def test_engine_raises_on_exchange_error_flag(emu_engine):
+    """Engine.check_exchange_errors(): a non-zero error word raises SpecLossError and is cleared."""
+    from dl_speech_enhancement_b200 import _abi
+
+    err = torch.zeros(1, dtype=torch.int32)
+    emu_engine._exchanges[("g", "cpu", 7)] = dict(err=err, timeout_ns=1)
+    try:
+        emu_engine.check_exchange_errors()        # clean: no raise
+        err[0] = 3
+        with pytest.raises(_abi.SpecLossError, match="timed out"):
+            emu_engine.check_exchange_errors()
+        assert int(err[0]) == 0
+    finally:
+        emu_engine._exchanges.pop(("g", "cpu", 7))

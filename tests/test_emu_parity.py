@@ -251,3 +251,48 @@ def test_emulated_explicit_magnitude_losses(emu_engine):
         assert rel_l2(xg.grad.numpy(), xr.grad.numpy()) <= 1e-6 and rel_l2(yg.grad.numpy(), yr.grad.numpy()) <= 1e-6
     same = magnitude_loss(x.clone().requires_grad_(True), x, 0, engine=emu_engine)
     assert float(same.detach()) == 0.0
+
+
+def test_eight_resolutions_in_one_call(emu_engine):
+    """SPL_MAX_TRANSFORMS = 8 STFT resolutions = 24 sums in one call (the reduction and the exchange slot are sized for
+    3 x SPL_MAX_TRANSFORMS); a ninth raises."""
+    import torch
+
+    from dl_speech_enhancement_b200 import modules
+    from dl_speech_enhancement_b200.functional import spectral_losses
+    from oracle import spectral_oracle as so
+
+    res = [(512, 50 + 10 * i, 240) for i in range(8)]
+    crit = modules.MultiResolutionSTFTLoss([r[0] for r in res], [r[1] for r in res], [r[2] for r in res])
+    y_hat, y = so.synth_pair(1, 700, seed=5)
+    x = y_hat.clone().requires_grad_(True)
+    sc, mag = spectral_losses(x, y, crit.plans(), engine=emu_engine)
+    (sc + mag).backward()
+    ref, gref = so.losses_and_grad(y_hat, y, [so.StftRes(*r) for r in res], None, dtype=torch.float64)
+    np.testing.assert_allclose([float(sc), float(mag)], ref[:2], rtol=1e-4)
+    assert rel_l2(x.grad.numpy(), gref.numpy()) <= 1e-3
+    nine = modules.MultiResolutionSTFTLoss([512] * 9, [50] * 9, [240] * 9)
+    with pytest.raises(RuntimeError, match="resolutions"):
+        spectral_losses(x, y, nine.plans(), engine=emu_engine)
+
+
+def test_second_backward_needs_retain_graph(emu_engine):
+    """The gradient workspace is a saved tensor: backward(retain_graph=True) allows a second backward with the same result
+    (the reference's autograd graph behaves so), and a second backward without it raises torch's usual error."""
+    import torch
+
+    from dl_speech_enhancement_b200 import modules
+    from dl_speech_enhancement_b200.functional import spectral_losses
+    from oracle import spectral_oracle as so
+
+    crit = modules.MultiResolutionSTFTLoss([512], [50], [240])
+    y_hat, y = so.synth_pair(1, 700, seed=6)
+    x = y_hat.clone().requires_grad_(True)
+    sc, mag = spectral_losses(x, y, crit.plans(), engine=emu_engine)
+    (sc + mag).backward(retain_graph=True)
+    g1 = x.grad.clone()
+    x.grad = None
+    (sc + mag).backward()
+    assert torch.equal(g1, x.grad)
+    with pytest.raises(RuntimeError, match="second time|already been freed"):
+        (sc + mag).backward()
