@@ -1,0 +1,97 @@
+"""BASELINE configs[2] / SURVEY 8(f1): the reference's OWN denoise trainer step with a chosen pair of criteria.
+
+TEST / MEASUREMENT INFRASTRUCTURE ONLY.  Everything that runs is the reference's unmodified code
+(trainer.denoise.Trainer._train_step, trainer/denoise.py:52-84 -> TrainerGAN._metric_loss, trainerGAN.py:214-241 ->
+_update_generator, :271-281; models.autoencoder.AudioDec.Generator with the symAD_vctk_48000_hop300 hyper-parameters),
+imported through oracle/ref_loader.py; the only thing swapped is what sits in criterion["mel"] / criterion["stft"]:
+the reference's losses.MultiMelSpectrogramLoss / MultiResolutionSTFTLoss, or this repo's drop-in modules.  What the
+entry scripts of the reference do around the trainer (build the dicts, bin/train.py:66-103, train_denoise.py:100-135) is
+restated here in a dozen lines, because the concrete entry script is not part of the reference repo.
+"""
+from __future__ import annotations
+
+import copy
+import tempfile
+import time
+
+import torch
+
+from oracle import ref_loader
+
+
+class _NoTqdm:
+    def update(self, n=1):
+        pass
+
+    def close(self):
+        pass
+
+
+def synthetic_batches(n, batch, length, seed, device="cpu"):
+    """(x_noisy, x_clean) pairs shaped like dataloader/collater.py:57-60 output: (B, 1, T) fp32."""
+    g = torch.Generator().manual_seed(seed)
+    out = []
+    for _ in range(n):
+        clean = 0.1 * torch.randn(batch, 1, length, generator=g)
+        noisy = clean + 0.05 * torch.randn(batch, 1, length, generator=g)
+        out.append((noisy.to(device), clean.to(device)))
+    return out
+
+
+def build_trainer(ns, mel_cls, stft_cls, device, seed=0, use_stft=True, init_state=None):
+    """A trainer.denoise.Trainer over a freshly initialised (seeded) symAD generator.  mel_cls / stft_cls are the criterion
+    classes (reference's or this repo's); both take the YAML blocks verbatim."""
+    cfg = copy.deepcopy(ns.config)
+    cfg["use_mel_loss"] = True
+    cfg["use_stft_loss"] = bool(use_stft)         # shipped YAML: false; flipping it is the MR-STFT route
+    cfg["outdir"] = tempfile.mkdtemp(prefix="specloss_trainer_")
+    cfg["train_max_steps"] = 1 << 30
+    torch.manual_seed(seed)
+    gen = ns.Generator(**cfg["generator_params"])
+    if init_state is not None:
+        gen.load_state_dict(init_state)
+    gen = gen.to(device)
+    criterion = {"mel": mel_cls(**cfg["mel_loss_params"]).to(device)}
+    if use_stft:
+        criterion["stft"] = stft_cls(**cfg["stft_loss_params"]).to(device)
+    opt = torch.optim.Adam(gen.parameters(), **cfg["generator_optimizer_params"])
+    sch = torch.optim.lr_scheduler.StepLR(opt, **cfg["generator_scheduler_params"])
+    tr = ns.Trainer(steps=0, epochs=0, data_loader={}, model={"generator": gen}, criterion=criterion,
+                    optimizer={"generator": opt}, scheduler={"generator": sch}, config=cfg, device=device)
+    tr.tqdm = _NoTqdm()
+    return tr
+
+
+def run_steps(trainer, batches):
+    """Runs Trainer._train_step on every batch; returns the per-step records the trainer itself keeps
+    (total_train_loss is a running sum: the per-step value is the difference)."""
+    keys = ("train/mel_loss", "train/spectral_convergence_loss", "train/log_stft_magnitude_loss", "train/generator_loss")
+    prev = {k: 0.0 for k in keys}
+    rows = []
+    for batch in batches:
+        trainer._train_step(batch)
+        row = {}
+        for k in keys:
+            cur = trainer.total_train_loss.get(k, 0.0)
+            row[k.split("/", 1)[1]] = cur - prev[k]
+            prev[k] = cur
+        rows.append(row)
+    return rows
+
+
+def time_steps(trainer, batches, warmup=3):
+    """Wall-clock ms per _train_step (the step ends with .item() syncs, trainerGAN.py:299-300) after `warmup` steps."""
+    for b in batches[:warmup]:
+        trainer._train_step(b)
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for b in batches[warmup:]:
+        trainer._train_step(b)
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
+    return 1e3 * (time.perf_counter() - t0) / max(1, len(batches) - warmup)
+
+
+def load():
+    return ref_loader.load_reference_trainer()
