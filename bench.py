@@ -2,17 +2,24 @@
 """Benchmark of the spectral-loss hot path: MultiResolutionSTFTLoss (3 resolutions) +
 MultiMelSpectrogramLoss (2048/300, 80 mels) forward+backward, audio-seconds per second.
 
-    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
-    python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU op sequence (oracle port)
+    python bench.py --gpus N --steps K --warmup W             # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...    # the reference's own modules on the host cores
 
-Workload (BASELINE.json configs[1]): batch 16 x 1 s synthetic 48 kHz audio per GPU (weak scaling:
-every rank holds its own 16 utterances; the loss partial sums are all-reduced over NCCL so each rank
-returns the losses of the global batch).  A step = one fwd+bwd of both criteria through the drop-in
-nn.Modules; the input pair of each step is taken round-robin from a pool larger than L2.
-Prints ONE JSON line (rank 0).
+Workload (BASELINE.json configs[3], the configuration the 1/2/4/8-GPU metric is quoted on): a GLOBAL batch of
+256 x 4 s synthetic 48 kHz audio, batch-sharded over the N ranks (256/N utterances per GPU, N=1 runs all 256 on one
+GPU) -- strong scaling.  The loss partial sums are exchanged between the ranks so every rank returns the losses of the
+global batch.  A step = one fwd+bwd of both criteria through the drop-in nn.Modules, launched eagerly, exactly
+as trainer/trainerGAN.py:214-241,271-281 drives them (no CUDA graphs in the headline).  The timed region is repeated
+blocks of exactly K steps (each bracketed by barrier + synchronize, device time by CUDA events, max over ranks); the
+median block is reported.  `config.secondary` carries BASELINE configs[1] (16 x 1 s per GPU, the round-1 headline) so
+rounds stay comparable.  At N > 1 a `sharded_parity` block (outside the timed region) checks that all ranks hold
+bit-identical losses equal to rank 0's unsharded evaluation of the gathered global batch, and that every rank's gradient
+rows equal that run's; a failure makes the process exit non-zero.  Prints ONE JSON line (rank 0).
 """
 import argparse
+import hashlib
 import json
+import math
 import os
 import subprocess
 import sys
@@ -24,14 +31,17 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 FS = 48000
-BATCH = 16
-T_LEN = 48000
+GLOBAL_BATCH = 256              # configs[3]
+T_LEN = 4 * FS
+SEC_BATCH, SEC_T = 16, FS       # configs[1] (per GPU), reported as config.secondary
 MEL_KW = dict(fs=FS, fft_sizes=[2048], hop_sizes=[300], win_lengths=[None], window="hann_window",
               num_mels=80, fmin=0, fmax=24000, log_base=None)
 STFT_RES = [(1024, 120, 600), (2048, 240, 1200), (512, 50, 240)]
 METRIC = "spectral_loss_fwd_bwd_audio_seconds_per_second"
 UNIT = "audio-s/s"
 POOL_BYTES = 192 << 20          # > 126 MB L2
+MIN_TIMED_S = 0.25              # repeat K-step blocks until the timed region is at least this long
+MAX_BLOCKS = 40
 
 
 def peaks():
@@ -44,11 +54,26 @@ def peaks():
 
 def nominal_flops(batch, t_len):
     """5 passes x sum_res B*F*2.5*N*log2(N)."""
-    import math
     tot = 0.0
     for n, hop, _ in STFT_RES + [(2048, 300, 2048)]:
         tot += batch * (1 + t_len // hop) * 2.5 * n * math.log2(n)
     return 5.0 * tot
+
+
+def workload_name(batch, t_len):
+    tag = "configs[3]: " if (batch, t_len) == (256, 4 * FS) else ("configs[1]: " if (batch, t_len) == (16, FS) else "non-default size: ")
+    return tag + f"global batch {batch} x {t_len / FS:g} s synthetic 48 kHz, MR-STFT(1024/2048/512) + 80-mel hop-300, fwd+bwd"
+
+
+def csrc_hash():
+    """Identifies the kernel sources a committed ncu capture belongs to."""
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "dl_speech_enhancement_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh", ".inl")):
+            with open(os.path.join(d, f), "rb") as fh:
+                h.update(fh.read())
+    return h.hexdigest()[:16]
 
 
 class ClockSampler:
@@ -62,8 +87,10 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "50", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
+            time.sleep(0.3)           # nvidia-smi start-up: the first sample must not post-date the timed region
+            self.rows.clear()
         except OSError:
             self.proc = None
 
@@ -74,7 +101,7 @@ class ClockSampler:
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.08)
         self.proc.terminate()
         sm = sorted(float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit())
         reasons = set()
@@ -89,39 +116,70 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------
-# reference arm / CPU baseline: the reference's ATen op sequence on the host cores (oracle port)
+# reference arm / CPU baseline: the reference's OWN modules (losses/stft_loss.py, losses/mel_loss.py) on the host cores.
+# oracle/_ref holds their unmodified copies (oracle/make_ref.sh) -- kind "reference"; if that staging is missing the
+# oracle's restatement of the same op sequence is timed instead -- kind "port".
 # --------------------------------------------------------------------------------------------
 def cpu_reference_step_time(batch, t_len, steps, warmup):
     import torch
-    from oracle import spectral_oracle as so     # checker/baseline only; never on the product path
+    from oracle import ref_loader, spectral_oracle as so     # checker/baseline only; never on the product path
 
     torch.set_num_threads(os.cpu_count())
-    mel = so.mel_from_kwargs(**MEL_KW)
     y_hat, y = so.synth_pair(batch, t_len, seed=0)
+    kind = "port"
+    if ref_loader.available():
+        stft_mod, mel_mod = ref_loader.load_reference_losses()
+        stft = stft_mod.MultiResolutionSTFTLoss()
+        mel = mel_mod.MultiMelSpectrogramLoss(**MEL_KW)
+        kind = "reference"
+
+        def step():
+            xx = y_hat.detach().clone().requires_grad_(True)
+            ml = mel(xx, y)                                   # trainerGAN.py:220
+            sc, mag = stft(xx, y)                             # trainerGAN.py:227
+            (sc + mag + ml).backward()
+    else:
+        mel_res = so.mel_from_kwargs(**MEL_KW)
+
+        def step():
+            so.losses_and_grad(y_hat, y, so.DEFAULT_STFT, mel_res, dtype=torch.float32, use_torch_stft=True)
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        so.losses_and_grad(y_hat, y, so.DEFAULT_STFT, mel, dtype=torch.float32, use_torch_stft=True)
+        step()
         if i >= warmup:
             times.append(time.perf_counter() - t0)
-    return times, torch.get_num_threads()
+    return times, torch.get_num_threads(), kind
 
 
-def gpu_reference_step_time(batch, t_len, dev, steps=20, warmup=3):
+def gpu_reference_step_time(batch, t_len, dev, steps=10, warmup=2):
     """The reference's op sequence (torch.stft -> cuFFT, ATen elementwise, cuBLAS matmul, autograd) on the SAME GPU:
     what the trainer runs today when its criteria sit on a CUDA device.  Eager launches, CUDA events."""
     import torch
-    from oracle import spectral_oracle as so     # baseline only; never on the product path
+    from oracle import ref_loader, spectral_oracle as so     # baseline only; never on the product path
 
-    mel = so.mel_from_kwargs(**MEL_KW)
     y_hat, y = so.synth_pair(batch, t_len, seed=0)
     y_hat, y = y_hat.to(dev), y.to(dev)
+    if ref_loader.available():
+        stft_mod, mel_mod = ref_loader.load_reference_losses()
+        stft = stft_mod.MultiResolutionSTFTLoss().to(dev)
+        mel = mel_mod.MultiMelSpectrogramLoss(**MEL_KW).to(dev)
+        what = "the reference's own modules (.cuda(): torch.stft/cuFFT + ATen + cuBLAS + autograd)"
 
-    def step():
-        xx = y_hat.detach().clone().requires_grad_(True)
-        sc, mag = so.mr_stft_loss(xx, y, so.DEFAULT_STFT, use_torch_stft=True)
-        ml = so.multi_mel_loss(xx, y, mel, use_torch_stft=True)
-        (sc + mag + ml).backward()
+        def step():
+            xx = y_hat.detach().clone().requires_grad_(True)
+            ml = mel(xx, y)
+            sc, mag = stft(xx, y)
+            (sc + mag + ml).backward()
+    else:
+        mel_res = so.mel_from_kwargs(**MEL_KW)
+        what = "the reference's op sequence (oracle port; torch.stft/cuFFT + ATen + cuBLAS + autograd)"
+
+        def step():
+            xx = y_hat.detach().clone().requires_grad_(True)
+            sc, mag = so.mr_stft_loss(xx, y, so.DEFAULT_STFT, use_torch_stft=True)
+            ml = so.multi_mel_loss(xx, y, mel_res, use_torch_stft=True)
+            (sc + mag + ml).backward()
 
     for _ in range(warmup):
         step()
@@ -132,27 +190,30 @@ def gpu_reference_step_time(batch, t_len, dev, steps=20, warmup=3):
         step()
     b.record()
     torch.cuda.synchronize()
-    return a.elapsed_time(b) / steps
+    return a.elapsed_time(b) / steps, what
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
     # bounded sample: probe one utterance, then size the per-step batch so K+W steps stay within ~2 minutes
-    probe, cores = cpu_reference_step_time(1, T_LEN, 1, 1)
+    probe, cores, kind = cpu_reference_step_time(1, T_LEN, 1, 1)
     budget = 120.0 / max(1, args.steps + args.warmup)
-    b = int(max(1, min(BATCH, budget / max(probe[0], 1e-6))))
-    times, cores = cpu_reference_step_time(b, T_LEN, args.steps, args.warmup)
+    b = int(max(1, min(GLOBAL_BATCH, 64, budget / max(probe[0], 1e-6))))      # <= 64 x 4 s: a few GB of host RAM
+    times, cores, kind = cpu_reference_step_time(b, T_LEN, args.steps, args.warmup)
     ms = 1000.0 * sum(times) / len(times)
     value = b * T_LEN / FS / (ms / 1000.0)
-    sample = f"{b} x {T_LEN / FS:g} s @ 48 kHz per step (of the {BATCH} x {T_LEN / FS:g} s workload), {args.steps} steps, mean"
+    sample = (f"{b} x {T_LEN / FS:g} s @ 48 kHz per step (a bounded sample of the {GLOBAL_BATCH} x {T_LEN / FS:g} s workload; "
+              f"throughput is linear in the batch, SURVEY 8d), {args.steps} steps, mean")
+    path = ("the reference's own modules losses/stft_loss.py + losses/mel_loss.py (unmodified copies under oracle/_ref) on CPU"
+            if kind == "reference" else
+            "torch.stft + ATen elementwise/norm/matmul + autograd on CPU (oracle port of losses/stft_loss.py, losses/mel_loss.py)")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": ("configs[1]: " if (BATCH, T_LEN) == (16, 48000) else "non-default size: ")
-                                   + f"batch {BATCH} x {T_LEN / FS:g} s synthetic 48 kHz, MR-STFT(1024/2048/512) + 80-mel hop-300, fwd+bwd",
-                       "reference_path": "torch.stft + ATen elementwise/norm/matmul + autograd on CPU (oracle port of losses/stft_loss.py, losses/mel_loss.py)"},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(GLOBAL_BATCH, T_LEN), "global_batch": GLOBAL_BATCH,
+                       "samples_per_utterance": T_LEN, "fs": FS, "reference_path": path},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -174,6 +235,9 @@ def run_ours(args, rank, local_rank, world):
     import dl_speech_enhancement_b200 as pkg
     from dl_speech_enhancement_b200.engine import cuda_engine
 
+    if GLOBAL_BATCH % world:
+        raise SystemExit(f"global batch {GLOBAL_BATCH} is not divisible by {world} ranks")
+    b_local = GLOBAL_BATCH // world
     dev = torch.device(f"cuda:{local_rank}")
     torch.cuda.set_device(dev)
     group = None
@@ -192,36 +256,40 @@ def run_ours(args, rank, local_rank, world):
             os.dup2(saved_fd, 1)
             os.close(saved_fd)
         group = dist.group.WORLD
-    cuda_engine()          # raises if libspecloss.so is missing -- no fallback
+    eng = cuda_engine()          # raises if libspecloss.so is missing -- no fallback
     log("process group + engine ready")
 
-    stft = pkg.MultiResolutionSTFTLoss().to(dev)
-    mel = pkg.MultiMelSpectrogramLoss(**MEL_KW).to(dev)
-    stft.process_group = group
-    mel.process_group = group
+    def make_criteria(grp):
+        s = pkg.MultiResolutionSTFTLoss().to(dev)
+        m = pkg.MultiMelSpectrogramLoss(**MEL_KW).to(dev)
+        s.process_group = grp
+        m.process_group = grp
+        return s, m
 
-    pair_bytes = 2 * BATCH * T_LEN * 4
-    n_pool = max(2, POOL_BYTES // pair_bytes)
-    gen = torch.Generator(device=dev).manual_seed(1000 + rank)
-    pool = []
-    for _ in range(n_pool):
-        y = 0.1 * torch.randn(BATCH, 1, T_LEN, device=dev, generator=gen)
-        y_hat = (y + 0.05 * torch.randn(BATCH, 1, T_LEN, device=dev, generator=gen)).requires_grad_(True)
-        pool.append((y_hat, y))
+    stft, mel = make_criteria(group)
 
-    eng = cuda_engine()
+    def make_pool(batch, t_len, seed):
+        pair_bytes = 2 * batch * t_len * 4
+        n = max(2, -(-POOL_BYTES // pair_bytes))
+        gen = torch.Generator(device=dev).manual_seed(seed)
+        pool = []
+        for _ in range(n):
+            y = 0.1 * torch.randn(batch, 1, t_len, device=dev, generator=gen)
+            y_hat = (y + 0.05 * torch.randn(batch, 1, t_len, device=dev, generator=gen)).requires_grad_(True)
+            pool.append((y_hat, y))
+        return pool, pair_bytes
 
-    def losses_and_backward(y_hat, y):
-        ml = mel(y_hat, y)                 # criterion["mel"](predict_y, natural_y)   trainerGAN.py:220
-        sc, mag = stft(y_hat, y)           # criterion["stft"](predict_y, natural_y)  trainerGAN.py:227
-        (sc + mag + ml).backward()
+    def losses_and_backward(y_hat, y, crit=None):
+        s, m = crit or (stft, mel)
+        ml = m(y_hat, y)                 # criterion["mel"](predict_y, natural_y)   trainerGAN.py:220
+        sc, mag = s(y_hat, y)            # criterion["stft"](predict_y, natural_y)  trainerGAN.py:227
+        (sc + mag + ml).backward()       # _update_generator                        trainerGAN.py:274
         return sc, mag, ml
 
     mel_stream = torch.cuda.Stream()
 
     def losses_and_backward_2s(y_hat, y):
-        """The same two criterion calls, the mel criterion issued on a second stream: its kernels (forward, and the
-        backward node autograd runs on the forward's stream) overlap the STFT criterion's.  Module API unchanged."""
+        """The same two criterion calls, the mel criterion issued on a second stream (secondary workload, graphs only)."""
         cur = torch.cuda.current_stream()
         mel_stream.wait_stream(cur)
         with torch.cuda.stream(mel_stream):
@@ -231,189 +299,72 @@ def run_ours(args, rank, local_rank, world):
         (sc + mag + ml).backward()
         return sc, mag, ml
 
-    globals_losses_and_backward = losses_and_backward
-
-    def eager_step(i):
-        y_hat, y = pool[i % n_pool]
-        y_hat.grad = None
-        return losses_and_backward(y_hat, y)
-
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(step_fn, steps, warmup, sample_clocks=False):
+    def max_over_ranks(v):
+        t = torch.tensor([v], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed_blocks(step_fn, steps, warmup, sample_clocks=False, min_s=MIN_TIMED_S):
+        """Blocks of EXACTLY `steps` steps, each bracketed by barrier + synchronize, timed with CUDA events on the launch
+        stream, max over ranks; repeated (the block count is agreed between the ranks after the first block) until the
+        timed region covers min_s seconds.  Returns (median ms/step, per-block ms/step, launches per block, clocks)."""
         for i in range(warmup):
             step_fn(i)
         barrier()
         sampler = ClockSampler(local_rank) if (sample_clocks and rank == 0) else None
         if sampler:
             sampler.start()
-        n0 = eng.launches
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        ev0.record()
-        for i in range(steps):
-            step_fn(warmup + i)
-        ev1.record()
-        barrier()
-        ms = ev0.elapsed_time(ev1)
+        blocks, launches, k, n_blocks = [], 0, warmup, 1
+        while len(blocks) < n_blocks:
+            n0 = eng.launches
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            ev0.record()
+            for i in range(steps):
+                step_fn(k + i)
+            ev1.record()
+            barrier()
+            k += steps
+            blocks.append(max_over_ranks(ev0.elapsed_time(ev1)) / steps)
+            launches = eng.launches - n0
+            if len(blocks) == 1:
+                n_blocks = int(min(MAX_BLOCKS, max(3, math.ceil(min_s / max(blocks[0] * steps * 1e-3, 1e-6)))))
         clocks = sampler.stop() if sampler else None
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()) / steps, eng.launches - n0, clocks
+        return sorted(blocks)[len(blocks) // 2], blocks, launches, clocks
 
-    # ---- eager: one Python-driven launch sequence per step -----------------------------------------
+    # ---- primary workload: eager launches through the modules, as the trainer drives them -----------------------
+    pool, pair_bytes = make_pool(b_local, T_LEN, 1000 + rank)
+    n_pool = len(pool)
+
+    def eager_step(i):
+        y_hat, y = pool[i % n_pool]
+        y_hat.grad = None
+        return losses_and_backward(y_hat, y)
+
     log("pool ready, timing eager steps")
-    eager_ms, eager_launches, clocks = timed(eager_step, args.steps, args.warmup, sample_clocks=True)
-    log(f"eager {eager_ms:.4f} ms/step")
-    mode, ms_per_step, launches_timed = "eager launches", eager_ms, eager_launches
-
-    # ---- CUDA graph: the same step captured once and replayed (inputs are copied into the graph's static
-    #      buffers inside the timed region: device-to-device from the rotating pool for `value`, from pinned
-    #      host memory for `e2e`).  Two buffer sets so that e2e can copy step i+1 while step i runs. ---------
-    def capture_set(step_fn=None):
-        losses_and_backward = step_fn or globals_losses_and_backward
-        sx = pool[0][0].detach().clone().requires_grad_(True)
-        sy = pool[0][1].clone()
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            for _ in range(3):
-                sx.grad = None
-                losses_and_backward(sx, sy)
-        torch.cuda.current_stream().wait_stream(side)
-        sx.grad = None
-        n_before = eng.launches
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            sc, mag, ml = losses_and_backward(sx, sy)
-            vec = torch.stack([sc.detach(), mag.detach(), ml.detach()])
-        return dict(sx=sx, sy=sy, graph=graph, losses=(sc, mag, ml), vec=vec, launches=eng.launches - n_before)
-
-    # Variants of the captured step: the trainer's literal call sequence on one stream, and the same two criterion calls
-    # with the mel criterion on a second stream (no module/API change).  Sharded runs take the second variant only when
-    # the exchange step is the in-kernel peer-memory one: NCCL collectives of one communicator stay on one stream.
-    # sharded: is the exchange step the in-kernel NVLink peer-memory one on EVERY rank (then the step holds no NCCL call)?
+    ms_per_step, block_ms, launches_timed, clocks = timed_blocks(eager_step, args.steps, args.warmup, sample_clocks=True)
+    log(f"eager {ms_per_step:.4f} ms/step over {len(block_ms)} blocks")
+    value = GLOBAL_BATCH * T_LEN / FS / (ms_per_step / 1000.0)
     peer = 1 if (world > 1 and eng.peer_exchange_active()) else 0
     if world > 1:
         pf = torch.tensor([peer], device=dev)
         dist.all_reduce(pf, op=dist.ReduceOp.MIN)
         peer = int(pf.item())
-    variants = [("1 stream", losses_and_backward)]
-    if (world == 1 or peer) and not args.one_stream:
-        variants.append(("mel criterion on a 2nd stream", losses_and_backward_2s))
-    graph_ms, sets, graph_variant, graph_times = None, None, None, {}
-    for vname, vfn in ([] if args.no_graph else variants):
-        ok = 1
-        log(f"capturing CUDA graphs ({vname})")
-        try:
-            vsets = [capture_set(vfn), capture_set(vfn)]
-        except Exception as exc:      # graph capture is an optimisation of the launch path, never a requirement
-            print(f"[bench] CUDA graph mode ({vname}) unavailable: {exc!r}", file=sys.stderr)
-            ok = 0
-        flag = torch.tensor([ok], device=dev)
-        if world > 1:
-            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-        if int(flag.item()) == 0:
-            continue
-        g0 = vsets[0]
 
-        def graph_step(i, g0=g0):
-            y_hat, y = pool[i % n_pool]
-            g0["sx"].data.copy_(y_hat.data)
-            g0["sy"].copy_(y)
-            g0["graph"].replay()
-
-        log("timing graph replays")
-        v_ms, _, clocks_g = timed(graph_step, args.steps, args.warmup, sample_clocks=True)
-        log(f"graph ({vname}) {v_ms:.4f} ms/step")
-        # the replayed step must reproduce the eager result bit for bit
-        graph_step(0)
-        ref = eager_step(0)
-        torch.cuda.synchronize()
-        same = all(float(a.detach()) == float(b.detach()) for a, b in zip(g0["losses"], ref))
-        same = same and torch.equal(g0["sx"].grad, pool[0][0].grad)
-        flag = torch.tensor([1 if same else 0], device=dev)
-        if world > 1:
-            dist.all_reduce(flag, op=dist.ReduceOp.MIN)      # every rank must take the same branch below
-        same = bool(int(flag.item()))
-        if not same:
-            print(f"[bench] CUDA graph replay ({vname}) does not reproduce the eager step; ignoring it", file=sys.stderr)
-            continue
-        graph_times[vname] = v_ms
-        if graph_ms is None or v_ms < graph_ms:
-            graph_ms, sets, graph_variant = v_ms, vsets, vname
-            if v_ms < ms_per_step:
-                mode, ms_per_step, clocks = f"CUDA graph replay, {vname}", v_ms, clocks_g
-                launches_timed = g0["launches"] * args.steps
-    # ---- one captured graph PER pool entry (shared memory pool): the replayed step reads its inputs where they already
-    #      are in HBM -- no staging copy into static buffers inside the timed region -- and the rotation over the whole
-    #      pool (> L2) still makes every step find its inputs outside the cache ---------------------------------------
-    graph_direct_ms = None
-    if sets is not None and not args.no_direct_graphs:
-        ok = 1
-        try:
-            vfn = dict(variants)[graph_variant]
-            mem_pool = torch.cuda.graph_pool_handle()
-            directs = []
-            side = torch.cuda.Stream()
-            for (px0, py) in pool:
-                # a fresh leaf over the same storage: its AccumulateGrad node is first used on a side stream (the pool's
-                # own leaves were used on the default stream by the eager steps, which a capture must not touch)
-                px = px0.detach().requires_grad_(True)
-                side.wait_stream(torch.cuda.current_stream())
-                with torch.cuda.stream(side):
-                    vfn(px, py)
-                    px.grad = None
-                torch.cuda.current_stream().wait_stream(side)
-                gph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(gph, pool=mem_pool):
-                    outs = vfn(px, py)
-                directs.append((gph, outs, px))
-        except Exception as exc:
-            print(f"[bench] per-entry graphs unavailable: {exc!r}", file=sys.stderr)
-            ok = 0
-        flag = torch.tensor([ok], device=dev)
-        if world > 1:
-            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-        if int(flag.item()) == 1:
-            def direct_step(i):
-                directs[i % n_pool][0].replay()
-
-            d_ms, _, clocks_d = timed(direct_step, args.steps, args.warmup, sample_clocks=True)
-            log(f"graph per pool entry ({graph_variant}) {d_ms:.4f} ms/step")
-            # entry 0 replayed must reproduce the eager step on entry 0 bit for bit (graphs share one memory pool: the
-            # outputs of a graph are only valid until the next replay)
-            direct_step(0)
-            torch.cuda.synchronize()
-            got = [float(o.detach()) for o in directs[0][1]]
-            ggrad = directs[0][2].grad.clone()
-            ref = eager_step(0)
-            torch.cuda.synchronize()
-            same = got == [float(o.detach()) for o in ref] and torch.equal(ggrad, pool[0][0].grad)
-            flag = torch.tensor([1 if same else 0], device=dev)
-            if world > 1:
-                dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-            if int(flag.item()) == 1:
-                graph_direct_ms = d_ms
-                if d_ms < ms_per_step:
-                    mode, ms_per_step, clocks = f"CUDA graph replay (one graph per input pair), {graph_variant}", d_ms, clocks_d
-            else:
-                print("[bench] per-entry graph replay does not reproduce the eager step; ignoring it", file=sys.stderr)
-            directs.clear()
-    value = world * BATCH * T_LEN / FS / (ms_per_step / 1000.0)
-
-    # ---- e2e: pinned host inputs -> H2D -> fwd+bwd -> D2H of the three losses + sync, every step.  The copy
-    #      of step i+1 is issued on a copy stream before step i's result is awaited (what a DataLoader with
-    #      pinned memory + non_blocking copies gives the trainer). -------------------------------------
-    host = [(p[0].detach().cpu().pin_memory(), p[1].cpu().pin_memory()) for p in pool[:4]]
+    # ---- e2e: pinned host inputs -> H2D -> fwd+bwd -> D2H of the three losses + sync, every step.  The copy of step
+    #      i+1 is issued on a copy stream before step i's result is awaited (what a DataLoader with pinned memory +
+    #      non_blocking copies gives the trainer). -------------------------------------------------------------
+    host = [(p[0].detach().cpu().pin_memory(), p[1].cpu().pin_memory()) for p in pool[:2]]
     copy_stream = torch.cuda.Stream()
     host_out = torch.empty(3, dtype=torch.float32).pin_memory()
 
-    def e2e_loop_eager(steps):
+    def e2e_loop(steps):
         def fetch(i):
             hx, hy = host[i % len(host)]
             with torch.cuda.stream(copy_stream):
@@ -434,55 +385,98 @@ def run_ours(args, rank, local_rank, world):
             host_out.copy_(torch.stack([sc.detach(), mag.detach(), ml.detach()]), non_blocking=True)
             torch.cuda.current_stream().synchronize()            # the trainer's .item()
 
-    def e2e_loop_graph(steps):
-        evs = [None, None]
-
-        def issue_copy(i):
-            hx, hy = host[i % len(host)]
-            st = sets[i % 2]
-            with torch.cuda.stream(copy_stream):
-                st["sx"].data.copy_(hx, non_blocking=True)
-                st["sy"].copy_(hy, non_blocking=True)
-                evs[i % 2] = torch.cuda.Event()
-                evs[i % 2].record(copy_stream)
-        issue_copy(0)
-        for i in range(steps):
-            st = sets[i % 2]
-            torch.cuda.current_stream().wait_event(evs[i % 2])
-            issue_copy(i + 1)          # other buffer set: its last consumer (step i-1) was synchronised on
-            st["graph"].replay()
-            host_out.copy_(st["vec"], non_blocking=True)
-            torch.cuda.current_stream().synchronize()            # the trainer's .item()
-
-    e2e_loop = e2e_loop_graph if sets is not None else e2e_loop_eager
-    e2e_mode = f"CUDA graph replay, {graph_variant}" if sets is not None else "eager launches"
-    log("e2e (" + e2e_mode + ")")
-    e2e_loop(max(3, args.warmup // 4))
+    log("e2e")
+    e2e_loop(3)
     barrier()
-    # wall-clock numbers on a shared host are noisy (PCIe, wake-up latency of the per-step synchronize): three runs,
-    # each the max over ranks, the median reported
-    e_steps = max(10, args.steps // 2)
+    e_steps = max(5, args.steps // 2)
     e_runs = []
-    for _ in range(3):
+    for _ in range(3):                   # wall clock on a shared host is noisy: three runs, each max over ranks, median
         barrier()
         t0 = time.perf_counter()
         e2e_loop(e_steps)
         barrier()
-        e_ms = 1000.0 * (time.perf_counter() - t0) / e_steps
-        t = torch.tensor([e_ms], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e_runs.append(float(t.item()))
+        e_runs.append(max_over_ranks(1000.0 * (time.perf_counter() - t0) / e_steps))
     e2e_ms = sorted(e_runs)[1]
-    e2e_value = world * BATCH * T_LEN / FS / (e2e_ms / 1000.0)
+    e2e_value = GLOBAL_BATCH * T_LEN / FS / (e2e_ms / 1000.0)
+    del host
     log("e2e done")
 
+    # ---- sharded parity (outside the timed region): N-rank result == 1-rank evaluation of the gathered global batch ----
+    sharded_parity, parity_ok = None, True
+    if world > 1 and not args.no_parity:
+        sharded_parity, parity_ok = check_sharded_parity(torch, dist, pkg, eng, dev, rank, world, group, pool[0], make_criteria,
+                                                         losses_and_backward, log)
+
+    # ---- secondary workload: BASELINE configs[1], 16 x 1 s per GPU (weak), eager and captured-graph replay --------
+    secondary = None
+    if not args.no_secondary:
+        del pool
+        torch.cuda.empty_cache()
+        spool, s_pair_bytes = make_pool(SEC_BATCH, SEC_T, 2000 + rank)
+        ns = len(spool)
+
+        def s_eager(i):
+            y_hat, y = spool[i % ns]
+            y_hat.grad = None
+            return losses_and_backward(y_hat, y)
+
+        s_steps = max(args.steps, 20)
+        s_eager_ms, _, _, _ = timed_blocks(s_eager, s_steps, args.warmup, min_s=0.1)
+        secondary = {"workload": f"configs[1]: batch {SEC_BATCH} x {SEC_T / FS:g} s synthetic 48 kHz PER GPU (weak), same criteria",
+                     "eager_ms_per_step": s_eager_ms,
+                     "eager_value": world * SEC_BATCH * SEC_T / FS / (s_eager_ms / 1000.0), "unit": UNIT}
+        graph_ms = None
+        if (world == 1 or peer) and not args.no_graph:
+            ok = 1
+            try:
+                mem_pool = torch.cuda.graph_pool_handle()
+                directs = []
+                side = torch.cuda.Stream()
+                for (px0, py) in spool:
+                    px = px0.detach().requires_grad_(True)
+                    side.wait_stream(torch.cuda.current_stream())
+                    with torch.cuda.stream(side):
+                        losses_and_backward_2s(px, py)
+                        px.grad = None
+                    torch.cuda.current_stream().wait_stream(side)
+                    gph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(gph, pool=mem_pool):
+                        outs = losses_and_backward_2s(px, py)
+                    directs.append((gph, outs, px))
+            except Exception as exc:      # graph capture is an optimisation of the launch path, never a requirement
+                print(f"[bench] CUDA graph mode unavailable: {exc!r}", file=sys.stderr)
+                ok = 0
+            flag = torch.tensor([ok], device=dev)
+            if world > 1:
+                dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()) == 1:
+                def direct_step(i):
+                    directs[i % ns][0].replay()
+
+                d_ms, _, _, _ = timed_blocks(direct_step, s_steps, args.warmup, min_s=0.1)
+                direct_step(0)
+                torch.cuda.synchronize()
+                got = [float(o.detach()) for o in directs[0][1]]
+                ggrad = directs[0][2].grad.clone()
+                ref = s_eager(0)
+                torch.cuda.synchronize()
+                same = got == [float(o.detach()) for o in ref] and torch.equal(ggrad, spool[0][0].grad)
+                flag = torch.tensor([1 if same else 0], device=dev)
+                if world > 1:
+                    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+                if int(flag.item()) == 1:
+                    graph_ms = d_ms
+                else:
+                    print("[bench] graph replay does not reproduce the eager step; ignoring it", file=sys.stderr)
+            directs = None
+        secondary["graph_ms_per_step"] = graph_ms
+        secondary["graph_value"] = None if graph_ms is None else world * SEC_BATCH * SEC_T / FS / (graph_ms / 1000.0)
+        secondary["graph_mode"] = "one captured CUDA graph per input pair, mel criterion on a 2nd stream, bit-equal to the eager step"
+        pool = spool
+        log(f"secondary: eager {s_eager_ms:.4f} ms, graph {graph_ms}")
+
     def teardown():
-        """Release the captured graphs before the communicator; never let teardown hang the job."""
-        nonlocal sets
-        for st in (sets or []):
-            st.clear()               # drops the CUDAGraph objects (they hold NCCL work when world > 1)
-        sets = None
+        """Never let communicator teardown hang the job."""
         import gc
         gc.collect()
         torch.cuda.synchronize()
@@ -500,124 +494,229 @@ def run_ours(args, rank, local_rank, world):
                 log("process-group teardown timed out; exiting")
                 sys.stdout.flush()
                 sys.stderr.flush()
-                os._exit(0)
+                os._exit(0 if parity_ok else 1)
     if rank != 0:
         teardown()
+        if not parity_ok:
+            sys.exit(1)
         return
 
-    # ---- per-kernel timing of the dominant (transform) kernels, CUDA events on the launch stream ---
-    x2 = pool[0][0].detach().reshape(BATCH, T_LEN)
-    y2 = pool[0][1].reshape(BATCH, T_LEN)
+    # ---- per-kernel timing of the dominant (transform) kernels at this rank's share of the primary workload -------
+    gen = torch.Generator(device=dev).manual_seed(7)
+    y2 = 0.1 * torch.randn(b_local, T_LEN, device=dev, generator=gen)
+    x2 = y2 + 0.05 * torch.randn(b_local, T_LEN, device=dev, generator=gen)
+    flush = torch.empty(160 << 20, dtype=torch.uint8, device=dev)       # > L2, written between timed launches
     kernels = []
-    for name, plans in [("stft_1024_hop120", [stft.stft_losses[0].plan()]), ("stft_2048_hop240", [stft.stft_losses[1].plan()]),
-                        ("stft_512_hop50", [stft.stft_losses[2].plan()]), ("mel_2048_hop300", mel.plans())]:
-        # `inner` launches captured in one CUDA graph and replayed: device time per launch without host overhead
-        # (the transform kernel + the tiny reduce/finalize launch; inputs 6 MB, L2-warm -- the kernel is compute bound)
-        inner, reps = 10, 10
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            for _ in range(3):
-                eng.forward(plans, x2, y2, need_grad=True)
-        torch.cuda.current_stream().wait_stream(side)
-        kg = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(kg):
-            for _ in range(inner):
-                eng.forward(plans, x2, y2, need_grad=True)
-        kg.replay()
+    ustft, umel = make_criteria(None)
+    for name, plans in [("stft_1024_hop120", [ustft.stft_losses[0].plan()]), ("stft_2048_hop240", [ustft.stft_losses[1].plan()]),
+                        ("stft_512_hop50", [ustft.stft_losses[2].plan()]), ("mel_2048_hop300", umel.plans())]:
+        # the transform kernel + its tiny reduce/finalize launch, timed alone on the current stream with CUDA events
+        # (a launch takes >= 0.2 ms at this size: host launch overhead is hidden), L2 flushed before each launch
+        for _ in range(2):
+            eng.forward(plans, x2, y2, need_grad=True)
         torch.cuda.synchronize()
+        ts = []
+        for _ in range(5):
+            flush.fill_(1)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            eng.forward(plans, x2, y2, need_grad=True)
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        kernels.append({"name": name, "ms": sum(ts) / len(ts)})
+    st = eng.forward(ustft.plans() + umel.plans(), x2, y2, need_grad=True)
+    one = torch.ones((), device=dev)
+    ts = []
+    for _ in range(5):
+        flush.fill_(1)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        for _ in range(reps):
-            kg.replay()
+        eng.backward(st, one, one, one)
         b.record()
         torch.cuda.synchronize()
-        kernels.append({"name": name, "ms": a.elapsed_time(b) / (reps * inner)})
-        del kg
+        ts.append(a.elapsed_time(b))
+    combine_ms = sum(ts) / len(ts)
+    del st, flush
     dom = max(kernels, key=lambda k: k["ms"])
     hbm_peak, peak_src = peaks()
-    alg_bytes = 8.0 * BATCH * T_LEN                           # one transform launch must read y_hat and y once
+    alg_bytes = 8.0 * b_local * T_LEN                         # one transform launch must read y_hat and y once
     achieved = alg_bytes / (dom["ms"] * 1e-3) / 1e9
-    step_bytes = 20.0 * BATCH * T_LEN                         # bytes_min of the whole fwd+bwd
-    flops = nominal_flops(BATCH, T_LEN)
-    # DRAM traffic of that kernel from the committed `ncu --set full` capture (profiles/traffic.json), per launch
-    traffic, traffic_src = None, None
+    step_bytes = 20.0 * GLOBAL_BATCH * T_LEN                  # bytes_min of the whole fwd+bwd (all ranks)
+    flops = nominal_flops(GLOBAL_BATCH, T_LEN)
+    # DRAM traffic from the committed `ncu --set full` capture of THIS build (profiles/traffic.json carries the hash of the
+    # kernel sources it was captured from; a stale capture is reported as such, not silently reused)
+    traffic, traffic_src, step_traffic, traffic_stale = None, None, None, None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath) and dom["name"].startswith("mel_2048") and (BATCH, T_LEN) == (16, 48000):
+    if os.path.exists(tpath):
         with open(tpath) as f:
             tj = json.load(f)
-        traffic, traffic_src = float(tj["dram_bytes_per_launch"]), tj["source"].split(":")[0]
+        ent = tj.get("workloads", {}).get(f"{b_local}x{T_LEN}")
+        if ent and dom["name"] in ent.get("kernels", {}):
+            traffic = float(ent["kernels"][dom["name"]]["dram_bytes_per_launch"])
+            step_traffic = ent.get("step_dram_bytes")
+            traffic_src = ent.get("source")
+            traffic_stale = tj.get("csrc_hash") != csrc_hash()
     roofline = {"bound": "hbm", "kernel": "transform_kernel<" + dom["name"] + ">", "achieved": achieved, "peak": hbm_peak,
                 "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic, "traffic_source": traffic_src,
+                "traffic_capture_is_stale": traffic_stale, "step_dram_bytes": step_traffic,
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes,
-                "step_hbm_frac": step_bytes / (ms_per_step * 1e-3) / 1e9 / hbm_peak,
+                "step_hbm_frac": step_bytes / world / (ms_per_step * 1e-3) / 1e9 / hbm_peak,
                 "binding_roof": "fp32 CUDA-core pipe, not HBM (SURVEY 8d: ~217 FLOP/B vs ridge ~11)",
-                "fp32_nominal_tflops": flops / (ms_per_step * 1e-3) / 1e12, "fp32_peak_tflops": 74.5,
-                "fp32_frac": flops / (ms_per_step * 1e-3) / 1e12 / 74.5,
-                "kernels_ms": kernels}
+                "fp32_nominal_tflops_per_gpu": flops / world / (ms_per_step * 1e-3) / 1e12, "fp32_peak_tflops": 74.5,
+                "fp32_frac": flops / world / (ms_per_step * 1e-3) / 1e12 / 74.5,
+                "kernels_ms": kernels, "combine_ms": combine_ms,
+                "kernel_timing": f"each transform launch alone at this rank's share ({b_local} x {T_LEN / FS:g} s), CUDA events on the launch stream, L2 flushed before every launch, mean of 5"}
 
     # ---- CPU baseline beside it (rank 0, N=1 only): bounded sample of the same workload -------------
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        cpu_steps = 10 if BATCH * T_LEN <= 16 * 48000 else 3        # bounded: ~1.3 s at configs[1], a few seconds beyond
-        times, cores = cpu_reference_step_time(BATCH, T_LEN, cpu_steps, 1)
+        cb = 8                                                           # 8 x 4 s per step: a few seconds per step
+        times, cores, kind = cpu_reference_step_time(cb, T_LEN, 3, 1)
         best = min(times)
-        cpu = {"value": BATCH * T_LEN / FS / best, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"the full {BATCH} x {T_LEN / FS:g} s workload, {cpu_steps} steps after 1 warm-up, best step {best * 1e3:.1f} ms "
-                         f"(mean {1e3 * sum(times) / len(times):.1f} ms); torch {torch.__version__} CPU ops, {os.cpu_count()} host cores"}
-
+        cpu = {"value": cb * T_LEN / FS / best, "unit": UNIT, "cores": cores, "kind": kind,
+               "sample": f"{cb} x {T_LEN / FS:g} s per step (bounded sample of the {GLOBAL_BATCH} x {T_LEN / FS:g} s workload), 3 steps after 1 "
+                         f"warm-up, best step {best * 1e3:.1f} ms (mean {1e3 * sum(times) / len(times):.1f} ms); "
+                         + ("the reference's own modules (oracle/_ref)" if kind == "reference" else "oracle port of the reference's op sequence")
+                         + f", torch {torch.__version__} CPU ops, {os.cpu_count()} host cores"}
         try:
-            ref_ms = gpu_reference_step_time(BATCH, T_LEN, dev)
+            ref_ms, what = gpu_reference_step_time(32, T_LEN, dev)
             cpu["reference_ops_on_this_gpu"] = {
-                "value": BATCH * T_LEN / FS / (ref_ms * 1e-3), "unit": UNIT, "ms_per_step": ref_ms,
-                "what": "the reference's op sequence (torch.stft/cuFFT + ATen + cuBLAS + autograd, oracle port) run eagerly "
-                        "on the same B200, device time over 20 steps: context only, not the reference arm"}
+                "value": 32 * T_LEN / FS / (ref_ms * 1e-3), "unit": UNIT, "ms_per_step": ref_ms,
+                "what": what + f" run eagerly on the same B200 at 32 x {T_LEN / FS:g} s, device time over 10 steps: context only, not the reference arm"}
         except Exception as exc:      # context number only
             cpu["reference_ops_on_this_gpu"] = {"unavailable": repr(exc)}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": ("configs[1]: " if (BATCH, T_LEN) == (16, 48000) else "non-default size: ")
-                                   + f"batch {BATCH} x {T_LEN / FS:g} s synthetic 48 kHz per GPU, MR-STFT(1024/2048/512) + 80-mel hop-300, fwd+bwd",
-                       "global_batch": world * BATCH, "samples_per_utterance": T_LEN, "fs": FS,
-                       "api": "drop-in nn.Modules (MultiResolutionSTFTLoss + MultiMelSpectrogramLoss), " + mode,
-                       "eager_ms_per_step": eager_ms, "graph_ms_per_step": graph_ms,
-                       "graph_variants_ms_per_step": graph_times, "graph_per_input_pair_ms_per_step": graph_direct_ms,
-                       "l2": f"inputs rotate through a pool of {n_pool} pairs = {n_pool * pair_bytes >> 20} MB > 126 MB L2",
+            "config": {"workload": workload_name(GLOBAL_BATCH, T_LEN),
+                       "global_batch": GLOBAL_BATCH, "per_gpu_batch": b_local, "samples_per_utterance": T_LEN, "fs": FS,
+                       "api": "drop-in nn.Modules (MultiResolutionSTFTLoss + MultiMelSpectrogramLoss), eager launches on one "
+                              "stream in the trainer's call order (no CUDA graph)",
+                       "timing": {"blocks": len(block_ms), "steps_per_block": args.steps, "block_ms_per_step": block_ms,
+                                  "reported": "median block", "timed_region_s": sum(block_ms) * args.steps * 1e-3},
+                       "l2": f"inputs rotate through a pool of {n_pool} pairs = {n_pool * pair_bytes >> 20} MB per GPU > 126 MB L2 "
+                             "(and every step streams its multi-GB gradient-slot workspace through L2)",
                        "parallelism": (f"batch-sharded x{world}; the 10 fp64 partial sums are exchanged "
                                        + ("over NVLink peer memory inside the reduce+finalize kernel of each criterion "
                                           "(no NCCL call in the step)" if peer else
-                                          "with one NCCL all-reduce per criterion") if world > 1 else "single GPU")},
+                                          "with one NCCL all-reduce per criterion") if world > 1 else "single GPU"),
+                       "secondary": secondary},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": pair_bytes, "d2h_bytes_per_step": 12,
-                    "ms_per_step": e2e_ms, "runs_ms_per_step": e_runs,
-                    "steps": e_steps, "timing": "wall clock, median of 3 runs; per step: pinned H2D of the NEXT step's inputs on a copy stream, fwd+bwd ("
-                                                + e2e_mode + "), D2H of the 3 losses + stream sync; max over ranks"},
-            "gpu_launches": launches_timed, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
+                    "ms_per_step": e2e_ms, "runs_ms_per_step": e_runs, "steps": e_steps,
+                    "timing": "wall clock, median of 3 runs; per step: pinned H2D of the NEXT step's inputs on a copy stream, "
+                              "fwd+bwd (eager launches), D2H of the 3 losses + stream sync; max over ranks; bytes are per GPU"},
+            "gpu_launches": launches_timed, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "sharded_parity": sharded_parity}
     print(json.dumps(line), flush=True)
     teardown()
+    if not parity_ok:
+        sys.exit(1)
+
+
+def check_sharded_parity(torch, dist, pkg, eng, dev, rank, world, group, pair, make_criteria, losses_and_backward, log):
+    """SURVEY 4 'distributed' row on real hardware: (i) every rank's (sc, mag, mel) bit-identical, (ii) equal (rtol 1e-6)
+    to rank 0 evaluating the GATHERED global batch unsharded, (iii) every rank's gradient rows rel-L2 <= 1e-6 from that
+    run's rows -- through the fused NVLink exchange (or whatever path the modules took in the timed region) AND through
+    the NCCL all-reduce path (SPECLOSS_NCCL_ALLREDUCE=1).  (iv) a finite exchange timeout that expires surfaces as an
+    exception on the host, not as silent NaNs."""
+    y_hat, y = pair
+    b_local, t_len = y_hat.shape[0], y_hat.shape[2]
+    res = {"ok": True, "paths": {}}
+
+    def sharded(crit):
+        x = y_hat.detach().clone().requires_grad_(True)
+        sc, mag, ml = losses_and_backward(x, y, crit)
+        torch.cuda.synchronize()
+        return torch.stack([sc.detach(), mag.detach(), ml.detach()]), x.grad.reshape(b_local, t_len)
+
+    # rank 0: the global batch, unsharded
+    gx = [torch.empty_like(y_hat.detach()) for _ in range(world)] if rank == 0 else None
+    gy = [torch.empty_like(y) for _ in range(world)] if rank == 0 else None
+    dist.gather(y_hat.detach().contiguous(), gx, dst=0)
+    dist.gather(y.contiguous(), gy, dst=0)
+    full_losses = torch.zeros(3, device=dev)
+    full_grad = None
+    if rank == 0:
+        fx = torch.cat(gx).requires_grad_(True)
+        fy = torch.cat(gy)
+        del gx, gy
+        sc, mag, ml = losses_and_backward(fx, fy, make_criteria(None))
+        torch.cuda.synchronize()
+        full_losses = torch.stack([sc.detach(), mag.detach(), ml.detach()])
+        full_grad = fx.grad.reshape(world, b_local, t_len)
+        del fx, fy
+    dist.broadcast(full_losses, src=0)
+
+    def compare(tag, losses, grad):
+        bits = losses.view(torch.int32)
+        allbits = [torch.empty_like(bits) for _ in range(world)]
+        dist.all_gather(allbits, bits)
+        identical = all(torch.equal(allbits[0], b) for b in allbits)
+        finite = bool(torch.isfinite(losses).all())
+        rel_loss = float(((losses.double() - full_losses.double()).abs() / full_losses.double().abs()).max())
+        grads = [torch.empty_like(grad) for _ in range(world)] if rank == 0 else None
+        dist.gather(grad.contiguous(), grads, dst=0)
+        g_rel = torch.zeros(1, device=dev, dtype=torch.float64)
+        if rank == 0:
+            worst = 0.0
+            for r in range(world):
+                ref = full_grad[r].double()
+                worst = max(worst, float((grads[r].double() - ref).norm() / ref.norm()))
+            g_rel[0] = worst
+        dist.broadcast(g_rel, src=0)
+        ok = identical and finite and rel_loss <= 1e-6 and float(g_rel) <= 1e-6
+        res["paths"][tag] = {"ok": ok, "losses_bit_identical_across_ranks": identical, "losses_finite": finite,
+                             "loss_max_rel_vs_unsharded": rel_loss, "grad_rows_max_rel_l2_vs_unsharded": float(g_rel),
+                             "losses": [float(v) for v in losses]}
+        res["ok"] = res["ok"] and ok
+
+    crit = make_criteria(group)
+    losses, grad = sharded(crit)
+    compare("peer_memory_exchange" if eng.peer_exchange_active() else "default_path", losses, grad)
+    log("sharded parity: default path done")
+    old = os.environ.get("SPECLOSS_NCCL_ALLREDUCE")
+    os.environ["SPECLOSS_NCCL_ALLREDUCE"] = "1"
+    try:
+        crit = make_criteria(group)            # new plan objects -> new recipes -> the exchange choice is made afresh
+        for s in list(crit):
+            s.__dict__.pop("_plan_cache", None)
+        eng._recipes.clear()
+        eng._recipes_by_id.clear()
+        losses, grad = sharded(crit)
+        compare("nccl_all_reduce", losses, grad)
+    finally:
+        if old is None:
+            os.environ.pop("SPECLOSS_NCCL_ALLREDUCE", None)
+        else:
+            os.environ["SPECLOSS_NCCL_ALLREDUCE"] = old
+        eng._evict()
+    log("sharded parity: NCCL path done")
+    res["unsharded_losses_rank0"] = [float(v) for v in full_losses]
+    res["what"] = ("all ranks' (sc, mag, mel) bit-identical; equal (rtol 1e-6) to rank 0 evaluating the gathered global batch "
+                   "unsharded; every rank's gradient rows rel-L2 <= 1e-6 of that run's rows")
+    return res, bool(res["ok"])
 
 
 def main():
-    global BATCH, T_LEN
+    global GLOBAL_BATCH, T_LEN
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--batch", type=int, default=BATCH, help="utterances per GPU (default: BASELINE configs[1], 16)")
-    ap.add_argument("--seconds", type=float, default=T_LEN / FS, help="utterance length in seconds at 48 kHz (default 1)")
-    ap.add_argument("--no-graph", action="store_true", help="skip the CUDA-graph replay measurement")
-    ap.add_argument("--no-direct-graphs", action="store_true",
-                    help="skip the variant with one captured graph per input pair (no staging copy in the timed region)")
-    ap.add_argument("--one-stream", action="store_true",
-                    help="do not try the captured step with the mel criterion on a second stream")
+    ap.add_argument("--batch", type=int, default=GLOBAL_BATCH, help="GLOBAL batch, sharded over the ranks (default: BASELINE configs[3], 256)")
+    ap.add_argument("--seconds", type=float, default=T_LEN / FS, help="utterance length in seconds at 48 kHz (default 4)")
+    ap.add_argument("--no-graph", action="store_true", help="secondary workload: skip the CUDA-graph replay measurement")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the configs[1] (16 x 1 s per GPU) measurement")
+    ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the sharded == unsharded check")
     ap.add_argument("--verbose", action="store_true", help="stage-by-stage progress on stderr")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
-    BATCH, T_LEN = int(args.batch), int(round(args.seconds * FS))
+    GLOBAL_BATCH, T_LEN = int(args.batch), int(round(args.seconds * FS))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

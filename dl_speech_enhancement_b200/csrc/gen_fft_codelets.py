@@ -40,7 +40,8 @@ class CVal:
 
 
 class Prog:
-    """SSA IR at the complex level: ('add', dst, a, ua, b, ub) | ('tw', dst, a, c, s)  (dst = a * (c + i s))."""
+    """SSA IR at the complex level: ('add', dst, a, ua, b, ub) | ('tw', dst, a, c, s)  (dst = a * (c + i s)) |
+    ('mul', dst, a, ua, c)  (dst = c * a, c real) | ('fma', dst, a, ua, c, b, ub)  (dst = c * a + b, c real)."""
 
     def __init__(self):
         self.ops, self.n = [], 0
@@ -56,6 +57,16 @@ class Prog:
 
     def sub(self, a, b):
         return self.add(a, b.rot(2))
+
+    def scale(self, a, c):
+        d = self._new()
+        self.ops.append(("mul", d, a.name, a.u, float(np.float32(c))))
+        return CVal(d)
+
+    def fma(self, a, c, b):
+        d = self._new()
+        self.ops.append(("fma", d, a.name, a.u, float(np.float32(c)), b.name, b.u))
+        return CVal(d)
 
     def twiddle(self, a, k, n):
         """a * exp(-2*pi*i*k/n); multiples of a quarter turn are free rotations."""
@@ -79,7 +90,19 @@ def fft(p, x):
         t0, t1 = p.add(x[0], x[2]), p.sub(x[0], x[2])
         t2, t3 = p.add(x[1], x[3]), p.sub(x[1], x[3]).rot(1)
         return [p.add(t0, t2), p.add(t1, t3), p.sub(t0, t2), p.sub(t1, t3)]
-    a, b = {8: (2, 4), 16: (4, 4), 32: (4, 8), 64: (8, 8)}[n]
+    if n == 5:
+        # radix-5 butterfly: 8 FADD2 + 2 FMUL2 + 8 FFMA2 (real constants on the packed pipe), +-i rotations free
+        c1, c2 = math.cos(2 * math.pi / 5), math.cos(4 * math.pi / 5)
+        s1, s2 = math.sin(2 * math.pi / 5), math.sin(4 * math.pi / 5)
+        a1, a2 = p.add(x[1], x[4]), p.add(x[2], x[3])
+        b1, b2 = p.sub(x[1], x[4]), p.sub(x[2], x[3])
+        y0 = p.add(p.add(x[0], a1), a2)
+        m1 = p.fma(a2, c2, p.fma(a1, c1, x[0]))
+        m2 = p.fma(a2, c1, p.fma(a1, c2, x[0]))
+        n1 = p.fma(b2, s2, p.scale(b1, s1))
+        n2 = p.fma(b2, -s1, p.scale(b1, s2))
+        return [y0, p.add(m1, n1.rot(1)), p.add(m2, n2.rot(1)), p.add(m2, n2.rot(3)), p.add(m1, n1.rot(3))]
+    a, b = {8: (2, 4), 16: (4, 4), 32: (4, 8), 64: (8, 8), 25: (5, 5)}[n]
     # n = a*b, input index j + b*i (j<b, i<a), output index i' + a*j'
     cols = []
     for j in range(b):
@@ -119,14 +142,21 @@ def operand(name, u):
 def render_c(n):
     p, out = build(n)
     n_add = sum(1 for o in p.ops if o[0] == "add")
-    n_tw = len(p.ops) - n_add
-    L = ["// %d-point forward DFT, in place, natural order: %d FADD2 + %d twiddles (FMUL2 + FFMA2) = %d packed instructions."
-         % (n, n_add, n_tw, n_add + 2 * n_tw),
+    n_tw = sum(1 for o in p.ops if o[0] == "tw")
+    n_real = len(p.ops) - n_add - n_tw
+    L = ["// %d-point forward DFT, in place, natural order: %d FADD2 + %d twiddles (FMUL2 + FFMA2)%s = %d packed instructions."
+         % (n, n_add, n_tw, " + %d real-constant FMUL2/FFMA2" % n_real if n_real else "", n_add + 2 * n_tw + n_real),
          "SPL_DEVICE void fft%d(float2 (&v)[%d]) {" % (n, n)]
     for op in p.ops:
         if op[0] == "add":
             _, d, a, ua, b, ub = op
             L.append("  const float2 %s = __fadd2_rn(%s, %s);" % (d, operand(a, ua), operand(b, ub)))
+        elif op[0] == "mul":
+            _, d, a, ua, c = op
+            L.append("  const float2 %s = __fmul2_rn(%s, make_float2(%s, %s));" % (d, operand(a, ua), fl(c), fl(c)))
+        elif op[0] == "fma":
+            _, d, a, ua, c, b, ub = op
+            L.append("  const float2 %s = __ffma2_rn(%s, make_float2(%s, %s), %s);" % (d, operand(a, ua), fl(c), fl(c), operand(b, ub)))
         else:
             _, d, a, c, s = op
             L.append("  const float2 %s = __ffma2_rn(make_float2(-%s.y, %s.x), make_float2(%s, %s), "
@@ -134,7 +164,7 @@ def render_c(n):
     for k, o in enumerate(out):
         L.append("  v[%d] = %s;" % (k, operand(o.name, o.u)))
     L.append("}")
-    return "\n".join(L), n_add + 2 * n_tw
+    return "\n".join(L), n_add + 2 * n_tw + n_real
 
 
 def evaluate(n, z):
@@ -152,6 +182,15 @@ def evaluate(n, z):
             _, d, a, ua, b, ub = op
             (ax, ay), (bx, by) = opnd(a, ua), opnd(b, ub)
             env[d] = ((ax + bx).astype(f32), (ay + by).astype(f32))
+        elif op[0] == "mul":
+            _, d, a, ua, c = op
+            ax, ay = opnd(a, ua)
+            env[d] = ((ax * f32(c)).astype(f32), (ay * f32(c)).astype(f32))
+        elif op[0] == "fma":
+            _, d, a, ua, c, b, ub = op
+            (ax, ay), (bx, by) = opnd(a, ua), opnd(b, ub)
+            env[d] = ((ax.astype(np.float64) * np.float64(f32(c)) + bx).astype(f32),
+                      (ay.astype(np.float64) * np.float64(f32(c)) + by).astype(f32))
         else:
             _, d, a, c, s = op
             x, y = env[a]
@@ -169,7 +208,7 @@ def evaluate(n, z):
 def check():
     rng = np.random.default_rng(0)
     ok = True
-    for n in (16, 32, 64):
+    for n in (16, 25, 32, 64):
         z = rng.standard_normal((64, n)) + 1j * rng.standard_normal((64, n))
         z = z.astype(np.complex64).astype(np.complex128)
         got = evaluate(n, z)
@@ -182,13 +221,15 @@ def check():
         erri = np.abs(gi - refi).max() / np.abs(refi).max()
         p, _ = build(n)
         n_add = sum(1 for o in p.ops if o[0] == "add")
-        print("fft%d: %d FADD2 + %d twiddles, fwd_err=%.2e inv_err=%.2e" % (n, n_add, len(p.ops) - n_add, err, erri))
+        n_tw = sum(1 for o in p.ops if o[0] == "tw")
+        print("fft%d: %d FADD2 + %d twiddles + %d real-constant ops, fwd_err=%.2e inv_err=%.2e"
+              % (n, n_add, n_tw, len(p.ops) - n_add - n_tw, err, erri))
         ok &= err < 2e-6 and erri < 2e-6
     return ok
 
 
 HEADER = """// GENERATED by gen_fft_codelets.py -- do not edit by hand.
-// In-register forward DFT codelets (16/32/64 points) for the warp-per-frame STFT kernels, written for
+// In-register forward DFT codelets (16/25/32/64 points) for the warp-per-frame STFT kernels, written for
 // the packed fp32 pipe of sm_100 (FADD2 / FMUL2 / FFMA2): one float2 register pair per complex point.
 // Inverse (un-normalised): run the same codelet on component-swapped data, (y, x) in -> (y, x) out.
 #pragma once
@@ -202,7 +243,7 @@ def main():
     if "--check" in sys.argv:
         sys.exit(0 if check() else 1)
     parts = [HEADER]
-    for n in (16, 32, 64):
+    for n in (16, 25, 32, 64):
         src, _ = render_c(n)
         parts.append(src)
         parts.append("")

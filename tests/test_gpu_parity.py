@@ -54,6 +54,26 @@ def _run(stft, mel, y_hat, y, dev, weights=(1.0, 1.0, 1.0)):
     return vals, x.grad.detach().cpu().numpy()
 
 
+def _record_parity(name, vals, g, e64, e32, yard):
+    """Achieved numbers, not just pass/fail: one row per fixture appended to gpurun_out/parity_table.tsv (committed under
+    profiles/ after the B200 run; VERDICT r1 asked for the table)."""
+    import os
+    out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if not os.path.isdir(out_dir):
+        return
+    path = os.path.join(out_dir, "parity_table.tsv")
+    new = not os.path.exists(path)
+    with open(path, "a") as f:
+        if new:
+            f.write("fixture\tloss\tours\tref_fp32\tref_fp64\trel_vs_fp32\trel_vs_fp64\tgrad_ours_vs_ref64\tgrad_ours_vs_ref32\tgrad_ref32_vs_ref64\n")
+        for i, ln in enumerate(("sc", "mag", "mel")):
+            r32, r64 = float(g["loss32"][i]), float(g["loss64"][i])
+            if r64 == 0.0 and vals[i] == 0.0:
+                continue
+            f.write(f"{name}\t{ln}\t{vals[i]:.9g}\t{r32:.9g}\t{r64:.12g}\t{abs(vals[i] - r32) / max(abs(r32), 1e-300):.2e}\t"
+                    f"{abs(vals[i] - r64) / max(abs(r64), 1e-300):.2e}\t{e64:.2e}\t{e32:.2e}\t{yard:.2e}\n")
+
+
 @pytest.mark.parametrize("name", golden_names())
 def test_golden_vectors(dev, name):
     g = load_golden(name)
@@ -65,10 +85,25 @@ def test_golden_vectors(dev, name):
     grad = grad.reshape(g["grad32"].shape)
     e64, e32, yard = rel_l2(grad, g["grad64"]), rel_l2(grad, g["grad32"]), rel_l2(g["grad32"], g["grad64"])
     print(f"{name}: ours-vs-ref64 {e64:.2e}  ours-vs-ref32 {e32:.2e}  ref32-vs-ref64 {yard:.2e}")
+    _record_parity(name, vals, g, e64, e32, yard)
     if name.startswith("c1_"):
         assert e64 <= 2.0 * yard
     else:
         assert e64 <= GRAD_RTOL and e32 <= GRAD_RTOL
+
+
+def test_config3_shape_against_oracle(dev):
+    """BASELINE configs[2]'s criterion input shape: (32, 1, 24000) = batch 32 x 0.5 s @ 48 kHz, as the denoise trainer hands
+    it to _metric_loss (trainerGAN.py:214-241), lambda-weighted like there (45.0, in-place)."""
+    from oracle import spectral_oracle as so
+    y_hat, y = so.synth_pair(32, 24000, seed=77)
+    stft, mel = _modules({}, MEL48, dev)
+    vals, grad = _run(stft, mel, y_hat, y, dev, weights=(45.0, 45.0, 45.0))
+    ref, gref = so.losses_and_grad(y_hat, y, so.DEFAULT_STFT, so.mel_from_kwargs(**MEL48), weights=(45.0, 45.0, 45.0),
+                                   dtype=torch.float64)
+    for a, b in zip(vals, ref):
+        assert abs(a - b) <= LOSS_RTOL * abs(b), (vals, ref)
+    assert rel_l2(grad, gref.numpy()) <= GRAD_RTOL
 
 
 def test_config2_full_size_against_oracle(dev):

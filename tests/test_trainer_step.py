@@ -64,8 +64,17 @@ def test_trainer_step_losses_track_reference_criteria(use_stft):
             rel = abs(a[k] - b[k]) / abs(a[k])
             worst = max(worst, rel)
             assert rel <= TRACK_RTOL, (step, k, a[k], b[k], rel)
-    print(f"trainer step ({'mel+stft' if use_stft else 'mel'}): worst relative loss deviation over 4 steps {worst:.2e}")
-    # the weights the two runs end with stay together too (Adam, lr 1e-4, 4 steps)
+    # step 0 runs on identical weights: there the criteria alone are compared (fp32 evaluation noise only)
+    for k in keys:
+        assert abs(rows_ref[0][k] - rows_our[0][k]) <= 1e-5 * abs(rows_ref[0][k]), (k, rows_ref[0][k], rows_our[0][k])
+    # The weights the two runs end with: Adam divides by sqrt(v), so parameters whose gradient is at the fp32 noise level
+    # (biases of the strided convolutions) take near-random +-lr steps in ANY two fp32 evaluations; the bound is therefore
+    # on the scale of the weight movement itself (4 steps x lr 1e-4 on weights of magnitude ~5e-2), not on rounding.
     pa = torch.cat([p.detach().flatten() for p in tr_ref.model["generator"].encoder.parameters()])
     pb = torch.cat([p.detach().flatten() for p in tr_our.model["generator"].encoder.parameters()])
-    assert float((pa - pb).norm() / pa.norm()) <= 1e-4
+    p0 = torch.cat([init[k].flatten() for k, _ in tr_ref.model["generator"].encoder.named_parameters(prefix="encoder")]).to(dev)
+    moved = float((pa - p0).norm() / p0.norm())
+    apart = float((pa - pb).norm() / pa.norm())
+    print(f"trainer step ({'mel+stft' if use_stft else 'mel'}): worst relative loss deviation over 4 steps {worst:.2e}; "
+          f"encoder weights moved {moved:.2e} (relative), runs ended {apart:.2e} apart")
+    assert apart <= 0.1 * moved, (apart, moved)
