@@ -15,7 +15,7 @@ from ctypes import POINTER, c_char_p, c_float, c_int32, c_int64, c_void_p
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libspecloss.so")
 CSRC = os.path.join(_HERE, "csrc")
-ABI_VERSION = 12
+ABI_VERSION = 13
 
 SPL_KIND_STFT = 0
 SPL_KIND_MEL = 1
@@ -49,7 +49,8 @@ class SplGeometry(ctypes.Structure):
 EXPORTS = ("spl_abi_version", "spl_last_error", "spl_fill_twiddle", "spl_geometry_of", "spl_forward",
            "spl_reduce", "spl_finalize", "spl_reduce_finalize", "spl_exchange_buffer_bytes", "spl_reduce_exchange_finalize", "spl_backward", "spl_spectrogram", "spl_spectrogram_backward", "spl_mel_project",
            "spl_shape_geometry", "spl_shape_forward", "spl_shape_finalize", "spl_shape_backward",
-           "spl_mag_loss_geometry", "spl_mag_loss_forward", "spl_mag_loss_backward")
+           "spl_mag_loss_geometry", "spl_mag_loss_forward", "spl_mag_loss_backward",
+           "spl_melpow_geometry", "spl_melpow_l1")
 
 
 class SpecLossError(RuntimeError):
@@ -111,6 +112,11 @@ def bind(lib: ctypes.CDLL) -> ctypes.CDLL:
     lib.spl_mag_loss_backward.restype = c_int32
     lib.spl_mag_loss_backward.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                           c_void_p]
+    lib.spl_melpow_geometry.restype = c_int32
+    lib.spl_melpow_geometry.argtypes = [c_int32, c_int32, c_int32, c_int32, POINTER(c_int64)]
+    lib.spl_melpow_l1.restype = c_int32
+    lib.spl_melpow_l1.argtypes = [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_int32, c_int32,
+                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     ver = lib.spl_abi_version()
     if ver != ABI_VERSION:
         raise SpecLossError(f"libspecloss ABI version {ver}, expected {ABI_VERSION}")
@@ -133,7 +139,7 @@ def build_library(verbose: bool = False) -> str:
     if not os.path.exists(nvcc):
         raise SpecLossError("nvcc not found; libspecloss.so cannot be built")
     srcs = [os.path.join(CSRC, f) for f in ("specloss.cu", "specloss_kernels.cuh", "specloss_host.inl",
-                                            "fft_codelets.cuh", "melgemm.cuh")]
+                                            "fft_codelets.cuh", "melgemm.cuh", "melpower.cuh")]
     hdr = os.path.join(os.path.dirname(_HERE), "include", "specloss.h")
     newest = max(os.path.getmtime(p) for p in srcs + [hdr])
     if os.path.exists(LIB_PATH) and os.path.getmtime(LIB_PATH) >= newest:

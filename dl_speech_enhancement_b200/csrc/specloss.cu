@@ -3,6 +3,7 @@
 #include "../../include/specloss.h"
 #include "specloss_kernels.cuh"
 #include "melgemm.cuh"
+#include "melpower.cuh"
 
 #include <cmath>
 #include <cstdarg>
@@ -277,6 +278,16 @@ int spl_launch_shape_backward(const spl::ShapeParams& p, int grid, int wpc, void
 
 int spl_launch_shape_finalize(const spl::ShapeFinalizeParams& fp, void* stream) {
   spl::shape_finalize_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(fp);
+  SPL_CUDA(cudaGetLastError());
+  return SPL_OK;
+}
+
+int spl_launch_melpow(const spl::MelPowParams& p, int grid, int wpc, size_t smem, void* stream) {
+  if (smem > kMaxSmem) return fail(SPL_E_INVALID, "power-mel metric: %zu B of shared memory exceed 227 KB", smem);
+  static thread_local bool configured[64] = {false};
+  int rc = opt_in_smem(spl::melpow_kernel, configured);
+  if (rc) return rc;
+  spl::melpow_kernel<<<grid, wpc * 32, smem, static_cast<cudaStream_t>(stream)>>>(p);
   SPL_CUDA(cudaGetLastError());
   return SPL_OK;
 }

@@ -24,6 +24,7 @@
 //   int spl_launch_shape_forward(const spl::ShapeParams&, int grid, int wpc, void* stream);
 //   int spl_launch_shape_backward(const spl::ShapeParams&, int grid, int wpc, void* stream);
 //   int spl_launch_shape_finalize(const spl::ShapeFinalizeParams&, void* stream);
+//   int spl_launch_melpow(const spl::MelPowParams&, int grid, int wpc, size_t smem, void* stream);   -- grid/wpc from spl_shape_dims
 namespace {
 
 constexpr long long kMaxPartialRows = 1024 * 32;      // upper bound on grid * warps per CTA on any device
@@ -583,6 +584,61 @@ int32_t spl_mag_loss_backward(const float* x_mag, const float* y_mag, int64_t n,
   p.x = x_mag; p.y = y_mag; p.n = n; p.sums = sums; p.g_sc = g_sc; p.g_mag = g_mag; p.gx = gx; p.gy = gy;
   p.vec = (((uintptr_t)x_mag | (uintptr_t)y_mag | (uintptr_t)gx | (uintptr_t)gy) & 15) == 0;
   return spl_launch_mag_backward(p, stream);
+}
+
+// ---- power-mel L1 metric, n_fft = 400 (mel_spectrogram.py:36-44) -----------------------------------------------------
+static int melpow_check(int rows, int T, int n_fft, int hop) {
+  if (n_fft != spl::kMp) return fail(SPL_E_INVALID, "power-mel metric: n_fft %d is not %d (torchaudio MelSpectrogram default)", n_fft, spl::kMp);
+  if (rows < 1) return fail(SPL_E_INVALID, "rows %d < 1", rows);
+  if (hop < 1) return fail(SPL_E_INVALID, "hop %d < 1", hop);
+  if (T <= n_fft / 2) return fail(SPL_E_INVALID, "reflect padding needs T > n_fft/2 (T=%d, n_fft=%d)", T, n_fft);
+  if ((long long)rows * (1 + T / hop) > 0x7fffffffLL) return fail(SPL_E_INVALID, "rows * frames exceeds 2^31");
+  return SPL_OK;
+}
+
+int32_t spl_melpow_geometry(int32_t rows, int32_t T, int32_t n_fft, int32_t hop, int64_t* partial_count) {
+  if (!partial_count) return fail(SPL_E_INVALID, "spl_melpow_geometry: null output");
+  int rc = melpow_check(rows, T, n_fft, hop);
+  if (rc) return rc;
+  int grid = 0, wpc = 0;
+  rc = spl_shape_dims((long long)rows * (1 + T / hop), &grid, &wpc);
+  if (rc) return rc;
+  *partial_count = (int64_t)grid * wpc;
+  return SPL_OK;
+}
+
+int32_t spl_melpow_l1(const float* x, const float* y, int32_t rows, int32_t T, int32_t n_fft, int32_t hop,
+                      const float* window, const float* twiddle, int32_t n_mels, int32_t nnz,
+                      const int32_t* mel_ptr, const int32_t* mel_ent, double* partials, double* sum, float* loss,
+                      float* mel_x, float* mel_y, void* stream) {
+  int rc = melpow_check(rows, T, n_fft, hop);
+  if (rc) return rc;
+  if (!x || !y || !window || !twiddle || !mel_ptr || !mel_ent || !partials || !sum || !loss)
+    return fail(SPL_E_INVALID, "spl_melpow_l1: null pointer");
+  if (n_mels < 1 || n_mels > spl::kMpMaxMels) return fail(SPL_E_INVALID, "n_mels %d must be in [1, %d]", n_mels, spl::kMpMaxMels);
+  if (nnz < 1 || nnz > spl::kMpMaxNnz) return fail(SPL_E_INVALID, "filterbank non-zeros %d must be in [1, %d]", nnz, spl::kMpMaxNnz);
+  const int n_frames = 1 + T / hop;
+  int grid = 0, wpc = 0;
+  rc = spl_shape_dims((long long)rows * n_frames, &grid, &wpc);
+  if (rc) return rc;
+  spl::MelPowParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.x = x; p.y = y; p.rows = rows; p.T = T; p.hop = hop; p.n_frames = n_frames;
+  p.window = window; p.twiddle = reinterpret_cast<const float2*>(twiddle);
+  p.n_mels = n_mels; p.nnz = nnz; p.mel_ptr = mel_ptr; p.mel_ent = reinterpret_cast<const int2*>(mel_ent);
+  p.partials = partials; p.mel_x = mel_x; p.mel_y = mel_y;
+  const spl::MelPowSmem sm = spl::melpow_smem(n_mels, nnz);
+  rc = spl_launch_melpow(p, grid, wpc, ((size_t)sm.total + (size_t)sm.per_warp * wpc) * 4, stream);
+  if (rc) return rc;
+  spl::ReduceParams rp;
+  std::memset(&rp, 0, sizeof(rp));
+  rp.n_sums = 1; rp.base[0] = partials; rp.stride[0] = 1; rp.count[0] = grid * wpc; rp.out = sum;
+  rc = spl_launch_reduce(rp, stream);
+  if (rc) return rc;
+  spl::ShapeFinalizeParams fp;                       // loss = sum / count: the one-term case of the shape-loss finalize
+  std::memset(&fp, 0, sizeof(fp));
+  fp.n = 1; fp.count[0] = (double)rows * n_mels * n_frames; fp.sums = sum; fp.loss = loss;
+  return spl_launch_shape_finalize(fp, stream);
 }
 
 }  // extern "C"

@@ -207,6 +207,28 @@ class TransformPlan:
             raise RuntimeError("window buffer must be float32 with win_length taps (fp32-only implementation)")
 
 
+def melpow_twiddle_table() -> torch.Tensor:
+    """W_400^(n1*k2) for the 25 x 16 transform of the power-mel metric: fp32 roundings of fp64, layout [k2 < 16][n1 < 25]."""
+    e = (np.arange(16)[:, None] * np.arange(25)[None, :]) % 400
+    th = 2.0 * np.pi * e.astype(np.float64) / 400
+    tab = np.stack([np.cos(th), -np.sin(th)], axis=-1).astype(np.float32)
+    return torch.from_numpy(tab.reshape(-1).copy())
+
+
+def melpow_csr(fb: np.ndarray):
+    """(n_freqs, n_mels) filterbank -> CSR by mel row: (ptr int32 [n_mels + 1], entries int32 [nnz][2] = {bin, weight bits})."""
+    n_freqs, n_mels = fb.shape
+    ptr, ent = [0], []
+    for m in range(n_mels):
+        for k in np.flatnonzero(fb[:, m]):
+            ent.append((int(k), int(np.float32(fb[k, m]).view(np.int32))))
+        ptr.append(len(ent))
+    if not ent:
+        raise RuntimeError("the mel filterbank is all zeros")
+    return (torch.from_numpy(np.asarray(ptr, dtype=np.int32)),
+            torch.from_numpy(np.asarray(ent, dtype=np.int32).reshape(-1).copy()))
+
+
 def gemm_ld(n_fft: int) -> int:
     """Row pitch (floats) of the amplitude operand of the mel GEMM: n_fft/2+1 bins padded to whole 32-float k-blocks."""
     return ((n_fft // 2 + 1) + 31) // 32 * 32
@@ -622,6 +644,29 @@ class Engine:
                                                          dx.data_ptr(), self._stream(dx)))
         self.launches += 1
         return dx
+
+    # -- power-mel L1 metric (Mel_L1 of the reference's evaluation scripts) ------------------------------------
+    @_on_tensor_device(0)
+    def melpow_l1(self, x: torch.Tensor, y: torch.Tensor, n_fft: int, hop: int, window: torch.Tensor, twiddle: torch.Tensor,
+                  n_mels: int, mel_ptr: torch.Tensor, mel_ent: torch.Tensor, want_mels: bool = False):
+        """x, y: (rows, T) fp32 contiguous -> (loss 0-dim, mel_x, mel_y): nn.L1Loss()(M(x), M(y)) with M the power-mel
+        spectrogram (mel_spectrogram.py:36-44); mel_x / mel_y (rows, n_mels, 1 + T // hop) only when want_mels."""
+        rows, t_len = x.shape
+        dev = x.device
+        n_part = ctypes.c_int64()
+        _abi.check(self.lib, self.lib.spl_melpow_geometry(rows, t_len, n_fft, hop, ctypes.byref(n_part)))
+        partials = torch.empty(n_part.value, dtype=torch.float64, device=dev)
+        total = torch.empty(1, dtype=torch.float64, device=dev)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        frames = 1 + t_len // hop
+        mel_x = torch.empty(rows, n_mels, frames, dtype=torch.float32, device=dev) if want_mels else None
+        mel_y = torch.empty(rows, n_mels, frames, dtype=torch.float32, device=dev) if want_mels else None
+        _abi.check(self.lib, self.lib.spl_melpow_l1(
+            x.data_ptr(), y.data_ptr(), rows, t_len, n_fft, hop, window.data_ptr(), twiddle.data_ptr(), n_mels,
+            mel_ent.numel() // 2, mel_ptr.data_ptr(), mel_ent.data_ptr(), partials.data_ptr(), total.data_ptr(),
+            loss.data_ptr(), _ptr(mel_x), _ptr(mel_y), self._stream(x)))
+        self.launches += 3
+        return loss, mel_x, mel_y
 
     # -- losses on explicit magnitude tensors ----------------------------------------------------
     @_on_tensor_device(0)

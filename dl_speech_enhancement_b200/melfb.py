@@ -41,3 +41,29 @@ def mel_filterbank(sr: float, n_fft: int, n_mels: int = 128, fmin: float = 0.0, 
     tri = np.clip(np.minimum(up, down), 0.0, None)
     tri *= (2.0 / (corners[2:] - corners[:-2]))[:, None]
     return tri.astype(np.float32)
+
+
+def htk_mel_filterbank(sample_rate: int, n_fft: int, n_mels: int = 128, f_min: float = 0.0, f_max=None):
+    """(n_fft // 2 + 1, n_mels) fp32 triangular filterbank of torchaudio.transforms.MelSpectrogram's defaults
+    (mel_scale="htk", norm=None) -- the bank behind the reference's `Mel_L1` metric (mel_spectrogram.py:36-44).
+    torchaudio (third party, pinned 2.1.1 in the reference's requirements.txt) computes it in FP32 with torch ops:
+        all_freqs = linspace(0, sr // 2, n_freqs);  m = linspace(hz2mel(f_min), hz2mel(f_max), n_mels + 2)
+        f = 700 (10^(m / 2595) - 1);  fb = max(0, min(-(f[:-2] - all_freqs) / (f[1:-1] - f[:-2]), (f[2:] - all_freqs) / (f[2:] - f[1:-1])))
+    The same op sequence on fp32 torch tensors is restated here so that the weights agree with torchaudio's bit for bit
+    (an fp64 evaluation differs from it by ~1e-5 relative: f ~ 1e4 Hz carries 1e-3 Hz of fp32 rounding)."""
+    import math
+
+    import torch
+
+    f_max = float(sample_rate // 2) if f_max is None else float(f_max)
+    n_freqs = n_fft // 2 + 1
+    all_freqs = torch.linspace(0, sample_rate // 2, n_freqs)
+    m_min = 2595.0 * math.log10(1.0 + (float(f_min) / 700.0))
+    m_max = 2595.0 * math.log10(1.0 + (f_max / 700.0))
+    m_pts = torch.linspace(m_min, m_max, n_mels + 2)
+    f_pts = 700.0 * (10.0 ** (m_pts / 2595.0) - 1.0)
+    f_diff = f_pts[1:] - f_pts[:-1]
+    slopes = f_pts.unsqueeze(0) - all_freqs.unsqueeze(1)
+    down = (-1.0 * slopes[:, :-2]) / f_diff[:-1]
+    up = slopes[:, 2:] / f_diff[1:]
+    return torch.max(torch.zeros(1), torch.min(down, up)).numpy()

@@ -20,7 +20,7 @@ import torch
 
 from . import melfb
 from ._abi import SPL_KIND_MEL, SPL_KIND_STFT
-from .engine import TransformPlan, fft_geometry, mel_gemm_weights, mel_tables, twiddle_table
+from .engine import TransformPlan, cuda_engine, fft_geometry, mel_gemm_weights, mel_tables, melpow_csr, melpow_twiddle_table, twiddle_table
 from .functional import log_mel_spectrogram, magnitude_loss, shape_loss, spectral_losses
 from .functional import spectrogram as _spectrogram_fn
 
@@ -278,3 +278,69 @@ class MultiWindowShapeLoss(torch.nn.Module):
 
     def forward(self, y_hat, y):
         return shape_loss(y_hat, y, [m.winlen for m in self.shape_losses], group=self.process_group)
+
+
+class MelL1(torch.nn.Module):
+    """The reference's `Mel_L1` evaluation metric (mel_spectrogram.py:36-44, duplicated at sandbox.py:183-191):
+        nn.L1Loss()(M(pred), M(target)),  M = torchaudio.transforms.MelSpectrogram(sample_rate)
+    with torchaudio's defaults: n_fft = win_length = 400 (periodic Hann), hop 200, reflect-centred, power 2, 128 HTK mel
+    filters, no normalisation, no log.  Same constructor arguments as torchaudio.transforms.MelSpectrogram for the subset
+    the metric uses; anything else raises.  Forward only (it is a printed metric, mel_spectrogram.py:47-64): the result
+    carries no autograd graph.  Runs on the sm_100a power-mel kernel (csrc/melpower.cuh, a 25 x 16 = 400-point transform)."""
+
+    def __init__(self, sample_rate=16000, n_fft=400, win_length=None, hop_length=None, f_min=0.0, f_max=None, pad=0,
+                 n_mels=128, window_fn=torch.hann_window, power=2.0, normalized=False, center=True, pad_mode="reflect",
+                 norm=None, mel_scale="htk"):
+        super().__init__()
+        win_length = n_fft if win_length is None else win_length
+        if n_fft != 400 or win_length != n_fft:
+            raise NotImplementedError("MelL1: the power-mel kernel implements torchaudio's default n_fft = win_length = 400")
+        if pad != 0 or power != 2.0 or normalized or not center or pad_mode != "reflect" or norm is not None or mel_scale != "htk":
+            raise NotImplementedError("MelL1: only torchaudio.transforms.MelSpectrogram's defaults (pad=0, power=2, "
+                                      "normalized=False, center=True, reflect, norm=None, mel_scale='htk') are implemented")
+        self.sample_rate, self.n_fft, self.win_length = sample_rate, n_fft, win_length
+        self.hop_length = win_length // 2 if hop_length is None else hop_length
+        self.n_mels = n_mels
+        fb = melfb.htk_mel_filterbank(sample_rate, n_fft, n_mels, f_min, f_max)
+        self.register_buffer("window", window_fn(win_length))
+        self.register_buffer("fb", torch.from_numpy(fb.copy()))
+        self.register_buffer("_twiddle", melpow_twiddle_table(), persistent=False)
+        ptr, ent = melpow_csr(fb)
+        self.register_buffer("_mel_ptr", ptr, persistent=False)
+        self.register_buffer("_mel_ent", ent, persistent=False)
+
+    def _run(self, pred, target, want_mels):
+        if pred.shape != target.shape:
+            raise RuntimeError(f"shape mismatch: {tuple(pred.shape)} vs {tuple(target.shape)}")
+        x = _explicit_input(pred.detach(), "MelL1")
+        y = _explicit_input(target.detach(), "MelL1")
+        if x.device != y.device or x.device != self.window.device:
+            raise RuntimeError("MelL1: inputs and module buffers must be on the same CUDA device (call .to(device))")
+        lead = x.shape[:-1]
+        x, y = x.reshape(-1, x.shape[-1]), y.reshape(-1, y.shape[-1])
+        loss, mx, my = cuda_engine().melpow_l1(x, y, self.n_fft, self.hop_length, self.window, self._twiddle, self.n_mels,
+                                               self._mel_ptr, self._mel_ent, want_mels)
+        if want_mels:
+            mx, my = mx.reshape(lead + mx.shape[1:]), my.reshape(lead + my.shape[1:])
+        return loss, mx, my
+
+    def forward(self, pred, target):
+        """pred, target: (..., T) fp32 CUDA -> 0-dim L1 between their power-mel spectrograms."""
+        return self._run(pred, target, False)[0]
+
+    def mel_spectrograms(self, pred, target):
+        """(M(pred), M(target)), each (..., n_mels, 1 + T // hop): the tensors the metric compares."""
+        return self._run(pred, target, True)[1:]
+
+
+_MEL_L1 = {}
+
+
+def Mel_L1(pred, target, sample_rate=48000):
+    """Drop-in for the reference's module-level `Mel_L1(pred, target)` (mel_spectrogram.py:36-44:
+    `mel_spectrogram = transforms.MelSpectrogram(48000)` at import time, then L1 of the two outputs)."""
+    key = (sample_rate, str(pred.device))
+    crit = _MEL_L1.get(key)
+    if crit is None:
+        crit = _MEL_L1[key] = MelL1(sample_rate).to(pred.device)
+    return crit(pred, target)

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SPL_ABI_VERSION 12
+#define SPL_ABI_VERSION 13
 
 #define SPL_OK 0
 #define SPL_E_INVALID (-1)   /* bad argument / outside the supported envelope */
@@ -194,6 +194,22 @@ int32_t spl_mag_loss_forward(const float* x_mag, const float* y_mag, int64_t n, 
  * (NULL = 0). */
 int32_t spl_mag_loss_backward(const float* x_mag, const float* y_mag, int64_t n, const double* sums,
                               const float* g_sc, const float* g_mag, float* gx, float* gy, void* stream);
+
+/* Power-mel L1 evaluation metric `Mel_L1(pred, target)` (mel_spectrogram.py:36-44, sandbox.py:183-191):
+ * nn.L1Loss()(M(pred), M(target)) with M = torchaudio.transforms.MelSpectrogram(48000), i.e. n_fft = win = 400 (periodic
+ * Hann), hop 200, reflect-centred, |STFT|^2, 128 HTK mel filters without normalisation, no log.  Forward only.
+ *   x, y      : device (rows, T)
+ *   n_fft     : must be 400 (= 25 x 16: the transform of this kernel); hop any >= 1
+ *   window    : device, 400 taps;  twiddle: device, 800 floats: W_400^(n1*k2) = exp(-2 pi i n1 k2 / 400) at [k2*25 + n1], k2 < 16, n1 < 25
+ *   mel_ptr / mel_ent : device CSR of the (n_mels x 201) filterbank: row m owns entries [mel_ptr[m], mel_ptr[m+1]) of
+ *               mel_ent = {bin, bits of the weight} pairs (nnz of them)
+ *   partials  : device doubles, spl_melpow_geometry() of them;  sum: device double[1];  loss: device float[1]
+ *   mel_x / mel_y : NULL, or device (rows, n_mels, 1 + T/hop) outputs M(pred) / M(target) */
+int32_t spl_melpow_geometry(int32_t rows, int32_t T, int32_t n_fft, int32_t hop, int64_t* partial_count);
+int32_t spl_melpow_l1(const float* x, const float* y, int32_t rows, int32_t T, int32_t n_fft, int32_t hop,
+                      const float* window, const float* twiddle, int32_t n_mels, int32_t nnz,
+                      const int32_t* mel_ptr, const int32_t* mel_ent, double* partials, double* sum, float* loss,
+                      float* mel_x, float* mel_y, void* stream);
 
 #ifdef __cplusplus
 }

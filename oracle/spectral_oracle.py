@@ -380,3 +380,41 @@ def shape_loss_and_grad(y_hat, y, winlens: Sequence[int], dtype=np.float64):
         r = np.repeat(np.arange(rows)[:, None], n, axis=1)
         np.add.at(grad, (r, idx), np.sign(px - py) * np.sign(x[r, idx]) / (rows * n * len(winlens)))
     return float(loss), grad.reshape(shape)
+
+
+# --------------------------------------------------------------------------------------
+# Mel_L1 evaluation metric: mel_spectrogram.py:36-44 (duplicate: sandbox.py:183-191)
+#   mel_spectrogram = torchaudio.transforms.MelSpectrogram(48000);  Mel_L1 = nn.L1Loss()(mel(pred), mel(target))
+# The arithmetic lives in torchaudio (third party; requirements.txt pins torchaudio==2.1.1, the container has 2.11):
+# transforms.MelSpectrogram defaults = Spectrogram(n_fft 400, win 400 periodic Hann, hop 200, pad 0, power 2,
+# normalized False, center True, reflect) -> MelScale(128 mels, f_min 0, f_max sr/2, norm None, mel_scale "htk").
+# Pinned by tests/golden/mel_l1_*.npz, produced by torchaudio itself (tests/golden/make_golden_mel_l1.py).
+# --------------------------------------------------------------------------------------
+def htk_fbanks(sample_rate: int, n_fft: int = 400, n_mels: int = 128, f_min: float = 0.0, f_max=None) -> torch.Tensor:
+    """torchaudio.functional.melscale_fbanks(n_fft // 2 + 1, f_min, f_max, n_mels, sample_rate, norm=None, mel_scale="htk"):
+    fp32 throughout, as torchaudio computes it; (n_freqs, n_mels)."""
+    import math
+
+    f_max = float(sample_rate // 2) if f_max is None else float(f_max)
+    all_freqs = torch.linspace(0, sample_rate // 2, n_fft // 2 + 1)
+    m_pts = torch.linspace(2595.0 * math.log10(1.0 + f_min / 700.0), 2595.0 * math.log10(1.0 + f_max / 700.0), n_mels + 2)
+    f_pts = 700.0 * (10.0 ** (m_pts / 2595.0) - 1.0)
+    f_diff = f_pts[1:] - f_pts[:-1]
+    slopes = f_pts.unsqueeze(0) - all_freqs.unsqueeze(1)
+    return torch.max(torch.zeros(1), torch.min((-1.0 * slopes[:, :-2]) / f_diff[:-1], slopes[:, 2:] / f_diff[1:]))
+
+
+def power_mel(x: torch.Tensor, sample_rate: int = 48000, n_fft: int = 400, hop: int = 200, n_mels: int = 128) -> torch.Tensor:
+    """MelSpectrogram(sample_rate)(x): (..., T) -> (..., n_mels, 1 + T // hop), in x's dtype (the fp32 filterbank and window
+    are cast, which is what module.double() does to torchaudio's buffers)."""
+    lead = x.shape[:-1]
+    x2 = x.reshape(-1, x.shape[-1])
+    spec = torch.fft.rfft(frames(x2, n_fft, hop, n_fft, "hann_window"), dim=-1)          # (B, F, K)
+    power = spec.real ** 2 + spec.imag ** 2
+    mel = torch.matmul(power, htk_fbanks(sample_rate, n_fft, n_mels).to(device=x.device, dtype=x.dtype))     # (B, F, n_mels)
+    return mel.transpose(1, 2).reshape(lead + (n_mels, mel.shape[1]))
+
+
+def mel_l1(pred: torch.Tensor, target: torch.Tensor, sample_rate: int = 48000) -> torch.Tensor:
+    """Mel_L1(pred, target) = mean |MelSpectrogram(pred) - MelSpectrogram(target)|."""
+    return (power_mel(pred, sample_rate) - power_mel(target, sample_rate)).abs().mean()

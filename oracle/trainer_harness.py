@@ -93,5 +93,65 @@ def time_steps(trainer, batches, warmup=3):
     return 1e3 * (time.perf_counter() - t0) / max(1, len(batches) - warmup)
 
 
+class PortMel(torch.nn.Module):
+    """The oracle's restatement of MultiMelSpectrogramLoss on the explicit-rFFT route (oracle/spectral_oracle.py): a second,
+    independently rounded fp32 implementation of the reference's math -- the CONTROL for free-running trainer comparisons."""
+
+    def __init__(self, **kw):
+        super().__init__()
+        from oracle import spectral_oracle as so
+        self.res = so.mel_from_kwargs(**kw)
+
+    def forward(self, y_hat, y):
+        from oracle import spectral_oracle as so
+        return so.multi_mel_loss(y_hat, y, self.res, use_torch_stft=False)
+
+
+class PortStft(torch.nn.Module):
+    def __init__(self, **kw):
+        super().__init__()
+        from oracle import spectral_oracle as so
+        self.res = so.stft_from_kwargs(**kw)
+
+    def forward(self, x, y):
+        from oracle import spectral_oracle as so
+        return so.mr_stft_loss(x, y, self.res, use_torch_stft=False)
+
+
+class InDouble(torch.nn.Module):
+    """A criterion evaluated in fp64 on fp32 tensors (inputs upcast, losses and hence gradients rounded back to fp32 once):
+    the 'as exact as fp32 storage allows' run that two fp32 implementations are both measured against."""
+
+    def __init__(self, inner):
+        super().__init__()
+        self.inner = inner.double()
+
+    def forward(self, pred, target):
+        out = self.inner(pred.double(), target.double())
+        return tuple(o.float() for o in out) if isinstance(out, tuple) else out.float()
+
+
+def in_double(cls):
+    """Class-like factory for build_trainer(): cls(**kw) wrapped in InDouble."""
+    return lambda **kw: InDouble(cls(**kw))
+
+
+class Tee(torch.nn.Module):
+    """Wraps a criterion of the running trainer: forwards to it unchanged (its losses drive the optimiser) and records, per
+    call, the (prediction, target) pair it was given and -- through a tensor hook -- the gradient autograd delivers to the
+    prediction after backward.  Lets a second implementation be evaluated on EXACTLY the tensors the trainer produced."""
+
+    def __init__(self, inner, log, hook):
+        super().__init__()
+        self.inner, self.log, self.hook = inner, log, hook
+
+    def forward(self, pred, target):
+        if self.hook and pred.requires_grad:
+            rec = {"pred": pred.detach().clone(), "target": target.detach().clone()}
+            pred.register_hook(lambda g, rec=rec: rec.__setitem__("grad", g.detach().clone()))
+            self.log.append(rec)
+        return self.inner(pred, target)
+
+
 def load():
     return ref_loader.load_reference_trainer()

@@ -23,7 +23,20 @@ def _all_golden():
 
 def golden_names():
     """Spectral-loss fixtures (tests/golden/make_golden.py)."""
-    return [n for n in _all_golden() if not n.startswith("shape_")]
+    return [n for n in _all_golden() if not n.startswith(("shape_", "mel_l1_"))]
+
+
+def mel_l1_golden_names():
+    """Mel_L1 fixtures, produced by torchaudio (tests/golden/make_golden_mel_l1.py)."""
+    return [n for n in _all_golden() if n.startswith("mel_l1_")]
+
+
+def load_mel_l1_golden(name):
+    import torch
+
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    return dict(pred=torch.from_numpy(z["pred"]), target=torch.from_numpy(z["target"]), loss32=float(z["loss32"]),
+                loss64=float(z["loss64"]), mel_pred64=z["mel_pred64"], mel_target64=z["mel_target64"])
 
 
 def shape_golden_names():
@@ -81,7 +94,7 @@ def emu_engine():
     so_path = os.path.join(EMU_DIR, "libspecloss_emu.so")
     srcs = [os.path.join(EMU_DIR, "specloss_emu.cpp"), os.path.join(EMU_DIR, "cuda_emu.h"),
             os.path.join(ROOT, "include", "specloss.h")] + \
-        [os.path.join(_abi.CSRC, f) for f in ("specloss_kernels.cuh", "specloss_host.inl", "fft_codelets.cuh")]
+        [os.path.join(_abi.CSRC, f) for f in ("specloss_kernels.cuh", "specloss_host.inl", "fft_codelets.cuh", "melpower.cuh")]
     if not os.path.exists(so_path) or os.path.getmtime(so_path) < max(os.path.getmtime(s) for s in srcs):
         cmd = ["g++", "-std=c++20", "-O1", "-fPIC", "-shared", "-pthread", "-I" + EMU_DIR, "-o", so_path, srcs[0]]
         res = subprocess.run(cmd, capture_output=True, text=True)

@@ -5,6 +5,7 @@
 #define SPECLOSS_EMU 1
 #include "../../include/specloss.h"
 #include "../../dl_speech_enhancement_b200/csrc/specloss_kernels.cuh"
+#include "../../dl_speech_enhancement_b200/csrc/melpower.cuh"
 #include "melgemm_params_emu.h"
 
 #include <cstdarg>
@@ -151,6 +152,12 @@ int spl_launch_shape_backward(const spl::ShapeParams& p, int grid, int wpc, void
 
 int spl_launch_shape_finalize(const spl::ShapeFinalizeParams& fp, void*) {
   spl::shape_finalize_body(fp);
+  return SPL_OK;
+}
+
+int spl_launch_melpow(const spl::MelPowParams& p, int grid, int wpc, size_t smem, void*) {
+  run_grid(grid, wpc, smem, [&](float* sm, int tid) { spl::melpow_load_tables(p, sm, tid, wpc * 32); },
+           [&](float* sm, int block, int tid) { spl::melpow_body(p, sm, block, tid, grid, wpc); });
   return SPL_OK;
 }
 

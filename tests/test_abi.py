@@ -22,7 +22,7 @@ def lib():
 def declared_symbols():
     src = open(os.path.join(ROOT, "include", "specloss.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(spl_[a-z_]+)\s*\(", src)))
+    return sorted(set(re.findall(r"\b(spl_[a-z0-9_]+)\s*\(", src)))
 
 
 def test_header_and_binding_agree():
