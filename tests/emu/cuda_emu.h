@@ -6,6 +6,7 @@
 #include <barrier>
 #include <cmath>
 #include <cstddef>
+#include <cstdlib>
 
 #define __device__
 #define __host__
@@ -35,7 +36,19 @@ struct EmuWarp {
 extern thread_local EmuWarp* emu_warp;
 extern thread_local int emu_lane;
 
-static inline void __syncwarp() { emu_warp->bar.arrive_and_wait(); }
+// Fault injection for the race-detector's positive control (tests/emu/tsan_race_check.py): with
+// SPECLOSS_EMU_SKIP_SYNC=n every lane skips its n-th __syncwarp() of the process (all 32 lanes skip the same one, so the
+// barrier count stays balanced); ThreadSanitizer must then report the shared-memory race that barrier was there to prevent.
+static inline bool emu_skip_this_sync() {
+  static const long skip = [] { const char* e = std::getenv("SPECLOSS_EMU_SKIP_SYNC"); return e ? std::atol(e) : 0L; }();
+  if (skip <= 0) return false;
+  static thread_local long count = 0;
+  return ++count == skip;
+}
+static inline void __syncwarp() {
+  if (emu_skip_this_sync()) return;
+  emu_warp->bar.arrive_and_wait();
+}
 static inline void __syncthreads() { emu_warp->bar.arrive_and_wait(); }   // emulated CTAs are one warp wide
 static inline float __shfl_xor_sync(unsigned, float v, int lane_mask) {
   emu_warp->slots[emu_lane] = v;

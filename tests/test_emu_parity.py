@@ -296,3 +296,19 @@ def test_second_backward_needs_retain_graph(emu_engine):
     assert torch.equal(g1, x.grad)
     with pytest.raises(RuntimeError, match="second time|already been freed"):
         (sc + mag).backward()
+
+
+def test_shared_memory_race_check_under_thread_sanitizer():
+    """compute-sanitizer's racecheck is not available on this pool; the emulator's lanes are real threads and its barriers
+    real barriers, so ThreadSanitizer over the emulated kernels is the shared-memory race detector (tests/emu/
+    tsan_race_check.py: clean run must report nothing, a run with one __syncwarp() skipped must be caught)."""
+    import os
+    import subprocess
+    import sys
+
+    script = os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu", "tsan_race_check.py")
+    res = subprocess.run([sys.executable, script], capture_output=True, text=True, timeout=1500)
+    if res.returncode == 2:
+        pytest.skip("libtsan / g++ -fsanitize=thread not available")
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-2000:]
+    assert "data-race reports = 0" in res.stdout.splitlines()[0]
