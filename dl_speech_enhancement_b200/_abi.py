@@ -15,7 +15,7 @@ from ctypes import POINTER, c_char_p, c_float, c_int32, c_int64, c_void_p
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libspecloss.so")
 CSRC = os.path.join(_HERE, "csrc")
-ABI_VERSION = 13
+ABI_VERSION = 14
 
 SPL_KIND_STFT = 0
 SPL_KIND_MEL = 1
@@ -35,6 +35,7 @@ class SplTransform(ctypes.Structure):
         ("window", c_void_p), ("twiddle", c_void_p),
         ("n_mels", c_int32), ("inv_ln_base", c_float),
         ("mel_tasks", c_void_p), ("mel_entries", c_void_p), ("mel_rounds", c_int32), ("mel_entry_rows", c_int32), ("bin_tab", c_void_p),
+        ("twiddle_eo", c_void_p), ("mel_entries_eo", c_void_p),
         ("partials", c_void_p), ("gframes", c_void_p),
     ]
 
@@ -46,7 +47,7 @@ class SplGeometry(ctypes.Structure):
     ]
 
 
-EXPORTS = ("spl_abi_version", "spl_last_error", "spl_fill_twiddle", "spl_geometry_of", "spl_forward",
+EXPORTS = ("spl_abi_version", "spl_last_error", "spl_fill_twiddle", "spl_fill_twiddle_eo", "spl_geometry_of", "spl_forward",
            "spl_reduce", "spl_finalize", "spl_reduce_finalize", "spl_exchange_buffer_bytes", "spl_reduce_exchange_finalize", "spl_backward", "spl_spectrogram", "spl_spectrogram_backward", "spl_mel_project",
            "spl_shape_geometry", "spl_shape_forward", "spl_shape_finalize", "spl_shape_backward",
            "spl_mag_loss_geometry", "spl_mag_loss_forward", "spl_mag_loss_backward",
@@ -65,6 +66,8 @@ def bind(lib: ctypes.CDLL) -> ctypes.CDLL:
     lib.spl_last_error.argtypes = []
     lib.spl_fill_twiddle.restype = c_int32
     lib.spl_fill_twiddle.argtypes = [c_int32, c_void_p]
+    lib.spl_fill_twiddle_eo.restype = c_int32
+    lib.spl_fill_twiddle_eo.argtypes = [c_void_p]
     lib.spl_geometry_of.restype = c_int32
     lib.spl_geometry_of.argtypes = [POINTER(SplTransform), c_int32, c_int32, POINTER(SplGeometry)]
     lib.spl_forward.restype = c_int32
@@ -139,7 +142,7 @@ def build_library(verbose: bool = False) -> str:
     if not os.path.exists(nvcc):
         raise SpecLossError("nvcc not found; libspecloss.so cannot be built")
     srcs = [os.path.join(CSRC, f) for f in ("specloss.cu", "specloss_kernels.cuh", "specloss_host.inl",
-                                            "fft_codelets.cuh", "melgemm.cuh", "melpower.cuh")]
+                                            "fft_codelets.cuh", "melgemm.cuh", "melpower.cuh", "transform_eo.cuh")]
     hdr = os.path.join(os.path.dirname(_HERE), "include", "specloss.h")
     newest = max(os.path.getmtime(p) for p in srcs + [hdr])
     if os.path.exists(LIB_PATH) and os.path.getmtime(LIB_PATH) >= newest:

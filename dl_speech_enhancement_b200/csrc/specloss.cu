@@ -4,6 +4,7 @@
 #include "specloss_kernels.cuh"
 #include "melgemm.cuh"
 #include "melpower.cuh"
+#include "transform_eo.cuh"
 
 #include <cmath>
 #include <cstdarg>
@@ -50,6 +51,7 @@ int spl_launch_shape(int n_fft, size_t table_bytes, size_t warp_bytes, long long
   int rc = device_sm_count(&sms);
   if (rc) return rc;
   int w = n_fft == 2048 ? spl::MaxWarps<2048>::value : spl::MaxWarps<1024>::value;
+  if (n_fft == 2048 && w > SPL_EO_WARPS) w = SPL_EO_WARPS;      // (variant builds only: SPL_EO_WARPS < 12 also caps the 64-point kernels)
   static const int cap2048 = [] { const char* e = std::getenv("SPECLOSS_WARPS_2048"); return e ? std::atoi(e) : 0; }();
   static const int cap_small = [] { const char* e = std::getenv("SPECLOSS_WARPS_SMALL"); return e ? std::atoi(e) : 0; }();
   const int cap = n_fft == 2048 ? cap2048 : cap_small;          // tuning knobs (profiles/): fewer resident warps per SM
@@ -144,6 +146,18 @@ int spl_launch_transform(const spl::TransformParams& p, int grid, int wpc, size_
   int rc = opt_in_smem(kern, configured);
   if (rc) return rc;
   kern<<<grid, wpc * 32, smem, static_cast<cudaStream_t>(stream)>>>(p);
+  SPL_CUDA(cudaGetLastError());
+  return SPL_OK;
+}
+
+template <int KIND, bool GRAD, int WIN_T>
+int spl_launch_transform_eo(const spl::TransformParams& p, const float2* twiddle_eo, const void* mel_entries_eo, int grid, int wpc,
+                            size_t smem, void* stream) {
+  auto kern = spl::transform_eo_kernel<KIND, GRAD, WIN_T>;
+  static thread_local bool configured[64] = {false};
+  int rc = opt_in_smem(kern, configured);
+  if (rc) return rc;
+  kern<<<grid, wpc * 32, smem, static_cast<cudaStream_t>(stream)>>>(p, twiddle_eo, mel_entries_eo);
   SPL_CUDA(cudaGetLastError());
   return SPL_OK;
 }

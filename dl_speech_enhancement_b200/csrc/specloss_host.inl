@@ -6,6 +6,8 @@
 //       -- CTAs and warps per CTA of a transform launch over `items` warp work items (the reduction needs the
 //          same numbers: one row of partial sums per warp)
 //   template <int NFFT, int KIND, bool GRAD, int WIN_T> int spl_launch_transform(const spl::TransformParams&, int grid, int wpc, size_t smem, void* stream);
+//   template <int KIND, bool GRAD, int WIN_T> int spl_launch_transform_eo(const spl::TransformParams&, const float2* twiddle_eo,
+//                                                                         const void* mel_entries_eo, int grid, int wpc, size_t smem, void* stream);
 //   template <int NFFT> int spl_launch_spec(const spl::SpecParams&, int grid, int wpc, size_t smem, void* stream);
 //   template <int NFFT, int KIND> int spl_launch_specgrad(const spl::SpecGradParams&, int grid, int wpc, size_t smem, void* stream);
 //   int spl_fork(void* stream, int n, void** streams);   -- streams[0] = stream, streams[1..n) run concurrently after
@@ -32,6 +34,29 @@ constexpr long long kMaxPartialRows = 1024 * 32;      // upper bound on grid * w
 bool supported_nfft(int n) { return n == 512 || n == 1024 || n == 2048; }
 
 int frames_in_flight(int n_fft) { return n_fft == 512 ? 2 : 1; }
+
+// 2048-point losses on the 32 x 32 geometry (transform_eo.cuh) when the caller supplied its tables.  Measured on B200
+// (profiles/README.md r3h): the mel loss gains 29 % (3 half-size FFTs instead of 4, 12 resident warps instead of 8), the
+// STFT loss loses 3 % -- so by default only the mel loss takes this route.  SPECLOSS_EO_2048 = 0 (never) | mel (default) |
+// 1 (mel and STFT), for A/B measurements.
+int eo_mode_from_env() {
+  const char* e = std::getenv("SPECLOSS_EO_2048");
+  if (!e || !e[0] || e[0] == 'm') return 1;
+  return e[0] == '0' ? 0 : 2;
+}
+int eo_mode() {
+#ifdef SPECLOSS_EMU
+  return eo_mode_from_env();          // the test-suite switches routes between calls
+#else
+  static const int v = eo_mode_from_env();
+  return v;
+#endif
+}
+bool use_eo(const spl_transform* t) {
+  if (t->n_fft != 2048 || !t->twiddle_eo) return false;
+  if (t->kind == SPL_KIND_MEL) return t->mel_entries_eo && eo_mode() >= 1;
+  return eo_mode() >= 2;
+}
 
 int check_transform(const spl_transform* t, int B, int T) {
   if (!t) return fail(SPL_E_INVALID, "null transform");
@@ -72,6 +97,11 @@ void geometry(const spl_transform* t, int B, int T, spl_geometry* g) {
   // row of zeros), wpc <= 32
   g->partial_count = (int64_t)((items < kMaxPartialRows ? items : kMaxPartialRows) + 32) * g->n_sums;
   g->gframe_bytes = (int64_t)B * g->n_frames * t->win * (t->kind == SPL_KIND_STFT ? 8 : 4);
+  if (use_eo(t)) {
+    g->smem_table_bytes = (int64_t)spl::cta_tables_eo(t->win, t->kind, t->mel_rounds, t->mel_entry_rows).total * 4;
+    g->smem_warp_bytes = (int64_t)spl::eo_words_per_warp(t->kind, t->n_mels) * 4;
+    return;
+  }
   const spl::CtaTables ct = spl::cta_tables(t->n_fft, t->win, t->kind, t->mel_rounds, t->mel_entry_rows);
   g->smem_table_bytes = (int64_t)ct.total * 4;
   g->smem_warp_bytes = (int64_t)warp_words(t->n_fft, t->kind, t->n_mels) * 4;
@@ -107,9 +137,43 @@ int launch_any(const spl::TransformParams& p, int n_fft, int kind, bool grad, in
   return launch_win<2048, 0>(p, kind, grad, grid, wpc, smem, s);
 }
 
+template <int WIN_T>
+int launch_eo_win(const spl::TransformParams& p, const spl_transform* t, bool grad, int grid, int wpc, size_t smem, void* s) {
+  const float2* tw = reinterpret_cast<const float2*>(t->twiddle_eo);
+  if (t->kind == SPL_KIND_STFT)
+    return grad ? spl_launch_transform_eo<spl::kKindStft, true, WIN_T>(p, tw, nullptr, grid, wpc, smem, s)
+                : spl_launch_transform_eo<spl::kKindStft, false, WIN_T>(p, tw, nullptr, grid, wpc, smem, s);
+  return grad ? spl_launch_transform_eo<spl::kKindMel, true, WIN_T>(p, tw, t->mel_entries_eo, grid, wpc, smem, s)
+              : spl_launch_transform_eo<spl::kKindMel, false, WIN_T>(p, tw, t->mel_entries_eo, grid, wpc, smem, s);
+}
+
+int launch_eo(const spl::TransformParams& p, const spl_transform* t, bool grad, int grid, int wpc, size_t smem, void* s) {
+  if (p.win == 1200) return launch_eo_win<1200>(p, t, grad, grid, wpc, smem, s);
+  if (p.win == 2048) return launch_eo_win<2048>(p, t, grad, grid, wpc, smem, s);
+  return launch_eo_win<0>(p, t, grad, grid, wpc, smem, s);
+}
+
 }  // namespace
 
 extern "C" {
+
+int32_t spl_fill_twiddle_eo(float* host_out) {
+  if (!host_out) return fail(SPL_E_INVALID, "spl_fill_twiddle_eo: null output");
+  const double two_pi = 6.283185307179586476925286766559;
+  for (int k2 = 0; k2 < 32; ++k2)
+    for (int n1 = 0; n1 < 32; ++n1) {
+      const double th = two_pi * (double)((n1 * k2) % 1024) / 1024.0;
+      host_out[2 * (k2 * 32 + n1)] = (float)std::cos(th);
+      host_out[2 * (k2 * 32 + n1) + 1] = (float)(-std::sin(th));
+    }
+  float* wk = host_out + 2 * 1024;
+  for (int k = 0; k < spl::eo::WK; ++k) {
+    const double th = two_pi * (double)k / 2048.0;
+    wk[2 * k] = k <= 512 ? (float)std::cos(th) : 0.f;
+    wk[2 * k + 1] = k <= 512 ? (float)(-std::sin(th)) : 0.f;
+  }
+  return SPL_OK;
+}
 
 int32_t spl_abi_version(void) { return SPL_ABI_VERSION; }
 
@@ -184,7 +248,8 @@ int32_t spl_forward(const spl_transform* ts, int32_t n, const float* x, const fl
     p.mel_entry_rows = t->kind == SPL_KIND_MEL ? t->mel_entry_rows : 0;
     p.bin_tab = t->bin_tab;
     const size_t smem = (size_t)g.smem_table_bytes + (size_t)g.smem_warp_bytes * wpc;
-    rc = launch_any(p, t->n_fft, t->kind, t->gframes != nullptr, grid, wpc, smem, streams[i]);
+    rc = use_eo(t) ? launch_eo(p, t, t->gframes != nullptr, grid, wpc, smem, streams[i])
+                   : launch_any(p, t->n_fft, t->kind, t->gframes != nullptr, grid, wpc, smem, streams[i]);
     if (rc) break;
   }
   const int rc_join = spl_join(stream, n, streams);      // always re-join, also after a failed launch
@@ -409,6 +474,7 @@ int32_t spl_backward(const spl_transform* ts, int32_t n, int32_t B, int32_t T, c
     spl::CombineEntry& e = cp.e[r];
     e.frames = ts[r].gframes; e.kind = ts[r].kind; e.half = ts[r].n_fft / 2; e.hop = ts[r].hop; e.win = ts[r].win;
     e.left = (ts[r].n_fft - ts[r].win) / 2; e.n_frames = 1 + T / ts[r].hop;
+    e.planar = (ts[r].kind == SPL_KIND_STFT && use_eo(ts + r)) ? 1 : 0;
   }
   cp.coefs = coefs; cp.g_sc = g_sc; cp.g_mag = g_mag; cp.g_mel = g_mel; cp.dx = dx; cp.B = B; cp.T = T;
   return spl_launch_combine(cp, stream);

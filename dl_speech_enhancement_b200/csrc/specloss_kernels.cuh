@@ -1624,8 +1624,9 @@ SPL_DEVICE void exchange_body(const ExchangeParams& p, int lane) {
 // and folded over the reflect-padding margins.
 // ---------------------------------------------------------------------------------------------
 struct CombineEntry {
-  const void* frames;    // [B * n_frames][win] float2 (stft) | float (mel)
+  const void* frames;    // [B * n_frames][win] float2 (u, v) (stft) | float (mel) | planar stft: [B * n_frames][2][win] float
   int kind, half, hop, win, left, n_frames;
+  int planar;            // stft written by the even/odd 2048-point kernel: a u plane and a v plane per frame
 };
 struct CombineParams {
   int n;
@@ -1649,7 +1650,10 @@ SPL_DEVICE float gather_padded(const CombineEntry& e, int b, int ppos, float cu,
     const int tap = q - t * e.hop;
     if (tap >= e.win) break;
     const size_t o = ((size_t)b * e.n_frames + t) * e.win + tap;
-    if (e.kind == kKindStft) {
+    if (e.kind == kKindStft && e.planar) {
+      const float* src = reinterpret_cast<const float*>(e.frames) + (((size_t)b * e.n_frames + t) * 2) * e.win + tap;
+      acc = fmaf(cu, __ldg(src), fmaf(cv, __ldg(src + e.win), acc));
+    } else if (e.kind == kKindStft) {
       const float2 v = __ldg(reinterpret_cast<const float2*>(e.frames) + o);
       acc = fmaf(cu, v.x, fmaf(cv, v.y, acc));
     } else {
@@ -1668,7 +1672,23 @@ SPL_DEVICE void gather_padded4(const CombineEntry& e, int b, int ppos0, float cu
     const int tap = q0 - t * e.hop;                 // tap of the first of the four positions (may be negative)
     if (tap >= e.win) break;
     const size_t o = ((size_t)b * e.n_frames + t) * e.win + tap;     // meaningful for tap >= 0 only
-    if (e.kind == kKindStft) {
+    if (e.kind == kKindStft && e.planar) {
+      const size_t ou = (((size_t)b * e.n_frames + t) * 2) * e.win + tap;
+      const float* su = reinterpret_cast<const float*>(e.frames) + ou;
+      const float* sv = su + e.win;
+      if (tap >= 0 && tap + 3 < e.win && ((ou | (size_t)e.win) & 3) == 0) {
+        const float4 u = __ldg(reinterpret_cast<const float4*>(su));
+        const float4 v = __ldg(reinterpret_cast<const float4*>(sv));
+        acc[0] = fmaf(cu, u.x, fmaf(cv, v.x, acc[0]));
+        acc[1] = fmaf(cu, u.y, fmaf(cv, v.y, acc[1]));
+        acc[2] = fmaf(cu, u.z, fmaf(cv, v.z, acc[2]));
+        acc[3] = fmaf(cu, u.w, fmaf(cv, v.w, acc[3]));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (tap + j >= 0 && tap + j < e.win) acc[j] = fmaf(cu, __ldg(su + j), fmaf(cv, __ldg(sv + j), acc[j]));
+      }
+    } else if (e.kind == kKindStft) {
       const float2* src = reinterpret_cast<const float2*>(e.frames);
       if (tap >= 0 && tap + 3 < e.win && (o & 1) == 0) {
         const float4 v0 = __ldg(reinterpret_cast<const float4*>(src + o));

@@ -86,6 +86,24 @@ def twiddle_table(n_fft: int) -> torch.Tensor:
     return torch.from_numpy(tab.reshape(-1).copy())
 
 
+def twiddle_eo_table() -> torch.Tensor:
+    """Tables of the even/odd 2048-point kernels (csrc/transform_eo.cuh; mirrors spl_fill_twiddle_eo): W_1024^(n1*k2),
+    layout [k2 < 32][n1 < 32], then W_2048^k for k = 0..512 zero-padded to 516 entries; fp32 roundings of fp64."""
+    e = (np.arange(32)[:, None] * np.arange(32)[None, :]) % 1024
+    th = 2.0 * np.pi * e.astype(np.float64) / 1024
+    a = np.stack([np.cos(th), -np.sin(th)], axis=-1).reshape(-1)
+    k = np.arange(516)
+    th = 2.0 * np.pi * k.astype(np.float64) / 2048
+    b = np.stack([np.where(k <= 512, np.cos(th), 0.0), np.where(k <= 512, -np.sin(th), 0.0)], axis=-1).reshape(-1)
+    return torch.from_numpy(np.concatenate([a, b]).astype(np.float32))
+
+
+def slot_offset_eo(k: int) -> int:
+    """float2 index of the amplitude pair of bin k <= 1024 in the prediction's slot of the even/odd 2048-point kernel:
+    the natural position of k in the 32 x 32 layout (row k % 32, pitch 33, column k // 32); bin 1024 = pad word of row 0."""
+    return 32 if k == 1024 else (k % 32) * 33 + k // 32
+
+
 MEL_ITER_TARGET = int(os.environ.get("SPECLOSS_MEL_ITER", "16"))     # bins summed per lane per round of the projection schedule (tuning knob)
 
 
@@ -134,11 +152,12 @@ def mel_tables(melmat: np.ndarray, n_fft: int):
     if cur:
         rounds.append(cur)
     tasks = np.zeros((len(rounds), lanes, 4), np.int32)
-    entries = []
+    entries, entries_eo = [], []
     amp_slot = lambda k: slot_offset(n_fft, k)      # noqa: E731
     for r, grp_list in enumerate(rounds):
         iters = max((-(-ln // g) for g, _, _, ln in grp_list), default=0)
         ent = np.zeros((iters, lanes, 2), np.int32)
+        ent_eo = np.zeros((iters, lanes, 2), np.int32)
         tasks[r, :, 0] = 0xfff | (1 << 12) | (iters << 20)             # idle lanes
         tasks[r, :, 1] = len(entries)
         lane = 0
@@ -148,9 +167,13 @@ def mel_tables(melmat: np.ndarray, n_fft: int):
                 for s_i, k in enumerate(range(st + j, st + ln, g)):
                     ent[s_i, lane + j, 0] = amp_slot(k)
                     ent[s_i, lane + j, 1] = np.float32(melmat[k, m]).view(np.int32)
+                    if n_fft == 2048:
+                        ent_eo[s_i, lane + j] = (slot_offset_eo(k), ent[s_i, lane + j, 1])
             lane += g
         entries.extend(ent)
+        entries_eo.extend(ent_eo)
     entries = np.stack(entries) if entries else np.zeros((1, lanes, 2), np.int32)
+    entries_eo = np.stack(entries_eo) if entries_eo else np.zeros((1, lanes, 2), np.int32)
 
     bin_tab = np.zeros((k_bins, 4), np.int32)
     f2i = lambda v: np.float32(v).view(np.int32)                                 # noqa: E731
@@ -169,8 +192,11 @@ def mel_tables(melmat: np.ndarray, n_fft: int):
         else:
             bin_tab[k, :3] = (n_mels - 2, 0, f2i(melmat[k, nz[0]]))
     t = torch.from_numpy
-    return dict(mel_tasks=t(tasks.reshape(-1).copy()), mel_entries=t(entries.reshape(-1).copy()),
-                bin_tab=t(bin_tab.reshape(-1).copy()))
+    out = dict(mel_tasks=t(tasks.reshape(-1).copy()), mel_entries=t(entries.reshape(-1).copy()),
+               bin_tab=t(bin_tab.reshape(-1).copy()))
+    if n_fft == 2048:
+        out["mel_entries_eo"] = t(entries_eo.reshape(-1).copy())
+    return out
 
 
 @dataclass
@@ -186,6 +212,7 @@ class TransformPlan:
     n_mels: int = 0
     inv_ln_base: float = 1.0
     tables: dict = field(default_factory=dict)   # mel only: tensors named as the spl_transform fields
+    twiddle_eo: Optional[torch.Tensor] = None    # n_fft == 2048: tables of the even/odd kernels (None: 64-point-per-lane kernels)
 
     def validate(self):
         fft_geometry(self.n_fft)
@@ -403,7 +430,7 @@ class Engine:
         if rec is not None:
             return rec
         key = (tuple((p.kind, p.n_fft, p.hop, p.win, p.eps, p.n_mels, p.inv_ln_base, p.window.data_ptr(),
-                      p.twiddle.data_ptr()) + tuple(t.data_ptr() for t in p.tables.values()) for p in plans),
+                      p.twiddle.data_ptr(), _ptr(p.twiddle_eo)) + tuple(t.data_ptr() for t in p.tables.values()) for p in plans),
                batch, t_len, need_grad, str(dev))
         rec = self._recipes.get(key)
         if rec is not None:
@@ -435,6 +462,10 @@ class Engine:
             tr.eps = pl.eps
             tr.window, tr.twiddle = _ptr(pl.window), _ptr(pl.twiddle)
             tr.n_mels, tr.inv_ln_base = pl.n_mels, pl.inv_ln_base
+            if pl.twiddle_eo is not None and pl.n_fft == 2048:
+                if pl.twiddle_eo.device != dev:
+                    raise RuntimeError("loss module buffers are not on the input device: call .to(device)")
+                tr.twiddle_eo = _ptr(pl.twiddle_eo)
             if pl.kind == SPL_KIND_MEL:
                 for name, t in pl.tables.items():
                     if t.device != dev:
@@ -450,7 +481,7 @@ class Engine:
                 rec.off_gframes.append(off)
                 off = _align(off + g.gframe_bytes)
             n_sums += g.n_sums
-            rec.keep.extend([pl.window, pl.twiddle] + list(pl.tables.values()))
+            rec.keep.extend([pl.window, pl.twiddle, pl.twiddle_eo] + list(pl.tables.values()))
         rec.off_sums = off
         off = _align(off + 8 * n_sums)
         rec.off_lsums = off                    # this rank's sums when the global ones come from the peer exchange
@@ -583,7 +614,8 @@ class Engine:
         if plan.kind == SPL_KIND_MEL:
             want = (batch, plan.n_mels, frames)
             for name, t in plan.tables.items():
-                setattr(tr, name, _ptr(t))
+                if name != "mel_entries_eo":          # the explicit path runs the 64-point-per-lane kernels
+                    setattr(tr, name, _ptr(t))
             lanes = fft_geometry(plan.n_fft)[0]
             tr.mel_rounds = plan.tables["mel_tasks"].numel() // (4 * lanes)
             tr.mel_entry_rows = plan.tables["mel_entries"].numel() // (2 * lanes)

@@ -20,7 +20,7 @@ import torch
 
 from . import melfb
 from ._abi import SPL_KIND_MEL, SPL_KIND_STFT
-from .engine import TransformPlan, cuda_engine, fft_geometry, mel_gemm_weights, mel_tables, melpow_csr, melpow_twiddle_table, twiddle_table
+from .engine import TransformPlan, cuda_engine, fft_geometry, mel_gemm_weights, mel_tables, melpow_csr, melpow_twiddle_table, twiddle_eo_table, twiddle_table
 from .functional import log_mel_spectrogram, magnitude_loss, shape_loss, spectral_losses
 from .functional import spectrogram as _spectrogram_fn
 
@@ -123,10 +123,12 @@ class STFTLoss(torch.nn.Module):
         self.log_stft_magnitude_loss = LogSTFTMagnitudeLoss()
         self.register_buffer("window", _window(window, win_length))
         self.register_buffer("_twiddle", twiddle_table(fft_size), persistent=False)
+        if fft_size == 2048:
+            self.register_buffer("_twiddle_eo", twiddle_eo_table(), persistent=False)
 
     def plan(self) -> TransformPlan:
         return TransformPlan(SPL_KIND_STFT, self.fft_size, self.hop_size, self.win_length, 1e-7,
-                             self.window, self._twiddle)
+                             self.window, self._twiddle, twiddle_eo=getattr(self, "_twiddle_eo", None))
 
     def forward(self, x, y):
         return spectral_losses(x, y, _cached_plans(self, [self]), group=getattr(self, "process_group", None))
@@ -187,7 +189,11 @@ class MelSpectrogram(torch.nn.Module):
             raise ValueError(f"log_base: {log_base} is not supported.")
         self.num_mels = num_mels
         self.register_buffer("_twiddle", twiddle_table(fft_size), persistent=False)
-        for name, t in mel_tables(mel.T, fft_size).items():
+        if fft_size == 2048:
+            self.register_buffer("_twiddle_eo", twiddle_eo_table(), persistent=False)
+        tabs = mel_tables(mel.T, fft_size)
+        self._table_names = tuple(tabs.keys())
+        for name, t in tabs.items():
             self.register_buffer("_" + name, t, persistent=False)
         if num_mels <= 128:
             w_hi, w_lo = mel_gemm_weights(mel.T, fft_size)
@@ -195,10 +201,11 @@ class MelSpectrogram(torch.nn.Module):
             self.register_buffer("_w_lo", w_lo, persistent=False)
 
     def plan(self) -> TransformPlan:
-        tables = {n: getattr(self, "_" + n) for n in ("mel_tasks", "mel_entries", "bin_tab")}
+        tables = {n: getattr(self, "_" + n) for n in self._table_names}
         inv_ln = 1.0 if self.log_base is None else 1.0 / math.log(self.log_base)
         return TransformPlan(SPL_KIND_MEL, self.fft_size, self.hop_size, self.win_length, self.eps,
-                             self.window, self._twiddle, self.num_mels, inv_ln, tables)
+                             self.window, self._twiddle, self.num_mels, inv_ln, tables,
+                             twiddle_eo=getattr(self, "_twiddle_eo", None))
 
     def forward(self, x):
         from .engine import gemm_ld

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SPL_ABI_VERSION 13
+#define SPL_ABI_VERSION 14
 
 #define SPL_OK 0
 #define SPL_E_INVALID (-1)   /* bad argument / outside the supported envelope */
@@ -51,6 +51,11 @@ typedef struct spl_transform {
   int32_t mel_rounds;
   int32_t mel_entry_rows;       /* sum of iters over the rounds */
   const int32_t* bin_tab;       /* device [(n_fft/2+1) * 4]: {m0, bits(melmat[k,m0]), bits(melmat[k,m0+1]), 0} */
+  /* --- n_fft == 2048 only: tables of the even/odd kernels (32 x 32 geometry, csrc/transform_eo.cuh); NULL selects the
+   *     64-point-per-lane kernels --- */
+  const float* twiddle_eo;      /* device, 2*1024 + 2*516 floats written by spl_fill_twiddle_eo() */
+  const int32_t* mel_entries_eo;/* device, same shape as mel_entries with the amplitude slot offsets of the 32 x 32 geometry:
+                                   bin j < 1024 at (j % 32) * 33 + j / 32, bin 1024 at 32 (mel only) */
   /* --- per-call workspace, sized by spl_geometry() --- */
   double* partials;          /* device [partial_count]: one row of n_sums per warp of the launch */
   void* gframes;             /* device [gframe_bytes]: the windowed, un-scaled gradient of every frame
@@ -73,6 +78,10 @@ const char* spl_last_error(void);
 
 /* Host-side table: W_N^(n1*k2) rounded from fp64, layout [k2][n1] (2*n_fft floats, host memory). */
 int32_t spl_fill_twiddle(int32_t n_fft, float* host_out);
+
+/* Host-side tables of the even/odd 2048-point kernels: W_1024^(n1*k2) at [k2*32 + n1] (2*1024 floats) followed by
+ * W_2048^k for k = 0..512 zero-padded to 516 entries (2*516 floats); all rounded from fp64. */
+int32_t spl_fill_twiddle_eo(float* host_out);
 
 /* Sizes of the per-call workspace for batch (B, T).  Host only. */
 int32_t spl_geometry_of(const spl_transform* t, int32_t B, int32_t T, spl_geometry* out);

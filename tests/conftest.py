@@ -94,7 +94,7 @@ def emu_engine():
     so_path = os.path.join(EMU_DIR, "libspecloss_emu.so")
     srcs = [os.path.join(EMU_DIR, "specloss_emu.cpp"), os.path.join(EMU_DIR, "cuda_emu.h"),
             os.path.join(ROOT, "include", "specloss.h")] + \
-        [os.path.join(_abi.CSRC, f) for f in ("specloss_kernels.cuh", "specloss_host.inl", "fft_codelets.cuh", "melpower.cuh")]
+        [os.path.join(_abi.CSRC, f) for f in ("specloss_kernels.cuh", "specloss_host.inl", "fft_codelets.cuh", "melpower.cuh", "transform_eo.cuh")]
     if not os.path.exists(so_path) or os.path.getmtime(so_path) < max(os.path.getmtime(s) for s in srcs):
         cmd = ["g++", "-std=c++20", "-O1", "-fPIC", "-shared", "-pthread", "-I" + EMU_DIR, "-o", so_path, srcs[0]]
         res = subprocess.run(cmd, capture_output=True, text=True)

@@ -6,6 +6,7 @@
 #include "../../include/specloss.h"
 #include "../../dl_speech_enhancement_b200/csrc/specloss_kernels.cuh"
 #include "../../dl_speech_enhancement_b200/csrc/melpower.cuh"
+#include "../../dl_speech_enhancement_b200/csrc/transform_eo.cuh"
 #include "melgemm_params_emu.h"
 
 #include <cstdarg>
@@ -82,6 +83,15 @@ int spl_launch_transform(const spl::TransformParams& p, int grid, int wpc, size_
   run_grid(grid, wpc, smem,
            [&](float* sm, int tid) { spl::cta_load_tables<NFFT, KIND>(p, sm, tid, wpc * 32); },
            [&](float* sm, int block, int tid) { spl::transform_body<NFFT, KIND, GRAD, WIN_T>(p, sm, block, tid, grid, wpc); });
+  return SPL_OK;
+}
+
+template <int KIND, bool GRAD, int WIN_T>
+int spl_launch_transform_eo(const spl::TransformParams& p, const float2* twiddle_eo, const void* mel_entries_eo, int grid, int wpc,
+                            size_t smem, void*) {
+  run_grid(grid, wpc, smem,
+           [&](float* sm, int tid) { spl::cta_load_tables_eo<KIND>(p, twiddle_eo, mel_entries_eo, sm, tid, wpc * 32); },
+           [&](float* sm, int block, int tid) { spl::transform_eo_body<KIND, GRAD, WIN_T>(p, sm, block, tid, grid, wpc); });
   return SPL_OK;
 }
 

@@ -312,3 +312,72 @@ def test_shared_memory_race_check_under_thread_sanitizer():
         pytest.skip("libtsan / g++ -fsanitize=thread not available")
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-2000:]
     assert "data-race reports = 0" in res.stdout.splitlines()[0]
+
+
+@pytest.mark.parametrize("win,hop,t_len", [(1000, 256, 3001), (1023, 200, 2500), (2048, 512, 2200), (1200, 240, 2047)])
+def test_even_odd_2048_generic_windows_and_odd_lengths(emu_engine, win, hop, t_len, monkeypatch):
+    """The 2048-point losses on the 32 x 32 geometry (csrc/transform_eo.cuh): window lengths without a compile-time
+    kernel, an ODD window (the (even, odd) sample pairs then straddle the window's centring offset: scalar tap path), odd
+    utterance lengths (rows not 8-byte aligned: scalar loads) -- STFT and mel, forward and gradient, against the fp64
+    oracle; and the two kernel families (even/odd vs 64 points per lane) agree with each other."""
+    import torch
+
+    from dl_speech_enhancement_b200 import modules
+    from dl_speech_enhancement_b200.functional import spectral_losses
+    from oracle import spectral_oracle as so
+
+    monkeypatch.setenv("SPECLOSS_EO_2048", "1")          # STFT too (the product default takes this route for mel only)
+    y_hat, y = so.synth_pair(2, t_len, seed=win)
+    stft = modules.MultiResolutionSTFTLoss([2048], [hop], [win])
+    mel_kw = dict(fs=48000, fft_sizes=[2048], hop_sizes=[hop], win_lengths=[win], num_mels=80, fmin=0, fmax=24000, log_base=10.0)
+    mel = modules.MultiMelSpectrogramLoss(**mel_kw)
+    plans = stft.plans() + mel.plans()
+    assert all(p.twiddle_eo is not None for p in plans)
+    x = y_hat.clone().requires_grad_(True)
+    outs = spectral_losses(x, y, plans, engine=emu_engine)
+    sum(outs).backward()
+    ref, gref = so.losses_and_grad(y_hat, y, [so.StftRes(2048, hop, win)], so.mel_from_kwargs(**mel_kw), dtype=torch.float64)
+    got = [float(o.detach()) for o in outs]
+    np.testing.assert_allclose(got, ref, rtol=1e-4)
+    assert rel_l2(x.grad.numpy(), gref.numpy()) <= 1e-3
+    # the 64-point-per-lane kernels on the same input (plans without the even/odd tables)
+    for p in plans:
+        p.twiddle_eo = None
+    x2 = y_hat.clone().requires_grad_(True)
+    outs2 = spectral_losses(x2, y, plans, engine=emu_engine)
+    sum(outs2).backward()
+    np.testing.assert_allclose([float(o.detach()) for o in outs2], got, rtol=2e-6)
+    assert rel_l2(x2.grad.numpy(), x.grad.numpy()) <= 2e-4
+
+
+def test_even_odd_2048_identical_inputs_exact_zero(emu_engine, monkeypatch):
+    """loss(x, x) = 0 and a zero gradient EXACTLY: both signals run through the same instruction sequence."""
+    import torch
+
+    monkeypatch.setenv("SPECLOSS_EO_2048", "1")
+
+    from dl_speech_enhancement_b200 import modules
+    from dl_speech_enhancement_b200.functional import spectral_losses
+
+    x = (0.2 * torch.randn(1, 2600, generator=torch.Generator().manual_seed(9))).requires_grad_(True)
+    stft = modules.MultiResolutionSTFTLoss([2048], [240], [1200])
+    mel = modules.MultiMelSpectrogramLoss(fs=48000, fft_sizes=[2048], hop_sizes=[300], win_lengths=[None], num_mels=80, fmin=0,
+                                          fmax=24000, log_base=None)
+    outs = spectral_losses(x, x.detach().clone(), stft.plans() + mel.plans(), engine=emu_engine)
+    sum(outs).backward()
+    assert all(float(o.detach()) == 0.0 for o in outs)
+    assert float(x.grad.abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("mode", ["0", "1"], ids=["64-points-per-lane", "even-odd"])
+@pytest.mark.parametrize("name", ["gauss_b2_t4800", "silence_b3_t6000"])
+def test_both_2048_routes_match_reference(emu_engine, monkeypatch, name, mode):
+    """The product default sends the 2048-point mel loss down the even/odd route and the 2048-point STFT loss down the
+    64-point-per-lane route; both kernels exist for both losses (SPECLOSS_EO_2048 = 0 | mel | 1) and must all meet the
+    reference (the golden-vector tests above cover the default mix)."""
+    monkeypatch.setenv("SPECLOSS_EO_2048", mode)
+    g = load_golden(name)
+    vals, grad = run_losses(emu_engine, g)
+    for i in range(3):
+        assert abs(vals[i] - g["loss64"][i]) <= LOSS_RTOL * max(abs(g["loss64"][i]), 1e-12)
+    assert rel_l2(grad.reshape(g["grad64"].shape), g["grad64"]) <= GRAD_RTOL
