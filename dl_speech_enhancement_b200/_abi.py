@@ -15,7 +15,7 @@ from ctypes import POINTER, c_char_p, c_float, c_int32, c_int64, c_void_p
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libspecloss.so")
 CSRC = os.path.join(_HERE, "csrc")
-ABI_VERSION = 14
+ABI_VERSION = 15
 
 SPL_KIND_STFT = 0
 SPL_KIND_MEL = 1
@@ -51,7 +51,7 @@ EXPORTS = ("spl_abi_version", "spl_last_error", "spl_fill_twiddle", "spl_fill_tw
            "spl_reduce", "spl_finalize", "spl_reduce_finalize", "spl_exchange_buffer_bytes", "spl_reduce_exchange_finalize", "spl_backward", "spl_spectrogram", "spl_spectrogram_backward", "spl_mel_project",
            "spl_shape_geometry", "spl_shape_forward", "spl_shape_finalize", "spl_shape_backward",
            "spl_mag_loss_geometry", "spl_mag_loss_forward", "spl_mag_loss_backward",
-           "spl_melpow_geometry", "spl_melpow_l1")
+           "spl_melpow_geometry", "spl_melpow_l1", "spl_loss_forward", "spl_loss_backward")
 
 
 class SpecLossError(RuntimeError):
@@ -120,6 +120,13 @@ def bind(lib: ctypes.CDLL) -> ctypes.CDLL:
     lib.spl_melpow_l1.restype = c_int32
     lib.spl_melpow_l1.argtypes = [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_int32, c_int32,
                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.spl_loss_forward.restype = c_int32
+    lib.spl_loss_forward.argtypes = [POINTER(SplTransform), c_int32, c_void_p, c_void_p, c_int32, c_int32, c_void_p,
+                                     POINTER(c_int64), POINTER(c_int64), c_int64, c_int64, c_void_p, c_void_p, c_void_p,
+                                     c_void_p, c_void_p]
+    lib.spl_loss_backward.restype = c_int32
+    lib.spl_loss_backward.argtypes = [POINTER(SplTransform), c_int32, c_int32, c_int32, c_void_p, POINTER(c_int64), c_int64,
+                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     ver = lib.spl_abi_version()
     if ver != ABI_VERSION:
         raise SpecLossError(f"libspecloss ABI version {ver}, expected {ABI_VERSION}")

@@ -6,6 +6,7 @@
 #include "melpower.cuh"
 #include "transform_eo.cuh"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>

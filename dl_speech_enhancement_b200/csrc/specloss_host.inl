@@ -82,9 +82,81 @@ int warp_words(int n_fft, int kind, int n_mels) {
                        : spl::SmemLayout<2048, spl::kKindMel>::words_per_warp(n_mels);
 }
 
-long long warp_items(const spl_transform* t, int B, int T) {       // frames / frames in flight per warp
+// ---- launch plan of one transform over (B, T): geometry, resident warps and -- STFT loss with gradient -- how many
+// consecutive frames a warp overlap-adds in shared memory before the gradient leaves the SM (run_frames) -----------
+struct LaunchPlan {
+  int grid, wpc;
+  int run_frames, runs_per_utt, run_len;
+  long long items;               // warp work items
+  size_t table_bytes, warp_bytes;
+};
+
+// SPECLOSS_RUN_FRAMES: unset / 1 = one gradient slot per frame (the default), k >= 2 = runs of k frames overlap-added in
+// shared memory, 0 = choose by size.  Measured on B200 (profiles/r3j_ring.txt, 256 x 4 s): runs of 16 cut the gather from
+// 335 to 127 us per STFT resolution and the workspace 3.6x, but the transform kernels pay for the ring traffic (1024: +174 us,
+// 512: +224 us; 2048 loses 4 of its 12 resident warps to the ring and doubles) -- break-even at best, so it stays an
+// option for memory-bound deployments rather than the default.
+int run_frames_from_env() {
+  const char* e = std::getenv("SPECLOSS_RUN_FRAMES");
+  return e ? std::atoi(e) : 1;
+}
+int run_frames_request() {
+#ifdef SPECLOSS_EMU
+  return run_frames_from_env();       // the test-suite switches between calls
+#else
+  static const int v = run_frames_from_env();
+  return v;
+#endif
+}
+
+// Device-independent part of the plan (spl_geometry_of() must work without a GPU): shared-memory footprint and the run
+// length.  The run rule is written for the one device this library targets (B200: 148 SMs).
+constexpr int kNominalSms = 148;
+
+void plan_static(const spl_transform* t, int B, int T, bool grad, LaunchPlan* lp) {
   const int fpw = frames_in_flight(t->n_fft);
-  return ((long long)B * (1 + T / t->hop) + fpw - 1) / fpw;
+  const int n_frames = 1 + T / t->hop;
+  const bool eo = use_eo(t);
+  size_t table_bytes, warp_bytes;
+  if (eo) {
+    table_bytes = (size_t)spl::cta_tables_eo(t->win, t->kind, t->mel_rounds, t->mel_entry_rows).total * 4;
+    warp_bytes = (size_t)spl::eo_words_per_warp(t->kind, t->n_mels) * 4;
+  } else {
+    table_bytes = (size_t)spl::cta_tables(t->n_fft, t->win, t->kind, t->mel_rounds, t->mel_entry_rows).total * 4;
+    warp_bytes = (size_t)warp_words(t->n_fft, t->kind, t->n_mels) * 4;
+  }
+  lp->grid = lp->wpc = 0;
+  lp->run_frames = 1; lp->runs_per_utt = n_frames; lp->run_len = t->win;
+  lp->table_bytes = table_bytes; lp->warp_bytes = warp_bytes;
+  lp->items = ((long long)B * n_frames + fpw - 1) / fpw;
+  if (!grad || t->kind != SPL_KIND_STFT || eo) return;
+  // Runs: the gradient of a run of m frames is (m - 1) hop + win taps instead of m win.  Worth it when the per-frame
+  // slots no longer fit the L2 (they then make a round trip through HBM) and only while every resident warp still gets
+  // several runs; the ring costs win * 8 bytes of shared memory per frame in flight.
+  const size_t ring_bytes = (size_t)fpw * 8 * ((t->win + 1) & ~1);
+  const int want = run_frames_request();
+  if (want == 1 || table_bytes + warp_bytes + ring_bytes > 227 * 1024) return;
+  const int reg_warps = t->n_fft == 2048 ? 12 : 16;                              // MaxWarps<NFFT> of the kernels
+  const int smem_warps = (int)((227 * 1024 - table_bytes) / (warp_bytes + ring_bytes));
+  const long long dev_warps = (long long)kNominalSms * (smem_warps < reg_warps ? smem_warps : reg_warps);
+  const bool big = (long long)B * n_frames * t->win * 8 > (48ll << 20);          // slots of this transform vs the L2
+  const int cand[4] = {16, 8, 4, 2};
+  for (int c = 0; c < 4; ++c) {
+    const int m = want >= 2 ? want : cand[c];
+    if (m > n_frames) { if (want >= 2) break; continue; }
+    const int runs = (n_frames + m - 1) / m;
+    const long long items = ((long long)B * runs + fpw - 1) / fpw;
+    if (want >= 2 || (big && items >= 4 * dev_warps)) {
+      lp->run_frames = m; lp->runs_per_utt = runs; lp->run_len = (m - 1) * t->hop + t->win;
+      lp->items = items; lp->warp_bytes = warp_bytes + ring_bytes;
+      return;
+    }
+  }
+}
+
+int plan_transform(const spl_transform* t, int B, int T, bool grad, LaunchPlan* lp) {
+  plan_static(t, B, T, grad, lp);
+  return spl_launch_shape(t->n_fft, lp->table_bytes, lp->warp_bytes, lp->items, &lp->grid, &lp->wpc);
 }
 
 void geometry(const spl_transform* t, int B, int T, spl_geometry* g) {
@@ -92,29 +164,26 @@ void geometry(const spl_transform* t, int B, int T, spl_geometry* g) {
   g->n_frames = 1 + T / t->hop;
   g->n_bins = t->n_fft / 2 + 1;
   g->n_sums = t->kind == SPL_KIND_STFT ? 3 : 1;
-  const long long items = warp_items(t, B, T);
+  LaunchPlan fwd, grd;
+  plan_static(t, B, T, false, &fwd);
+  plan_static(t, B, T, true, &grd);
   // one row per warp of the launch: grid * wpc < items + wpc (the last CTA may hold idle warps, which still write a
-  // row of zeros), wpc <= 32
+  // row of zeros), wpc <= 32; the forward-only launch (frames) has at least as many items as the gradient launch (runs)
+  const long long items = fwd.items > grd.items ? fwd.items : grd.items;
   g->partial_count = (int64_t)((items < kMaxPartialRows ? items : kMaxPartialRows) + 32) * g->n_sums;
-  g->gframe_bytes = (int64_t)B * g->n_frames * t->win * (t->kind == SPL_KIND_STFT ? 8 : 4);
-  if (use_eo(t)) {
-    g->smem_table_bytes = (int64_t)spl::cta_tables_eo(t->win, t->kind, t->mel_rounds, t->mel_entry_rows).total * 4;
-    g->smem_warp_bytes = (int64_t)spl::eo_words_per_warp(t->kind, t->n_mels) * 4;
-    return;
-  }
-  const spl::CtaTables ct = spl::cta_tables(t->n_fft, t->win, t->kind, t->mel_rounds, t->mel_entry_rows);
-  g->smem_table_bytes = (int64_t)ct.total * 4;
-  g->smem_warp_bytes = (int64_t)warp_words(t->n_fft, t->kind, t->n_mels) * 4;
+  g->gframe_bytes = (int64_t)B * grd.runs_per_utt * grd.run_len * (t->kind == SPL_KIND_STFT ? 8 : 4);
+  g->smem_table_bytes = (int64_t)grd.table_bytes;
+  g->smem_warp_bytes = (int64_t)grd.warp_bytes;
 }
 
-// CTAs x warps of the launch of transform t over (B, T)
-int shape_of(const spl_transform* t, int B, int T, int* grid, int* wpc) {
-  spl_geometry g;
-  geometry(t, B, T, &g);
-  int rc = spl_launch_shape(t->n_fft, (size_t)g.smem_table_bytes, (size_t)g.smem_warp_bytes, warp_items(t, B, T), grid, wpc);
+// CTAs x warps of the launch of transform t over (B, T); grad = the launch that also writes the gradient
+int shape_of(const spl_transform* t, int B, int T, bool grad, int* grid, int* wpc) {
+  LaunchPlan lp;
+  int rc = plan_transform(t, B, T, grad, &lp);
   if (rc) return rc;
-  if ((long long)*grid * *wpc * g.n_sums > g.partial_count)
-    return fail(SPL_E_INVALID, "launch of %d x %d warps exceeds the %lld partial-sum rows", *grid, *wpc, (long long)(g.partial_count / g.n_sums));
+  *grid = lp.grid; *wpc = lp.wpc;
+  if ((long long)lp.grid * lp.wpc > kMaxPartialRows + 32)
+    return fail(SPL_E_INVALID, "launch of %d x %d warps exceeds the partial-sum rows", lp.grid, lp.wpc);
   return SPL_OK;
 }
 
@@ -229,25 +298,26 @@ int32_t spl_forward(const spl_transform* ts, int32_t n, const float* x, const fl
   if (rc) return rc;
   for (int i = 0; i < n; ++i) {
     const spl_transform* t = ts + order[i];
-    spl_geometry g;
-    geometry(t, B, T, &g);
-    int grid = 0, wpc = 0;
-    rc = shape_of(t, B, T, &grid, &wpc);
+    LaunchPlan lp;
+    const bool grad = t->gframes != nullptr;
+    rc = plan_transform(t, B, T, grad, &lp);
     if (rc) break;
+    const int grid = lp.grid, wpc = lp.wpc;
     spl::TransformParams p;
     std::memset(&p, 0, sizeof(p));
     p.x = x; p.y = y; p.B = B; p.T = T;
     p.hop = t->hop; p.win = t->win; p.left = (t->n_fft - t->win) / 2;
-    p.n_frames = g.n_frames;
+    p.n_frames = 1 + T / t->hop;
     p.eps = t->eps; p.window = t->window; p.twiddle = reinterpret_cast<const float2*>(t->twiddle);
     p.partials = t->partials; p.gframes = t->gframes;
+    p.run_frames = lp.run_frames; p.runs_per_utt = lp.runs_per_utt; p.run_len = lp.run_len;
     p.n_mels = t->kind == SPL_KIND_MEL ? t->n_mels : 0;
     p.inv_ln_base = t->inv_ln_base;
     p.mel_tasks = t->mel_tasks; p.mel_entries = t->mel_entries;
     p.mel_rounds = t->kind == SPL_KIND_MEL ? t->mel_rounds : 0;
     p.mel_entry_rows = t->kind == SPL_KIND_MEL ? t->mel_entry_rows : 0;
     p.bin_tab = t->bin_tab;
-    const size_t smem = (size_t)g.smem_table_bytes + (size_t)g.smem_warp_bytes * wpc;
+    const size_t smem = lp.table_bytes + lp.warp_bytes * wpc;
     rc = use_eo(t) ? launch_eo(p, t, t->gframes != nullptr, grid, wpc, smem, streams[i])
                    : launch_any(p, t->n_fft, t->kind, t->gframes != nullptr, grid, wpc, smem, streams[i]);
     if (rc) break;
@@ -370,7 +440,7 @@ static int build_reduce(const spl_transform* ts, int n, int B, int T, double* su
     if (rc) return rc;
     if (!ts[r].partials) return fail(SPL_E_INVALID, "transform %d: null partials", r);
     int grid = 0, wpc = 0;
-    rc = shape_of(ts + r, B, T, &grid, &wpc);
+    rc = shape_of(ts + r, B, T, ts[r].gframes != nullptr, &grid, &wpc);
     if (rc) return rc;
     const int n_sums = ts[r].kind == SPL_KIND_STFT ? 3 : 1;
     for (int j = 0; j < n_sums; ++j) {
@@ -472,12 +542,55 @@ int32_t spl_backward(const spl_transform* ts, int32_t n, int32_t B, int32_t T, c
     if (rc) return rc;
     if (!ts[r].gframes) return fail(SPL_E_INVALID, "transform %d: forward ran without gradient workspace", r);
     spl::CombineEntry& e = cp.e[r];
-    e.frames = ts[r].gframes; e.kind = ts[r].kind; e.half = ts[r].n_fft / 2; e.hop = ts[r].hop; e.win = ts[r].win;
-    e.left = (ts[r].n_fft - ts[r].win) / 2; e.n_frames = 1 + T / ts[r].hop;
+    LaunchPlan lp;
+    plan_static(ts + r, B, T, true, &lp);
+    // runs look to the gather like long frames: hop = run_frames * hop, win = run_len, one "frame" per run
+    e.frames = ts[r].gframes; e.kind = ts[r].kind; e.half = ts[r].n_fft / 2;
+    e.hop = ts[r].hop * lp.run_frames; e.win = lp.run_len;
+    e.left = (ts[r].n_fft - ts[r].win) / 2; e.n_frames = lp.runs_per_utt;
     e.planar = (ts[r].kind == SPL_KIND_STFT && use_eo(ts + r)) ? 1 : 0;
   }
   cp.coefs = coefs; cp.g_sc = g_sc; cp.g_mag = g_mag; cp.g_mel = g_mel; cp.dx = dx; cp.B = B; cp.T = T;
   return spl_launch_combine(cp, stream);
+}
+
+// ---- one call per direction (the unchanged-trainer path is host-bound at small batches: trainerGAN.py:214-241 launches
+// eagerly) -- the transforms are a per-recipe TEMPLATE (tables filled in, partials / gframes NULL); the per-call workspace
+// is one buffer carved up by byte offsets the caller computed once from spl_geometry_of().
+static int place_transforms(const spl_transform* ts, int n, void* ws, const int64_t* off_partials, const int64_t* off_gframes,
+                            spl_transform* out) {
+  if (n < 1 || n > SPL_MAX_TRANSFORMS) return fail(SPL_E_INVALID, "n=%d transforms not in [1,%d]", n, SPL_MAX_TRANSFORMS);
+  if (!ts || !ws) return fail(SPL_E_INVALID, "null transforms / workspace");
+  char* base = static_cast<char*>(ws);
+  for (int r = 0; r < n; ++r) {
+    out[r] = ts[r];
+    out[r].partials = off_partials ? reinterpret_cast<double*>(base + off_partials[r]) : nullptr;
+    out[r].gframes = off_gframes ? static_cast<void*>(base + off_gframes[r]) : nullptr;
+  }
+  return SPL_OK;
+}
+
+int32_t spl_loss_forward(const spl_transform* ts, int32_t n, const float* x, const float* y, int32_t B, int32_t T,
+                         void* ws, const int64_t* off_partials, const int64_t* off_gframes, int64_t off_sums,
+                         int64_t off_coefs, float* sc, float* mag, float* mel, uint32_t* counter, void* stream) {
+  if (!off_partials) return fail(SPL_E_INVALID, "spl_loss_forward: null partial-sum offsets");
+  spl_transform local[SPL_MAX_TRANSFORMS];
+  int rc = place_transforms(ts, n, ws, off_partials, off_gframes, local);
+  if (rc) return rc;
+  rc = spl_forward(local, n, x, y, B, T, stream);
+  if (rc) return rc;
+  char* base = static_cast<char*>(ws);
+  return spl_reduce_finalize(local, n, B, T, reinterpret_cast<double*>(base + off_sums), sc, mag, mel,
+                             reinterpret_cast<float*>(base + off_coefs), counter, stream);
+}
+
+int32_t spl_loss_backward(const spl_transform* ts, int32_t n, int32_t B, int32_t T, void* ws, const int64_t* off_gframes,
+                          int64_t off_coefs, const float* g_sc, const float* g_mag, const float* g_mel, float* dx, void* stream) {
+  if (!off_gframes) return fail(SPL_E_INVALID, "spl_loss_backward: forward ran without gradient workspace");
+  spl_transform local[SPL_MAX_TRANSFORMS];
+  int rc = place_transforms(ts, n, ws, nullptr, off_gframes, local);
+  if (rc) return rc;
+  return spl_backward(local, n, B, T, reinterpret_cast<const float*>(static_cast<char*>(ws) + off_coefs), g_sc, g_mag, g_mel, dx, stream);
 }
 
 // ---- waveform shape loss (losses/waveform_loss.py) ---------------------------------------------------------------

@@ -109,7 +109,14 @@ struct TransformParams {
   const float* window;   // win taps
   const float2* twiddle; // [R][L] : W_N^(n1*k2) at [k2 * L + n1]
   double* partials;      // [grid * warps per CTA][n_sums] : one row per warp
-  void* gframes;         // [B * n_frames][win] float2 (stft: u = sc part, v = log-mag part) | float (mel)
+  void* gframes;         // [B * n_frames][win] float2 (stft: u = sc part, v = log-mag part) | float (mel);
+                         // run_frames > 1: [B * runs_per_utt][run_len] float2, the frames of a run overlap-added
+  // Overlap-add in shared memory before the gradient leaves the SM (STFT loss, large batches): a warp takes a RUN of
+  // run_frames consecutive frames of one utterance, accumulates their windowed gradients in a ring of `win` taps and
+  // writes every sample of the run once: (run_frames - 1) * hop + win taps per run instead of run_frames * win.
+  int run_frames;        // 1: one gradient slot per frame (no ring)
+  int runs_per_utt;      // ceil(n_frames / run_frames)
+  int run_len;           // (run_frames - 1) * hop + win
   // mel only
   int n_mels;
   float inv_ln_base;     // 1 / ln(log_base)  (1 for natural log)
@@ -157,10 +164,12 @@ static __host__ __device__ inline CtaTables cta_tables(int n_fft, int win, int k
 template <int NFFT, int KIND>
 struct SmemLayout {
   using G = Geo<NFFT>;
-  static __host__ __device__ int words_per_warp(int n_mels) {
+  // ring_taps: window taps of the overlap-add ring (0 = none), one ring of float2 per frame in flight
+  static __host__ __device__ int words_per_warp(int n_mels, int ring_taps = 0) {
     int w = G::FPW * G::SLOT_F2 * 2;
     if (KIND == kKindMel) w += G::FPW * 2 * ((n_mels + 3) & ~3);
-    return (w + 3) & ~3;
+    w = (w + 3) & ~3;
+    return w + G::FPW * 2 * ((ring_taps + 1) & ~1);
   }
 };
 
@@ -605,13 +614,22 @@ SPL_DEVICE void transform_body(const TransformParams& p, float* smem, int block,
   const int2* mel_entries = reinterpret_cast<const int2*>(smem + ct.entries);
   const int4* bin_tab = reinterpret_cast<const int4*>(smem + ct.bintab);
 
-  float* wsm = smem + ct.total + (size_t)warp * SL::words_per_warp(p.n_mels);
+  const int m = (GRAD && KIND == kKindStft) ? p.run_frames : 1;       // frames per run (1: one gradient slot per frame)
+  const bool ring_on = m > 1;
+  const int ring_taps = ring_on ? win : 0;
+  float* wsm = smem + ct.total + (size_t)warp * SL::words_per_warp(p.n_mels, ring_taps);
   float2* S = reinterpret_cast<float2*>(wsm) + h * G::SLOT_F2;                       // this group's frame slot
   float2* msum = reinterpret_cast<float2*>(wsm + FPW * G::SLOT_F2 * 2) + h * align4(p.n_mels);   // mel: (Mx, My), then (gM, -)
+  float2* ring = reinterpret_cast<float2*>(wsm + SL::words_per_warp(p.n_mels, 0)) + h * ((ring_taps + 1) & ~1);
 
-  const int total = p.B * p.n_frames;
+  const int per_utt = ring_on ? p.runs_per_utt : p.n_frames;     // work items per utterance: runs or frames
+  const int total = p.B * per_utt;
   const unsigned grp_mask = (L == 32) ? 0xffffffffu : (((1u << (L & 31)) - 1u) << (h * L));
   double d1 = 0.0, d2 = 0.0, d3 = 0.0;      // this lane's share of the sums (stft: 4*S1, 4*S2, S3/(0.5 ln 2); mel: S4)
+  if (ring_on) {
+    for (int i = l; i < win; i += L) ring[i] = make_float2(0.f, 0.f);      // every flush leaves its taps at zero again
+    __syncwarp();
+  }
 
   // [region: frame loop]
   constexpr bool CTA_SYNC = SPL_SYNC_2048 && NFFT == 2048;
@@ -622,9 +640,15 @@ SPL_DEVICE void transform_body(const TransformParams& p, float* smem, int block,
     if (CTA_SYNC) __syncthreads();
     if (base >= total) continue;
     const int item = base + h;
-    const bool active = item < total;
-    const int b = active ? item / p.n_frames : 0;
-    const int t = active ? item - b * p.n_frames : 0;
+    const bool item_ok = item < total;
+    const int b = item_ok ? item / per_utt : 0;
+    const int t0 = item_ok ? (item - b * per_utt) * m : 0;
+    int start = 0;                 // ring position of tap 0 of the current frame
+    int done = 0;                  // frames of this run added to the ring so far
+    for (int j = 0; j < m; ++j) {
+    const int t = t0 + j;
+    const bool active = item_ok && t < p.n_frames;
+    if (FPW == 1 && !active) break;                    // warp-uniform: the last run of an utterance is shorter
     float s1 = 0.f, s2 = 0.f, s3 = 0.f;
     // Two phases share ONE copy of the R-point codelet: 0 = forward transform + epilogue (+ first half of the
     // inverse), 1 = second half of the inverse + windowed store.
@@ -662,12 +686,14 @@ SPL_DEVICE void transform_body(const TransformParams& p, float* smem, int block,
         }
         if (active) { d1 += (double)s1; d2 += (double)s2; d3 += (double)s3; }
         if (GRAD) inv_pass_b<NFFT>(A, Sr, tw, lr);
-      } else if (active) {
+      } else if (!ring_on) {
+        if (active) {
         // [region: window + store]
         // v[n2] = sample n = l + L*n2 of the two real gradient sequences with swapped components: (.y, .x) = (u, v).
         // Windowed frame gradient -> this frame's slot in HBM (coalesced; one writer per element).
-        float2* out2 = reinterpret_cast<float2*>(p.gframes) + (size_t)item * win;
-        float* out1 = reinterpret_cast<float*>(p.gframes) + (size_t)item * win;
+        const int fidx = b * p.n_frames + t;
+        float2* out2 = reinterpret_cast<float2*>(p.gframes) + (size_t)fidx * win;
+        float* out1 = reinterpret_cast<float*>(p.gframes) + (size_t)fidx * win;
         const float* wp = wtab + (l - left);
 #pragma unroll
         for (int n2 = 0; n2 < R; ++n2) {
@@ -680,7 +706,57 @@ SPL_DEVICE void transform_body(const TransformParams& p, float* smem, int block,
             else                   out1[lo + l] = v[n2].y * w;
           }
         }
+        }
+      } else {
+        // [region: window + ring]
+        // Overlap-add into the ring: tap n of frame j of the run sits at ring position (j * hop + n) mod win.
+        if (active) {
+          const float* wp = wtab + (l - left);
+#pragma unroll
+          for (int n2 = 0; n2 < R; ++n2) {
+            const int lo = L * n2 - left;
+            if (WIN_T > 0 && (lo + L - 1 < 0 || lo >= WIN_T)) continue;
+            const bool all_lanes = WIN_T > 0 && lo >= 0 && lo + L - 1 < WIN_T;
+            if (all_lanes || (lo + l >= 0 && lo + l < win)) {
+              const float w = wp[L * n2];
+              int idx = start + lo + l;
+              idx = idx >= win ? idx - win : idx;
+              ring[idx] = __ffma2_rn(make_float2(v[n2].y, v[n2].x), make_float2(w, w), ring[idx]);
+            }
+          }
+        }
+        __syncwarp();
+        // the first `hop` taps of this frame are final: no later frame of the run reaches them
+        if (active) {
+          float2* out2 = reinterpret_cast<float2*>(p.gframes) + (size_t)item * p.run_len + (size_t)done * p.hop;
+          for (int i = l; i < p.hop; i += L) {
+            int idx = start + i;
+            idx = idx >= win ? idx - win : idx;
+            out2[i] = ring[idx];
+            ring[idx] = make_float2(0.f, 0.f);
+          }
+          start += p.hop;
+          start = start >= win ? start - win : start;
+          done += 1;
+        }
       }
+    }
+    }
+    if (ring_on) {
+      // end of the run: the remaining win - hop taps of its last frame, then zeros up to run_len (a short last run)
+      __syncwarp();
+      if (item_ok && done > 0) {
+        float2* out2 = reinterpret_cast<float2*>(p.gframes) + (size_t)item * p.run_len + (size_t)done * p.hop;
+        const int rest = win - p.hop;
+        for (int i = l; i < rest; i += L) {
+          int idx = start + i;
+          idx = idx >= win ? idx - win : idx;
+          out2[i] = ring[idx];
+          ring[idx] = make_float2(0.f, 0.f);
+        }
+        for (int i = done * p.hop + rest + l; i < p.run_len; i += L) out2[i - done * p.hop] = make_float2(0.f, 0.f);
+      }
+      __syncwarp();
     }
   }
 

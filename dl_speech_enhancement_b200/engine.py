@@ -285,19 +285,36 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
 
 
 class ForwardState:
-    """What backward needs: the ctypes transform array (pointers into the workspace kept alive here)."""
-    __slots__ = ("transforms", "n", "keep", "batch", "t_len", "has_grad", "sc", "mag", "mel", "n_launches",
-                 "ws", "off_sums", "off_coefs", "n_sums", "coefs_ptr", "device")
+    """What backward needs: the recipe (template transforms + workspace offsets) and the workspace address."""
+    __slots__ = ("rec", "n", "keep", "batch", "t_len", "has_grad", "sc", "mag", "mel", "n_launches",
+                 "ws", "ws_ptr", "off_sums", "off_coefs", "n_sums", "coefs_ptr", "device", "_transforms")
 
     def __init__(self):
-        self.transforms = None
+        self.rec = None
+        self._transforms = None
         self.n = 0
         self.keep = None
         self.ws = None
+        self.ws_ptr = 0
         self.batch = self.t_len = 0
         self.has_grad = False
         self.sc = self.mag = self.mel = None
         self.n_launches = 0
+
+    @property
+    def transforms(self):
+        """The spl_transform array of THIS call (template + pointers into this call's workspace), for the multi-step entry
+        points (spl_reduce / spl_finalize / spl_reduce_exchange_finalize / spl_backward).  Built on first use: the
+        unsharded path never needs it (spl_loss_forward / spl_loss_backward place the workspace themselves)."""
+        if self._transforms is None:
+            rec, n = self.rec, self.n
+            arr = (SplTransform * n)()
+            ctypes.memmove(arr, rec.template, rec.nbytes)
+            for i in range(n):
+                arr[i].partials = self.ws_ptr + rec.off_partials[i]
+                arr[i].gframes = self.ws_ptr + rec.off_gframes[i] if self.has_grad else None
+            self._transforms = arr
+        return self._transforms
 
     def detach_workspace(self) -> torch.Tensor:
         """Hands the workspace tensor over to the caller (the autograd function saves it with save_for_backward, which
@@ -325,7 +342,8 @@ class _Recipe:
     """Everything about a (plan list, batch shape, grad mode) that does not change from call to call:
     the filled ctypes transform array and the carve-up of the single per-call workspace buffer."""
     __slots__ = ("template", "nbytes", "n", "off_partials", "off_gframes", "off_sums", "off_coefs", "ws_bytes",
-                 "n_sums", "has_stft", "has_mel", "keep", "off_lsums", "serial", "plan_refs")
+                 "n_sums", "has_stft", "has_mel", "keep", "off_lsums", "serial", "plan_refs", "c_off_partials",
+                 "c_off_gframes", "counter_ptr")
 
 
 class Engine:
@@ -492,8 +510,11 @@ class Engine:
         rec.has_stft = any(p.kind == SPL_KIND_STFT for p in plans)
         rec.has_mel = any(p.kind == SPL_KIND_MEL for p in plans)
         rec.template, rec.nbytes = arr, ctypes.sizeof(arr)
+        rec.c_off_partials = (ctypes.c_int64 * n)(*rec.off_partials)
+        rec.c_off_gframes = (ctypes.c_int64 * n)(*rec.off_gframes) if need_grad else None
         self._recipe_serial += 1
         rec.serial = self._recipe_serial       # same on every rank (SPMD): names the recipe's peer-exchange buffers
+        rec.counter_ptr = self._counter_ptr(dev, rec.serial)
         if len(self._recipes) > 64:
             self._evict()
         self._recipes[key] = rec
@@ -513,53 +534,58 @@ class Engine:
         n = rec.n
         ws = torch.empty(rec.ws_bytes, dtype=torch.uint8, device=dev)
         base = ws.data_ptr()
-        arr = (SplTransform * n)()
-        ctypes.memmove(arr, rec.template, rec.nbytes)
-        for i in range(n):
-            arr[i].partials = base + rec.off_partials[i]
-            arr[i].gframes = base + rec.off_gframes[i] if need_grad else None
         st = ForwardState()
-        st.batch, st.t_len, st.has_grad, st.n, st.transforms = batch, t_len, need_grad, n, arr
+        st.rec, st.ws_ptr = rec, base
+        st.batch, st.t_len, st.has_grad, st.n = batch, t_len, need_grad, n
         st.keep = (ws, rec.keep)
         # separate 0-dim outputs: callers scale them in place (trainer/trainerGAN.py:221,228-229)
-        st.sc = torch.empty((), dtype=torch.float32, device=dev) if rec.has_stft else None
-        st.mag = torch.empty((), dtype=torch.float32, device=dev) if rec.has_stft else None
-        st.mel = torch.empty((), dtype=torch.float32, device=dev) if rec.has_mel else None
+        if rec.has_stft:
+            st.sc = torch.empty((), dtype=torch.float32, device=dev)
+            st.mag = torch.empty((), dtype=torch.float32, device=dev)
+        if rec.has_mel:
+            st.mel = torch.empty((), dtype=torch.float32, device=dev)
         st.ws, st.off_sums, st.off_coefs, st.n_sums, st.device = ws, rec.off_sums, rec.off_coefs, rec.n_sums, dev
         st.coefs_ptr = base + rec.off_coefs
         stream = self._stream(x)
         lib = self.lib
+        if group is None and (global_batch is None or global_batch == batch):
+            # unsharded: transforms + reduce + finalize behind ONE C-ABI call
+            counter = rec.counter_ptr
+            rc = lib.spl_loss_forward(rec.template, n, x.data_ptr(), y.data_ptr(), batch, t_len, base, rec.c_off_partials,
+                                      rec.c_off_gframes, rec.off_sums, rec.off_coefs, _ptr(st.sc), _ptr(st.mag), _ptr(st.mel),
+                                      counter, stream)
+            if rc:
+                _abi.check(lib, rc)
+            st.n_launches = n + 1
+            self.launches += st.n_launches
+            return st
+        arr = st.transforms
         _abi.check(lib, lib.spl_forward(arr, n, x.data_ptr(), y.data_ptr(), batch, t_len, stream))
         sums_ptr, coefs_ptr = base + rec.off_sums, base + rec.off_coefs
-        if group is None and (global_batch is None or global_batch == batch):
-            _abi.check(lib, lib.spl_reduce_finalize(arr, n, batch, t_len, sums_ptr, _ptr(st.sc), _ptr(st.mag),
-                                                    _ptr(st.mel), coefs_ptr, self._counter_ptr(dev, rec.serial), stream))
+        ex = self._exchange(group, dev, rec.serial) if group is not None else None
+        if ex is not None:
+            if ex["timeout_ns"] > 0:
+                self.check_exchange_errors()
+            # reduce + NVLink peer-memory exchange + finalize in one launch (spl_reduce_exchange_finalize)
+            if global_batch is None:
+                global_batch = batch * ex["world"]
+            lsums_ptr = base + rec.off_lsums
+            _abi.check(lib, lib.spl_reduce_exchange_finalize(
+                arr, n, batch, t_len, int(global_batch), lsums_ptr, sums_ptr, ex["rank"], ex["world"],
+                ex["ptrs"], ex["state"].data_ptr(), ex["timeout_ns"], ex["err"].data_ptr(),
+                _ptr(st.sc), _ptr(st.mag), _ptr(st.mel), coefs_ptr, stream))
+            st.keep = st.keep + (ex,)
             st.n_launches = n + 1
         else:
-            ex = self._exchange(group, dev, rec.serial) if group is not None else None
-            if ex is not None:
-                if ex["timeout_ns"] > 0:
-                    self.check_exchange_errors()
-                # reduce + NVLink peer-memory exchange + finalize in one launch (spl_reduce_exchange_finalize)
+            _abi.check(lib, lib.spl_reduce(arr, n, batch, t_len, sums_ptr, stream))
+            if group is not None:
+                import torch.distributed as dist
+                dist.all_reduce(st.sums, op=dist.ReduceOp.SUM, group=group)   # the single exchange step
                 if global_batch is None:
-                    global_batch = batch * ex["world"]
-                lsums = ws[rec.off_lsums:rec.off_lsums + 8 * rec.n_sums]
-                _abi.check(lib, lib.spl_reduce_exchange_finalize(
-                    arr, n, batch, t_len, int(global_batch), lsums.data_ptr(), sums_ptr, ex["rank"], ex["world"],
-                    ex["ptrs"], ex["state"].data_ptr(), ex["timeout_ns"], ex["err"].data_ptr(),
-                    _ptr(st.sc), _ptr(st.mag), _ptr(st.mel), coefs_ptr, stream))
-                st.keep = st.keep + (ex,)
-                st.n_launches = n + 1
-            else:
-                _abi.check(lib, lib.spl_reduce(arr, n, batch, t_len, sums_ptr, stream))
-                if group is not None:
-                    import torch.distributed as dist
-                    dist.all_reduce(st.sums, op=dist.ReduceOp.SUM, group=group)   # the single exchange step
-                    if global_batch is None:
-                        global_batch = batch * dist.get_world_size(group)
-                _abi.check(lib, lib.spl_finalize(arr, n, sums_ptr, int(global_batch), t_len, _ptr(st.sc), _ptr(st.mag),
-                                                 _ptr(st.mel), coefs_ptr, stream))
-                st.n_launches = n + 2
+                    global_batch = batch * dist.get_world_size(group)
+            _abi.check(lib, lib.spl_finalize(arr, n, sums_ptr, int(global_batch), t_len, _ptr(st.sc), _ptr(st.mag),
+                                             _ptr(st.mel), coefs_ptr, stream))
+            st.n_launches = n + 2
         self.launches += st.n_launches
         return st
 
@@ -756,9 +782,11 @@ class Engine:
             return g
 
         gs = (scalar(g_sc), scalar(g_mag), scalar(g_mel))
-        _abi.check(self.lib, self.lib.spl_backward(st.transforms, st.n, st.batch, st.t_len, st.coefs_ptr,
-                                                   _ptr(gs[0]), _ptr(gs[1]), _ptr(gs[2]), dx.data_ptr(),
-                                                   self._stream(dx)))
+        rec = st.rec
+        rc = self.lib.spl_loss_backward(rec.template, st.n, st.batch, st.t_len, st.ws_ptr, rec.c_off_gframes, rec.off_coefs,
+                                        _ptr(gs[0]), _ptr(gs[1]), _ptr(gs[2]), dx.data_ptr(), self._stream(dx))
+        if rc:
+            _abi.check(self.lib, rc)
         self.launches += 1
         return dx
 

@@ -41,7 +41,7 @@ class _SpectralLossFn(torch.autograd.Function):
     def forward(ctx, x, y, plans, engine, group, global_batch):
         x2, y2 = _as_2d(x, "prediction"), _as_2d(y, "target")
         need_grad = ctx.needs_input_grad[0]
-        st = engine.forward(plans, x2.detach(), y2.detach(), need_grad, group, global_batch)
+        st = engine.forward(plans, x2, y2, need_grad, group, global_batch)      # only shapes and addresses are read
         if need_grad:
             # The gradient workspace travels as a SAVED TENSOR: autograd frees it right after backward() unless the
             # caller asked for retain_graph=True (then a second backward works, as with the reference's graph), and a

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SPL_ABI_VERSION 14
+#define SPL_ABI_VERSION 15
 
 #define SPL_OK 0
 #define SPL_E_INVALID (-1)   /* bad argument / outside the supported envelope */
@@ -133,6 +133,17 @@ int32_t spl_reduce_exchange_finalize(const spl_transform* ts, int32_t n, int32_t
  * the reference modules.  g_* are device scalars (NULL = 0). */
 int32_t spl_backward(const spl_transform* ts, int32_t n, int32_t B, int32_t T, const float* coefs,
                      const float* g_sc, const float* g_mag, const float* g_mel, float* dx, void* stream);
+
+/* One call per direction for the unsharded case (what a trainer that launches eagerly pays per step is host time):
+ * spl_loss_forward = spl_forward + spl_reduce_finalize, spl_loss_backward = spl_backward.  `ts` is a per-recipe TEMPLATE
+ * (tables filled in; partials / gframes ignored); the per-call workspace `ws` (device) is carved up by BYTE offsets the
+ * caller computed once from spl_geometry_of(): off_partials[n], off_gframes[n] (NULL = forward only, torch.no_grad),
+ * off_sums (doubles), off_coefs (2*n floats). */
+int32_t spl_loss_forward(const spl_transform* ts, int32_t n, const float* x, const float* y, int32_t B, int32_t T,
+                         void* ws, const int64_t* off_partials, const int64_t* off_gframes, int64_t off_sums,
+                         int64_t off_coefs, float* sc, float* mag, float* mel, uint32_t* counter, void* stream);
+int32_t spl_loss_backward(const spl_transform* ts, int32_t n, int32_t B, int32_t T, void* ws, const int64_t* off_gframes,
+                          int64_t off_coefs, const float* g_sc, const float* g_mag, const float* g_mel, float* dx, void* stream);
 
 /* Explicit magnitude spectrogram out[b, t, k] = sqrt(max(|STFT(x)[b, t, k]|^2, eps)), (B, 1 + T/hop, ld) with
  * ld >= n_fft/2 + 1 floats per frame (pad columns are zeroed): the tensor stft() returns (stft_loss.py:19-35) and the

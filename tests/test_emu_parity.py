@@ -381,3 +381,32 @@ def test_both_2048_routes_match_reference(emu_engine, monkeypatch, name, mode):
     for i in range(3):
         assert abs(vals[i] - g["loss64"][i]) <= LOSS_RTOL * max(abs(g["loss64"][i]), 1e-12)
     assert rel_l2(grad.reshape(g["grad64"].shape), g["grad64"]) <= GRAD_RTOL
+
+
+@pytest.mark.parametrize("run_frames", [2, 3, 5, 16])
+@pytest.mark.parametrize("name", ["gauss_b2_t4800", "ragged_b3_t5003_2d", "minlen_b1_t1025"])
+def test_overlap_add_ring_runs(emu_engine, monkeypatch, name, run_frames):
+    """STFT gradient through the shared-memory overlap-add ring (a warp takes a run of `run_frames` consecutive frames and
+    writes (run_frames - 1) * hop + win taps per run instead of run_frames * win): same losses bit for bit, gradient equal to
+    the one-slot-per-frame path up to fp32 summation order, and within the reference tolerances.  Run lengths that do not
+    divide the frame count, runs longer than an utterance (minlen: 3 frames at n_fft 2048), two frames per warp (n_fft 512)."""
+    g = load_golden(name)
+    monkeypatch.setenv("SPECLOSS_RUN_FRAMES", "1")
+    base_vals, base_grad = run_losses(emu_engine, g)
+    monkeypatch.setenv("SPECLOSS_RUN_FRAMES", str(run_frames))
+    vals, grad = run_losses(emu_engine, g)
+    assert vals == base_vals
+    assert rel_l2(grad, base_grad) <= 2e-6
+    assert rel_l2(grad.reshape(g["grad64"].shape), g["grad64"]) <= GRAD_RTOL
+    # the workspace really shrank: taps per run vs taps per frame
+    from dl_speech_enhancement_b200 import _abi
+    tr = plans_for(g)[0]
+    st = _abi.SplTransform()
+    st.kind, st.n_fft, st.hop, st.win = tr.kind, tr.n_fft, tr.hop, tr.win
+    geo = _abi.SplGeometry()
+    b, t_len = g["y_hat"].reshape(-1, g["y_hat"].shape[-1]).shape
+    assert emu_engine.lib.spl_geometry_of(st, b, t_len, geo) == 0
+    frames = 1 + t_len // tr.hop
+    m = min(run_frames, frames) if run_frames <= frames else 1
+    runs = -(-frames // m)
+    assert geo.gframe_bytes == b * runs * ((m - 1) * tr.hop + tr.win) * 8
