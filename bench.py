@@ -687,6 +687,23 @@ def check_sharded_parity(torch, dist, pkg, eng, dev, rank, world, group, pair, m
         eng._recipes_by_id.clear()
         losses, grad = sharded(crit)
         compare("nccl_all_reduce", losses, grad)
+        # and its speed, for the record (10 eager steps after 3, device time, max over ranks)
+        x = y_hat.detach().clone().requires_grad_(True)
+        for _ in range(3):
+            x.grad = None
+            losses_and_backward(x, y, crit)
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            x.grad = None
+            losses_and_backward(x, y, crit)
+        e1.record()
+        torch.cuda.synchronize()
+        tms = torch.tensor([e0.elapsed_time(e1) / 10], device=dev, dtype=torch.float64)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        res["paths"]["nccl_all_reduce"]["ms_per_step"] = float(tms.item())
     finally:
         if old is None:
             os.environ.pop("SPECLOSS_NCCL_ALLREDUCE", None)

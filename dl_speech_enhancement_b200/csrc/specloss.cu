@@ -140,9 +140,9 @@ int spl_join(void* stream, int n, void** streams) {
   return SPL_OK;
 }
 
-template <int NFFT, int KIND, bool GRAD, int WIN_T>
+template <int NFFT, int KIND, bool GRAD, int WIN_T, bool RING = false>
 int spl_launch_transform(const spl::TransformParams& p, int grid, int wpc, size_t smem, void* stream) {
-  auto kern = spl::transform_kernel<NFFT, KIND, GRAD, WIN_T>;
+  auto kern = spl::transform_kernel<NFFT, KIND, GRAD, WIN_T, RING>;
   static thread_local bool configured[64] = {false};
   int rc = opt_in_smem(kern, configured);
   if (rc) return rc;

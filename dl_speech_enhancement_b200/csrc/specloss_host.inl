@@ -189,6 +189,8 @@ int shape_of(const spl_transform* t, int B, int T, bool grad, int* grid, int* wp
 
 template <int NFFT, int WIN_T>
 int launch_win(const spl::TransformParams& p, int kind, bool grad, int grid, int wpc, size_t smem, void* s) {
+  if (kind == SPL_KIND_STFT && grad && p.run_frames > 1)         // overlap-add ring: its own instantiation
+    return spl_launch_transform<NFFT, spl::kKindStft, true, WIN_T, true>(p, grid, wpc, smem, s);
   if (kind == SPL_KIND_STFT)
     return grad ? spl_launch_transform<NFFT, spl::kKindStft, true, WIN_T>(p, grid, wpc, smem, s)
                 : spl_launch_transform<NFFT, spl::kKindStft, false, WIN_T>(p, grid, wpc, smem, s);

@@ -597,7 +597,7 @@ SPL_DEVICE void mel_epilogue(float2 (&A)[Geo<NFFT>::AROWS][Geo<NFFT>::HL], float
 // WIN_T > 0: window length known at compile time (shipped configs), which prunes the zero taps out of the
 // load, the first butterflies of the forward transform and the last ones of the inverse.
 // ---------------------------------------------------------------------------------------------
-template <int NFFT, int KIND, bool GRAD, int WIN_T>
+template <int NFFT, int KIND, bool GRAD, int WIN_T, bool RING = false>
 SPL_DEVICE void transform_body(const TransformParams& p, float* smem, int block, int tid, int grid, int wpc) {
   using G = Geo<NFFT>;
   using SL = SmemLayout<NFFT, KIND>;
@@ -614,8 +614,9 @@ SPL_DEVICE void transform_body(const TransformParams& p, float* smem, int block,
   const int2* mel_entries = reinterpret_cast<const int2*>(smem + ct.entries);
   const int4* bin_tab = reinterpret_cast<const int4*>(smem + ct.bintab);
 
-  const int m = (GRAD && KIND == kKindStft) ? p.run_frames : 1;       // frames per run (1: one gradient slot per frame)
-  const bool ring_on = m > 1;
+  // RING (a separate instantiation, so that the default kernels carry none of its code): runs of p.run_frames frames
+  const int m = (RING && GRAD && KIND == kKindStft) ? p.run_frames : 1;       // frames per run (1: one gradient slot per frame)
+  const bool ring_on = RING && m > 1;
   const int ring_taps = ring_on ? win : 0;
   float* wsm = smem + ct.total + (size_t)warp * SL::words_per_warp(p.n_mels, ring_taps);
   float2* S = reinterpret_cast<float2*>(wsm) + h * G::SLOT_F2;                       // this group's frame slot
@@ -1845,12 +1846,12 @@ struct ReduceFinalizeParams {
 // registers) for the others; the host picks the actual warp count from the shared-memory budget.
 template <int NFFT> struct MaxWarps { static constexpr int value = NFFT == 2048 ? 12 : SPL_MAX_WARPS_SMALL; };
 
-template <int NFFT, int KIND, bool GRAD, int WIN_T>
+template <int NFFT, int KIND, bool GRAD, int WIN_T, bool RING = false>
 __global__ void __launch_bounds__(MaxWarps<NFFT>::value * 32, 1) transform_kernel(const TransformParams p) {
   extern __shared__ __align__(16) float smem_dyn[];
   cta_load_tables<NFFT, KIND>(p, smem_dyn, threadIdx.x, blockDim.x);
   __syncthreads();
-  transform_body<NFFT, KIND, GRAD, WIN_T>(p, smem_dyn, blockIdx.x, threadIdx.x, gridDim.x, blockDim.x >> 5);
+  transform_body<NFFT, KIND, GRAD, WIN_T, RING>(p, smem_dyn, blockIdx.x, threadIdx.x, gridDim.x, blockDim.x >> 5);
 }
 template <int NFFT>
 __global__ void __launch_bounds__(MaxWarps<NFFT>::value * 32, 1) spec_kernel(const SpecParams p) {

@@ -16,6 +16,7 @@ import tempfile
 
 src_csv, kern_sub, so_path = sys.argv[1:4]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 25
+sec_override = sys.argv[5] if len(sys.argv) > 5 else None          # mangled-name substring of the .text section
 
 rows = list(csv.reader(open(src_csv)))
 kern, data, hdr = None, {}, None
@@ -46,6 +47,8 @@ if m:
     sec = f"transform_kernelILi{n}ELi{kind}ELb{grad}ELi{win}EE"
 else:
     sec = kern_sub
+if sec_override:
+    sec = sec_override
 lines = sass.split("\n")
 start = next(i for i, l in enumerate(lines) if l.startswith(".text.") and sec in l)
 end = next((i for i in range(start + 1, len(lines)) if lines[i].startswith("//-----")), len(lines))

@@ -78,11 +78,11 @@ void run_grid(int grid, int wpc, size_t smem_bytes, Load&& load, Body&& body) {
   }
 }
 
-template <int NFFT, int KIND, bool GRAD, int WIN_T>
+template <int NFFT, int KIND, bool GRAD, int WIN_T, bool RING = false>
 int spl_launch_transform(const spl::TransformParams& p, int grid, int wpc, size_t smem, void*) {
   run_grid(grid, wpc, smem,
            [&](float* sm, int tid) { spl::cta_load_tables<NFFT, KIND>(p, sm, tid, wpc * 32); },
-           [&](float* sm, int block, int tid) { spl::transform_body<NFFT, KIND, GRAD, WIN_T>(p, sm, block, tid, grid, wpc); });
+           [&](float* sm, int block, int tid) { spl::transform_body<NFFT, KIND, GRAD, WIN_T, RING>(p, sm, block, tid, grid, wpc); });
   return SPL_OK;
 }
 
