@@ -110,3 +110,36 @@ def test_new_entry_points_reject_bad_arguments(lib):
     rc = lib.spl_reduce_exchange_finalize(ctypes.byref(_tr()), 1, 2, 9000, 4, ctypes.addressof(dummy), ctypes.addressof(dummy),
                                           5, 2, ptrs, ctypes.addressof(state), 0, None, None, None, None, ctypes.addressof(dummy), None)
     assert rc == -1 and "rank" in lib.spl_last_error().decode()
+
+
+def test_even_odd_tables_match_the_python_builder(lib):
+    """spl_fill_twiddle_eo (C) and engine.twiddle_eo_table (numpy) produce the same fp32 tables."""
+    from dl_speech_enhancement_b200.engine import twiddle_eo_table
+    n = 2 * 1024 + 2 * 516
+    buf = (ctypes.c_float * n)()
+    assert lib.spl_fill_twiddle_eo(buf) == 0
+    np.testing.assert_array_equal(np.frombuffer(buf, dtype=np.float32), twiddle_eo_table().numpy())
+    assert lib.spl_fill_twiddle_eo(None) == -1
+
+
+def test_one_call_entry_points_reject_bad_arguments(lib):
+    """spl_loss_forward / spl_loss_backward check their template and offsets before any launch."""
+    t = _tr()
+    off = (ctypes.c_int64 * 1)(0)
+    dummy = (ctypes.c_double * 64)()
+    a = ctypes.addressof(dummy)
+    assert lib.spl_loss_forward(ctypes.byref(t), 0, a, a, 2, 9000, a, off, None, 0, 0, None, None, None, a, None) == -1
+    assert "transforms" in lib.spl_last_error().decode()
+    assert lib.spl_loss_forward(ctypes.byref(t), 1, a, a, 2, 9000, None, off, None, 0, 0, None, None, None, a, None) == -1
+    assert lib.spl_loss_forward(ctypes.byref(t), 1, a, a, 2, 9000, a, None, None, 0, 0, None, None, None, a, None) == -1
+    assert "offsets" in lib.spl_last_error().decode()
+    assert lib.spl_loss_backward(ctypes.byref(t), 1, 2, 9000, a, None, 0, None, None, None, a, None) == -1
+    assert "gradient workspace" in lib.spl_last_error().decode()
+
+
+def test_geometry_with_runs(lib, monkeypatch):
+    """Workspace of the overlap-add ring (SPECLOSS_RUN_FRAMES is read at the first use of the CUDA library, so this
+    only checks the default here: one gradient slot per frame)."""
+    g = _abi.SplGeometry()
+    assert lib.spl_geometry_of(ctypes.byref(_tr()), 256, 192000, ctypes.byref(g)) == 0
+    assert g.gframe_bytes == 256 * 1601 * 600 * 8
