@@ -61,6 +61,14 @@ int spl_launch_shape(int n_fft, size_t table_bytes, size_t warp_bytes, long long
   if (by_smem < w) w = by_smem;
   const long long spread = (items + sms - 1) / sms;
   if (spread < w) w = (int)(spread < 1 ? 1 : spread);
+  // Small launches: the fewest warps per CTA that still finish in the same number of rounds (17.4 frames per SM take two
+  // rounds with 12 warps and with 9; nine warps per round contend less -- profiles/r3p_coresidency.txt: mel 45.2 -> 42.8 us
+  // at configs[1] with 10).  Irrelevant for large launches (w stays at its maximum).
+  {
+    const long long rounds = (spread + w - 1) / w;
+    const int balanced = (int)((spread + rounds - 1) / rounds);
+    if (balanced >= 1 && balanced < w) w = balanced;
+  }
   const long long need = (items + w - 1) / w;
   *grid = (int)(need < sms ? need : sms);
   *wpc = w;
