@@ -30,10 +30,10 @@ def csrc_hash():
 
 
 def short_name(full):
-    m = re.search(r"transform_eo_kernel<(\d), (?:\(bool\))?(\w+), (\d+)>", full)
+    m = re.search(r"transform_eo_kernel<(?:\(int\))?(\d), (?:\(bool\))?(\w+), (?:\(int\))?(\d+)>", full)
     if m:
         return ("mel" if m.group(1) == "1" else "stft") + "_2048_eo" + ("" if m.group(2) in ("1", "true") else "_nograd")
-    m = re.search(r"transform_kernel<(\d+), (\d), (?:\(bool\))?(\w+), (\d+)>", full)
+    m = re.search(r"transform_kernel<(?:\(int\))?(\d+), (?:\(int\))?(\d), (?:\(bool\))?(\w+), (?:\(int\))?(\d+)(?:, (?:\(bool\))?\w+)?>", full)
     if m:
         return ("mel_" if m.group(2) == "1" else "stft_") + m.group(1) + ("" if m.group(3) in ("1", "true") else "_nograd")
     for k in ("combine_kernel", "reduce_finalize_kernel", "reduce_exchange_finalize_kernel", "reduce_kernel", "finalize_kernel"):
