@@ -51,6 +51,15 @@ def trainer_available() -> bool:
         os.path.isfile(os.path.join(root, "models", "autoencoder", "AudioDec.py"))
 
 
+def gan_trainers_available() -> bool:
+    """The autoencoder and vocoder trainers with their models and shipped YAMLs, beside the denoise trainer."""
+    root = reference_root()
+    return trainer_available() and all(os.path.isfile(os.path.join(root, *p)) for p in (
+        ("trainer", "autoencoder.py"), ("trainer", "vocoder.py"), ("models", "vocoder", "HiFiGAN.py"),
+        ("models", "vocoder", "UnivNet.py"), ("config", "autoencoder", "symAD_vctk_48000_hop300.yaml"),
+        ("config", "vocoder", "AudioDec_v1_symAD_vctk_48000_hop300_clean.yaml")))
+
+
 def _install_librosa_shim():
     if "librosa" in sys.modules and not getattr(sys.modules["librosa"], "_specloss_shim", False):
         return
@@ -138,6 +147,26 @@ def load_reference_trainer():
     with open(os.path.join(root, "config", "denoise", "symAD_vctk_48000_hop300.yaml")) as f:
         ns.config = yaml.safe_load(f)
     ns.root = root
+    ns.trainers = {"denoise": ns.Trainer}
+    ns.configs = {"denoise/symAD_vctk_48000_hop300": ns.config}
+    if gan_trainers_available():
+        # trainer/autoencoder.py:19 (symmetric codec, stage 1 metric-only, stage 2 adversarial), trainer/vocoder.py:19 (HiFiGAN
+        # decoder on the frozen analyzer's codes); models and criteria as the shipped YAMLs name them
+        ns.trainers["autoencoder"] = importlib.import_module("trainer.autoencoder").Trainer
+        ns.trainers["vocoder"] = importlib.import_module("trainer.vocoder").Trainer
+        hifigan = importlib.import_module("models.vocoder.HiFiGAN")
+        univnet = importlib.import_module("models.vocoder.UnivNet")
+        ns.HiFiGANGenerator, ns.HiFiGANDiscriminator, ns.UnivNetDiscriminator = hifigan.Generator, hifigan.Discriminator, univnet.Discriminator
+        ns.discriminator_module = importlib.import_module("models.vocoder.modules.discriminator")
+        ns.GeneratorAdversarialLoss = losses.GeneratorAdversarialLoss
+        ns.DiscriminatorAdversarialLoss = losses.DiscriminatorAdversarialLoss
+        ns.FeatureMatchLoss = losses.FeatureMatchLoss
+        for sub in ("autoencoder", "vocoder"):
+            d = os.path.join(root, "config", sub)
+            for name in sorted(os.listdir(d)):
+                if name.endswith(".yaml"):
+                    with open(os.path.join(d, name)) as f:
+                        ns.configs[f"{sub}/{name[:-5]}"] = yaml.safe_load(f)
     return ns
 
 

@@ -62,10 +62,93 @@ def build_trainer(ns, mel_cls, stft_cls, device, seed=0, use_stft=True, init_sta
     return tr
 
 
+def _gan_parts(ns, cfg, device, mel_cls, stft_cls, shape_cls, use_stft, use_shape):
+    """What the AudioDec entry scripts put around a TrainerGAN (criterion / discriminator / optimizer / scheduler dicts named as
+    trainerGAN.py:214-300 reads them); the concrete scripts (codecTrain.py) are not part of the reference repo."""
+    cfg["use_mel_loss"] = True
+    cfg["use_stft_loss"] = bool(use_stft)
+    cfg["use_shape_loss"] = bool(use_shape)
+    cfg["outdir"] = tempfile.mkdtemp(prefix="specloss_trainer_")
+    cfg["train_max_steps"] = 1 << 30
+    disc_cls = ns.UnivNetDiscriminator if cfg["model_type"] in ("symAudioDecUniv", "UnivNet") else ns.HiFiGANDiscriminator
+    disc = disc_cls(**cfg["discriminator_params"]).to(device)
+    criterion = {"mel": mel_cls(**cfg["mel_loss_params"]).to(device),
+                 "gen_adv": ns.GeneratorAdversarialLoss(**cfg["generator_adv_loss_params"]).to(device),
+                 "dis_adv": ns.DiscriminatorAdversarialLoss(**cfg["discriminator_adv_loss_params"]).to(device)}
+    if cfg.get("use_feat_match_loss", False):
+        criterion["feat_match"] = ns.FeatureMatchLoss(**cfg.get("feat_match_loss_params", {})).to(device)
+    if use_stft:
+        criterion["stft"] = stft_cls(**cfg["stft_loss_params"]).to(device)
+    if use_shape:
+        criterion["shape"] = shape_cls(**cfg["shape_loss_params"]).to(device)
+    return disc, criterion
+
+
+def _optim(cfg, who, params):
+    opt = getattr(torch.optim, cfg[f"{who}_optimizer_type"])(params, **cfg[f"{who}_optimizer_params"])
+    sch = getattr(torch.optim.lr_scheduler, cfg[f"{who}_scheduler_type"])(opt, **cfg[f"{who}_scheduler_params"])
+    return opt, sch
+
+
+def build_autoencoder_trainer(ns, mel_cls, stft_cls, shape_cls, device, config="autoencoder/symAD_vctk_48000_hop300", seed=0,
+                              use_stft=True, use_shape=True, adversarial=False, init_state=None):
+    """trainer.autoencoder.Trainer (trainer/autoencoder.py:19-129) over a seeded symAD generator and the YAML's discriminator.
+    adversarial=False is stage 1 of the 'efficient' paradigm (steps < start_steps.discriminator: metric + VQ losses only,
+    :96-98), adversarial=True stage 2 (encoder/quantizer frozen, discriminator + feature matching on, :63-75,100-108)."""
+    cfg = copy.deepcopy(ns.configs[config])
+    cfg.setdefault("start_steps", {})["discriminator"] = 0 if adversarial else 1 << 30
+    torch.manual_seed(seed)
+    gen = ns.Generator(**cfg["generator_params"])
+    if init_state is not None:
+        gen.load_state_dict(init_state)
+    gen = gen.to(device)
+    disc, criterion = _gan_parts(ns, cfg, device, mel_cls, stft_cls, shape_cls, use_stft, use_shape)
+    og, sg = _optim(cfg, "generator", gen.parameters())
+    od, sd = _optim(cfg, "discriminator", disc.parameters())
+    tr = ns.trainers["autoencoder"](steps=0, epochs=0, data_loader={}, model={"generator": gen, "discriminator": disc},
+                                    criterion=criterion, optimizer={"generator": og, "discriminator": od},
+                                    scheduler={"generator": sg, "discriminator": sd}, config=cfg, device=device)
+    tr.tqdm = _NoTqdm()
+    return tr
+
+
+def build_vocoder_trainer(ns, mel_cls, stft_cls, shape_cls, device, config="vocoder/AudioDec_v1_symAD_vctk_48000_hop300_clean",
+                          seed=0, use_stft=True, use_shape=True, adversarial=True, init_state=None):
+    """trainer.vocoder.Trainer (trainer/vocoder.py:19-111): a HiFiGAN generator trained on the codes of a frozen analyzer (the
+    symAD generator of the matching autoencoder YAML, seeded instead of loaded from the checkpoint the YAML names; the
+    generator's input normalisation statistics file is not part of the repo: stats=None).  Its step compares with `>`
+    (:66,78,94), so the trainer starts at steps=2: generator on, discriminator on when adversarial."""
+    cfg = copy.deepcopy(ns.configs[config])
+    cfg["generator_train_start_steps"] = 0
+    cfg["discriminator_train_start_steps"] = 1 if adversarial else 1 << 30
+    ae_name = "autoencoder/" + ("symAD_libritts_24000_hop300" if "libritts" in config else
+                                "symADuniv_vctk_48000_hop300" if "univ" in config else "symAD_vctk_48000_hop300")
+    torch.manual_seed(seed)
+    analyzer = ns.Generator(**ns.configs[ae_name]["generator_params"]).to(device)
+    gp = dict(cfg["generator_params"])
+    gp["stats"] = None
+    gen = ns.HiFiGANGenerator(**gp)
+    if init_state is not None:
+        gen.load_state_dict(init_state)
+    gen = gen.to(device)
+    disc, criterion = _gan_parts(ns, cfg, device, mel_cls, stft_cls, shape_cls, use_stft, use_shape)
+    og, sg = _optim(cfg, "generator", gen.parameters())
+    od, sd = _optim(cfg, "discriminator", disc.parameters())
+    tr = ns.trainers["vocoder"](steps=2, epochs=0, data_loader={}, model={"generator": gen, "discriminator": disc, "analyzer": analyzer},
+                                criterion=criterion, optimizer={"generator": og, "discriminator": od},
+                                scheduler={"generator": sg, "discriminator": sd}, config=cfg, device=device)
+    tr.tqdm = _NoTqdm()
+    return tr
+
+
+TRAIN_KEYS = ("train/mel_loss", "train/spectral_convergence_loss", "train/log_stft_magnitude_loss", "train/shape_loss",
+              "train/generator_loss", "train/adversarial_loss", "train/feature_matching_loss", "train/discriminator_loss")
+
+
 def run_steps(trainer, batches):
     """Runs Trainer._train_step on every batch; returns the per-step records the trainer itself keeps
     (total_train_loss is a running sum: the per-step value is the difference)."""
-    keys = ("train/mel_loss", "train/spectral_convergence_loss", "train/log_stft_magnitude_loss", "train/generator_loss")
+    keys = TRAIN_KEYS
     prev = {k: 0.0 for k in keys}
     rows = []
     for batch in batches:

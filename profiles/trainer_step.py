@@ -39,12 +39,41 @@ def crit_ms(mel, stft, dev, batch, length, steps=30, warmup=5):
     return a.elapsed_time(b) / steps
 
 
+def gan_trainers(pkg, th, ns, dev):
+    """SURVEY 8(f1), the other two trainers at their shipped batch (16 x 0.2 s): trainer.autoencoder (stage 1 metric-only and
+    the adversarial stage) and trainer.vocoder (adversarial), mel + MR-STFT + shape criteria on, reference's vs this repo's."""
+    out = {"config": "trainer.autoencoder / trainer.vocoder Trainer._train_step at the shipped batch 16 x 9600, mel + MR-STFT + "
+                     "shape criteria enabled; wall clock per step incl. the trainer's .item() syncs",
+           "gpu": torch.cuda.get_device_name(0)}
+    n_steps, warm = 25, 5
+    g = torch.Generator().manual_seed(2)
+    batches = [(0.1 * torch.randn(16, 1, 9600, generator=g)).pin_memory() for _ in range(n_steps)]
+    cases = (("autoencoder_metric_stage", th.build_autoencoder_trainer, "autoencoder/symAD_vctk_48000_hop300", False),
+             ("autoencoder_adversarial_stage", th.build_autoencoder_trainer, "autoencoder/symAD_vctk_48000_hop300", True),
+             ("vocoder_hifigan", th.build_vocoder_trainer, "vocoder/AudioDec_v1_symAD_vctk_48000_hop300_clean", True),
+             ("vocoder_univnet", th.build_vocoder_trainer, "vocoder/AudioDec_v3_symADuniv_vctk_48000_hop300_clean", True))
+    for tag, build, config, adv in cases:
+        res = {"yaml": config}
+        for name, classes in (("reference_criteria", (ns.MultiMelSpectrogramLoss, ns.MultiResolutionSTFTLoss, ns.MultiWindowShapeLoss)),
+                              ("b200_criteria", (pkg.MultiMelSpectrogramLoss, pkg.MultiResolutionSTFTLoss, pkg.MultiWindowShapeLoss))):
+            tr = build(ns, *classes, dev, config=config, seed=5, adversarial=adv)
+            res[name] = {"step_ms": th.time_steps(tr, batches, warmup=warm)}
+            del tr
+            torch.cuda.empty_cache()
+        res["step_speedup"] = res["reference_criteria"]["step_ms"] / res["b200_criteria"]["step_ms"]
+        out[tag] = res
+    return out
+
+
 def main():
     import dl_speech_enhancement_b200 as pkg
     from oracle import trainer_harness as th
 
     dev = torch.device("cuda:0")
     ns = th.load()
+    if os.environ.get("PROF_TRAINER", "denoise") != "denoise":
+        print(json.dumps(gan_trainers(pkg, th, ns, dev), indent=1))
+        return
     batch, length, n_steps, warm = 32, 24000, 25, 5
     batches = th.synthetic_batches(n_steps, batch, length, seed=11, device="cpu")
     pinned = [(a.pin_memory(), b.pin_memory()) for a, b in batches]

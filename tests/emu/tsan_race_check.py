@@ -94,13 +94,18 @@ def main():
         print(first)
     ok = done and races == 0
     caught = 0
+    tried = 0
+    all_controls = "--all-controls" in sys.argv
     for skip in (3, 9, 40):                        # three different barriers of the first kernels
         r, d, f = run(skip)
+        tried += 1
         print(f"positive control, __syncwarp() #{skip} of every lane skipped: data-race reports = {r}")
         if r:
             caught += 1
             print("  " + f.replace("\n", "\n  ")[:600])
-    print(f"controls caught: {caught} of 3")
+            if not all_controls:                   # one caught control proves the detector; --all-controls runs the rest
+                break
+    print(f"controls caught: {caught} of {tried}")
     ok = ok and caught >= 1
     print("RACE CHECK", "PASSED" if ok else "FAILED")
     return 0 if ok else 1

@@ -138,3 +138,222 @@ def test_free_running_trainer_tracks_like_the_fp32_reference(use_stft):
           f"reference-fp32 run {our_ref:.2e}; vs the fp64-criteria run: this repo {our_f64:.2e}, reference-fp32 {ref_f64:.2e}")
     assert our_ref <= 1e-2 and our_f64 <= 1e-2
     assert rows_our[-1]["mel_loss"] < rows_our[0]["mel_loss"]          # and it trains
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# SURVEY 8(f1), the other two trainers: trainer/autoencoder.py:98 and trainer/vocoder.py:76 call the same
+# TrainerGAN._metric_loss (trainerGAN.py:214-241) -- criterion["mel"], criterion["stft"], criterion["shape"] -- on their own
+# generators, with their own shipped YAMLs (48 kHz VCTK, 24 kHz LibriTTS / fmax 12 kHz, the UnivNet variants), in the
+# metric-only stage and in the adversarial stage (where the prediction also feeds the discriminators).
+# ---------------------------------------------------------------------------------------------------------------------
+needs_gan_trainers = pytest.mark.skipif(not ref_loader.gan_trainers_available(),
+                                        reason="reference autoencoder/vocoder trainers neither mounted nor staged (oracle/make_ref.sh)")
+
+GAN_CASES = [
+    ("autoencoder", "autoencoder/symAD_vctk_48000_hop300", False),             # stage 1 as shipped: metric + VQ losses only
+    ("autoencoder", "autoencoder/symAD_libritts_24000_hop300", True),          # 24 kHz, fmax 12 kHz, adversarial stage
+    ("vocoder", "vocoder/AudioDec_v1_symAD_vctk_48000_hop300_clean", True),    # HiFiGAN decoder on the frozen analyzer's codes
+    ("vocoder", "vocoder/AudioDec_v3_symADuniv_vctk_48000_hop300_clean", True),  # UnivNet spectral discriminators
+]
+
+
+def _build_gan_trainer(th, ns, kind, config, adversarial, device, seed, classes=None):
+    mel_cls, stft_cls, shape_cls = classes or (ns.MultiMelSpectrogramLoss, ns.MultiResolutionSTFTLoss, ns.MultiWindowShapeLoss)
+    build = th.build_autoencoder_trainer if kind == "autoencoder" else th.build_vocoder_trainer
+    return build(ns, mel_cls, stft_cls, shape_cls, device, config=config, seed=seed, adversarial=adversarial)
+
+
+@needs_gan_trainers
+@pytest.mark.parametrize("kind,config", [("autoencoder", "autoencoder/symAD_vctk_48000_hop300"),
+                                         ("vocoder", "vocoder/AudioDec_v3_symADuniv_vctk_48000_hop300_clean")])
+def test_reference_gan_trainers_run_on_cpu_with_reference_criteria(kind, config):
+    """The widened harness itself (CPU, tiny): one adversarial-stage _train_step of the unmodified autoencoder / vocoder
+    trainer with mel + MR-STFT + shape enabled records every loss, steps both optimisers and counts the step."""
+    from oracle import trainer_harness as th
+
+    ns = th.load()
+    tr = _build_gan_trainer(th, ns, kind, config, True, torch.device("cpu"), seed=0)
+    disc_before = [p.detach().clone() for p in tr.model["discriminator"].parameters()]
+    steps0 = tr.steps
+    g = torch.Generator().manual_seed(3)
+    rows = th.run_steps(tr, [0.1 * torch.randn(1, 1, 2400, generator=g)])
+    for key in ("mel_loss", "spectral_convergence_loss", "log_stft_magnitude_loss", "shape_loss", "adversarial_loss",
+                "discriminator_loss", "generator_loss"):
+        assert rows[0][key] > 0, key
+    assert tr.steps == steps0 + 1
+    assert any(not torch.equal(a, b) for a, b in zip(disc_before, tr.model["discriminator"].parameters()))
+
+
+@pytest.mark.gpu
+@needs_gan_trainers
+@pytest.mark.parametrize("kind,config,adversarial", GAN_CASES, ids=[f"{k}-{c.split('/')[1]}-{'adv' if a else 'metric'}" for k, c, a in GAN_CASES])
+def test_criteria_agree_inside_the_autoencoder_and_vocoder_trainers(kind, config, adversarial):
+    """Three optimiser steps of the reference's autoencoder / vocoder Trainer._train_step at the shipped batch (16 x 0.2 s),
+    driven by the REFERENCE criteria (mel + MR-STFT + shape all on).  On exactly the (prediction, target) pair each step
+    handed to _metric_loss this repo's three criteria -- lambda-weighted and scaled in place like trainerGAN.py:221-239 --
+    must give the losses the trainer recorded (mel 1e-5, sc / mag 1e-4, shape 1e-6 relative) and a gradient w.r.t. the
+    prediction no further from the reference modules evaluated in fp64 than max(1e-3, 2 x the reference's own fp32
+    evaluation on the same tensors)."""
+    import dl_speech_enhancement_b200 as pkg
+    from oracle import trainer_harness as th
+
+    dev = torch.device("cuda:0")
+    ns = th.load()
+    tr = _build_gan_trainer(th, ns, kind, config, adversarial, dev, seed=7)
+    cfg = tr.config
+    fs = cfg["mel_loss_params"]["fs"]
+    log = []
+    tr.criterion["mel"] = th.Tee(tr.criterion["mel"], log, hook=True)
+    g = torch.Generator().manual_seed(21)
+    batches = [(0.1 * torch.randn(cfg["batch_size"], 1, cfg["batch_length"], generator=g)) for _ in range(3)]
+    rows = th.run_steps(tr, batches)
+    assert len(log) == 3
+
+    def criteria(mel_cls, stft_cls, shape_cls, double=False):
+        mods = (mel_cls(**cfg["mel_loss_params"]).to(dev), stft_cls(**cfg["stft_loss_params"]).to(dev),
+                shape_cls(**cfg["shape_loss_params"]).to(dev))
+        return tuple(m.double() for m in mods) if double else mods
+
+    def evaluate(mods, pred, target):
+        """_metric_loss restated on given modules: returns (mel, sc, mag, shape) floats and d(total)/d(pred)."""
+        mel_c, stft_c, shape_c = mods
+        x = pred.clone().requires_grad_(True)
+        mel = mel_c(x, target)
+        mel *= cfg["lambda_mel_loss"]
+        sc, mag = stft_c(x, target)
+        sc *= cfg["lambda_stft_loss"]
+        mag *= cfg["lambda_stft_loss"]
+        shape = shape_c(x, target)
+        shape *= cfg["lambda_shape_loss"]
+        (mel + (sc + mag) + shape).backward()
+        return [float(v.detach()) for v in (mel, sc, mag, shape)], x.grad
+
+    ours = criteria(pkg.MultiMelSpectrogramLoss, pkg.MultiResolutionSTFTLoss, pkg.MultiWindowShapeLoss)
+    ref32 = criteria(ns.MultiMelSpectrogramLoss, ns.MultiResolutionSTFTLoss, ns.MultiWindowShapeLoss)
+    ref64 = criteria(ns.MultiMelSpectrogramLoss, ns.MultiResolutionSTFTLoss, ns.MultiWindowShapeLoss, double=True)
+    worst = {"loss": 0.0, "ours": 0.0, "ref32": 0.0}
+    for step, (rec, row) in enumerate(zip(log, rows)):
+        assert rec["pred"].shape == (cfg["batch_size"], 1, cfg["batch_length"])
+        got, grad = evaluate(ours, rec["pred"], rec["target"])
+        _, g32 = evaluate(ref32, rec["pred"], rec["target"])
+        _, g64 = evaluate(ref64, rec["pred"].double(), rec["target"].double())
+        for val, key, tol in zip(got, ("mel_loss", "spectral_convergence_loss", "log_stft_magnitude_loss", "shape_loss"),
+                                 (1e-5, 1e-4, 1e-4, 1e-6)):
+            rel = abs(val - row[key]) / abs(row[key])
+            worst["loss"] = max(worst["loss"], rel)
+            assert rel <= tol, (step, key, val, row[key])
+        e_ours = float((grad.double() - g64).norm() / g64.norm())
+        e_ref = float((g32.double() - g64).norm() / g64.norm())
+        worst["ours"], worst["ref32"] = max(worst["ours"], e_ours), max(worst["ref32"], e_ref)
+        assert e_ours <= max(1e-3, 2.0 * e_ref), (step, e_ours, e_ref)
+    print(f"{kind} trainer, {config} @ {fs} Hz ({'adversarial' if adversarial else 'metric-only'} stage): worst loss deviation "
+          f"{worst['loss']:.2e}; gradient of mel + MR-STFT + shape w.r.t. the generator output, rel-L2 vs the reference modules in "
+          f"fp64: this repo {worst['ours']:.2e}, the reference modules in fp32 {worst['ref32']:.2e}")
+
+
+@pytest.mark.gpu
+@needs_gan_trainers
+def test_gan_trainers_step_with_drop_in_criteria():
+    """The switch itself: the autoencoder trainer (adversarial stage) and the vocoder trainer built with THIS repo's three
+    criteria classes in the criterion dict run their unmodified _train_step; the first step (identical weights and batch)
+    records the same losses as the run with the reference criteria, and the metric losses come down over 6 steps."""
+    import dl_speech_enhancement_b200 as pkg
+    from oracle import trainer_harness as th
+
+    dev = torch.device("cuda:0")
+    ns = th.load()
+    ours = (pkg.MultiMelSpectrogramLoss, pkg.MultiResolutionSTFTLoss, pkg.MultiWindowShapeLoss)
+    for kind, config in (("autoencoder", "autoencoder/symAD_vctk_48000_hop300"),
+                         ("vocoder", "vocoder/AudioDec_v1_symAD_vctk_48000_hop300_clean")):
+        g = torch.Generator().manual_seed(5)
+        batches = [0.1 * torch.randn(16, 1, 9600, generator=g) for _ in range(6)]
+        tr_ref = _build_gan_trainer(th, ns, kind, config, True, dev, seed=9)
+        tr_our = _build_gan_trainer(th, ns, kind, config, True, dev, seed=9, classes=ours)
+        assert type(tr_our.criterion["stft"]).__module__.startswith("dl_speech_enhancement_b200")
+        rows_ref = th.run_steps(tr_ref, batches[:1])
+        rows_our = th.run_steps(tr_our, batches)
+        for key, tol in (("mel_loss", 1e-5), ("spectral_convergence_loss", 1e-4), ("log_stft_magnitude_loss", 1e-4),
+                         ("shape_loss", 1e-6)):
+            assert abs(rows_ref[0][key] - rows_our[0][key]) <= tol * abs(rows_ref[0][key]), (kind, key, rows_ref[0][key], rows_our[0][key])
+        assert rows_our[-1]["mel_loss"] < rows_our[0]["mel_loss"], (kind, rows_our[0]["mel_loss"], rows_our[-1]["mel_loss"])
+        assert tr_our.steps == tr_ref.steps + 5
+
+
+@pytest.mark.gpu
+@needs_gan_trainers
+def test_univnet_discriminator_with_swapped_front_end():
+    """SURVEY 8(f2) in place: the reference's UnivNet multi-resolution spectral discriminator
+    (models/vocoder/modules/discriminator.py:549-570) with its module-level `spectrogram` name rebound to this repo's
+    drop-in -- the one-line switch INTEGRATION.md shows -- against the same module calling torchaudio.
+    Forward: every output of the discriminator stack.  Backward: the gradient the conv stack delivers to each of the three
+    magnitude tensors (captured from the stock run) is sent back through both front-ends and through torchaudio's in fp64;
+    comparing at the waveform of the WHOLE network instead is meaningless at this level, because a LeakyReLU pre-activation
+    that changes sign between two roundings changes the gradient discretely (measured on B200, profiles/r4e_dbg_univ.txt:
+    the period discriminators alone, which contain no spectrogram, are 2e-3 from their own fp64 evaluation)."""
+    import dl_speech_enhancement_b200 as pkg
+    from oracle import trainer_harness as th
+
+    dev = torch.device("cuda:0")
+    ns = th.load()
+    cfg = ns.configs["vocoder/AudioDec_v3_symADuniv_vctk_48000_hop300_clean"]
+    torch.manual_seed(3)
+    disc = ns.UnivNetDiscriminator(**cfg["discriminator_params"]).to(dev)
+    adv = ns.GeneratorAdversarialLoss(**cfg["generator_adv_loss_params"]).to(dev)
+    x0 = 0.1 * torch.randn(4, 1, 9600, device=dev)
+    mod = ns.discriminator_module
+    stock = mod.spectrogram
+    calls = []
+
+    def tapped(*args, **kw):
+        m = stock(*args, **kw)
+        m.retain_grad()
+        calls.append((kw, m))
+        return m
+
+    def run(front_end):
+        mod.spectrogram = front_end
+        try:
+            x = x0.clone().requires_grad_(True)
+            outs = disc(x)
+            adv(outs).backward()
+            return outs
+        finally:
+            mod.spectrogram = stock
+
+    # cuDNN runs fp32 convolutions in TF32 by default: a 1e-7 difference between two front-ends then flips 10-bit operand
+    # roundings and comes out of the conv stack as 1e-4.  With fp32 convolutions the comparison measures the front-end.
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        outs_ref = run(tapped)
+        outs_our = run(pkg.spectrogram)
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32
+    n, worst = 0, 0.0
+    for o_ref, o_our in zip(outs_ref, outs_our):
+        for a, b in zip(o_ref, o_our):
+            assert a.shape == b.shape
+            worst = max(worst, float((a - b).norm() / a.norm()))
+            n += 1
+    assert n >= 8 and worst <= 2e-5, (n, worst)
+    assert len(calls) == 3                                     # one front-end call per resolution
+    report = []
+    for kw, m in calls:
+        g = m.grad
+        assert g is not None and float(g.abs().max()) > 0
+
+        def vjp(fn, dtype):
+            x = x0.to(dtype).clone().requires_grad_(True)
+            k = dict(kw, window=kw["window"].to(dtype))
+            out = fn(x, **k)
+            (gx,) = torch.autograd.grad(out, x, g.to(dtype))
+            return gx.double()
+
+        g64 = vjp(stock, torch.float64)
+        e_our = float((vjp(pkg.spectrogram, torch.float32) - g64).norm() / g64.norm())
+        e_ref = float((vjp(stock, torch.float32) - g64).norm() / g64.norm())
+        report.append((kw["n_fft"], e_our, e_ref))
+        assert e_our <= max(1e-5, 2.0 * e_ref), (kw["n_fft"], e_our, e_ref)
+    print(f"UnivNet discriminator, {n} outputs: worst rel-L2 ours vs torchaudio front-end {worst:.2e}; the conv stack's gradient sent back "
+          "through the front-end, rel-L2 vs torchaudio in fp64 (n_fft: this repo / torchaudio fp32): "
+          + ", ".join(f"{nf}: {a:.1e} / {b:.1e}" for nf, a, b in report))
