@@ -375,6 +375,31 @@ def run_ours(args, rank, local_rank, world):
         dist.all_reduce(pf, op=dist.ReduceOp.MIN)
         peer = int(pf.item())
 
+    # ---- the same step through the one-call extension module (SpectralLoss: the four transforms concurrently, ONE gather, no
+    #      gradient accumulation between two autograd nodes).  Not the reference's API: reported beside the headline only. ----
+    fused_mod = pkg.SpectralLoss(None, MEL_KW).to(dev)
+    fused_mod.process_group = group
+
+    def fused_step(i):
+        y_hat, y = pool[i % n_pool]
+        y_hat.grad = None
+        sc, mag, ml = fused_mod(y_hat, y)
+        (sc + mag + ml).backward()
+
+    fused_ms, _, _, _ = timed_blocks(fused_step, args.steps, args.warmup, min_s=0.1)
+    ref_out = [float(v.detach()) for v in eager_step(0)]
+    g_two = pool[0][0].grad.clone()
+    pool[0][0].grad = None
+    sc, mag, ml = fused_mod(*pool[0])
+    (sc + mag + ml).backward()
+    fused_info = {"api": "dl_speech_enhancement_b200.SpectralLoss(stft_loss_params, mel_loss_params)(y_hat, y) -> (sc, mag, mel): "
+                         "extension, one autograd node for both criteria",
+                  "ms_per_step": fused_ms, "value": GLOBAL_BATCH * T_LEN / FS / (fused_ms / 1000.0), "unit": UNIT,
+                  "losses_equal_two_module_step": [float(v.detach()) for v in (sc, mag, ml)] == ref_out,
+                  "grad_rel_l2_vs_two_module_step": float((pool[0][0].grad - g_two).norm() / g_two.norm())}
+    del g_two, fused_mod
+    log(f"one-call module {fused_ms:.4f} ms/step")
+
     # ---- e2e: pinned host inputs -> H2D -> fwd+bwd -> D2H of the three losses + sync, every step.  The inputs land in two
     #      pre-allocated device buffer pairs (a prefetcher's double buffer: no allocator traffic inside the loop); the copy
     #      of step i+1 is issued on a copy stream before step i's kernels, so it runs under them (what a DataLoader with
@@ -644,6 +669,7 @@ def run_ours(args, rank, local_rank, world):
                                        + ("over NVLink peer memory inside the reduce+finalize kernel of each criterion "
                                           "(no NCCL call in the step)" if peer else
                                           "with one NCCL all-reduce per criterion") if world > 1 else "single GPU"),
+                       "one_call_extension": fused_info,
                        "secondary": secondary},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": pair_bytes, "d2h_bytes_per_step": 12,
                     "ms_per_step": e2e_ms, "runs_ms_per_step": e_runs, "steps": e_steps,

@@ -349,10 +349,11 @@ SPL_DEVICE void inv_pass_b(float2 (&A)[Geo<NFFT>::AROWS][Geo<NFFT>::HL], float2*
 
 // [region: tap load]
 // Taps of frame t of utterance rows xb / yb: reflect-pad, window, pack z = x*w + i*y*w into v[n2] (element
-// n = l + L*n2).  Returns whether every tap of this lane has x*w == y*w bit for bit.
+// n = l + L*n2).  Returns whether every tap of this lane has x*w == y*w bit for bit; amax = (max |x w|, max |y w|) over
+// this lane's taps (FMNMX: not on the FMA pipe), the input of equalise_pair() below.
 template <int NFFT, int WIN_T>
 SPL_DEVICE bool load_taps(float2 (&v)[Geo<NFFT>::R], const float* __restrict__ xb, const float* __restrict__ yb, int T,
-                          int s0, int win, int left, const float* wtab, int l, bool active) {
+                          int s0, int win, int left, const float* wtab, int l, bool active, float2& amax) {
   using G = Geo<NFFT>;
   constexpr int L = G::L, R = G::R;
   const bool interior = (s0 + left >= 0) && (s0 + left + win <= T);
@@ -373,6 +374,9 @@ SPL_DEVICE bool load_taps(float2 (&v)[Geo<NFFT>::R], const float* __restrict__ x
         xy = __fmul2_rn(make_float2(__ldg(xp + L * n2), __ldg(yp + L * n2)), make_float2(w, w));
       }
       same = same && (xy.x == xy.y);
+      // level statistic over EVERY tap: a subset (the centre half of the window was tried) misjudges frames whose energy
+      // sits in a transient near the frame edge and then scales the wrong way (trainer tensors: gradient error 8e-2)
+      amax = make_float2(fmaxf(amax.x, fabsf(xy.x)), fmaxf(amax.y, fabsf(xy.y)));
       v[n2] = xy;
     }
   } else {
@@ -389,10 +393,44 @@ SPL_DEVICE bool load_taps(float2 (&v)[Geo<NFFT>::R], const float* __restrict__ x
         yv = __ldg(&yb[sidx]) * w;
       }
       same = same && (xv == yv);
+      amax = make_float2(fmaxf(amax.x, fabsf(xv)), fmaxf(amax.y, fabsf(yv)));
       v[n2] = make_float2(xv, yv);
     }
   }
   return same;
+}
+
+// Prediction and target share one complex FFT (z = x w + i y w), whose rounding error in EVERY bin is eps * rms(Z): a
+// prediction much weaker than the target (an untrained decoder: |X^| << |Y|) would inherit the target's rounding noise, and
+// the log-magnitude gradient ~ 1/|X^| amplifies it (measured: gradient 5e-5 ... 2e-2 from fp64 where the reference's fp32 is
+// at 1e-6, profiles/r4g_*).  So the prediction's taps are multiplied by the power of two that brings the frame's level of x w to
+// the level of y w -- exact in fp32 -- and the unpacked spectrum 2 X^ is multiplied by the inverse power of two,
+// again exact: the packed transform then sees two signals of equal level and each spectrum carries the rounding error of
+// its own level, as in a transform of its own.  Bit-identical frames have equal maxima: no scaling, and the exact-zero
+// property of loss(x, x) is untouched.  Returns 1 / s; v[].x is scaled in place.  Cost: ~3 % of a transform kernel.
+template <int L, int R>
+SPL_DEVICE float equalise_pair(float2 (&v)[R], float2 amax, unsigned grp_mask) {
+  // Level of a signal in this frame = the mean binade, over the lanes, of each lane's largest tap (a lane holds every L-th
+  // tap): one integer redux.sync per signal.  Unlike the frame maximum it is not fooled by a single spike (an untrained
+  // HiFiGAN decoder emits them: max / rms = 34 on the vocoder trainer's tensors), unlike an energy sum it costs nothing on
+  // the FMA pipe.  A lane without any signal (digital silence) switches the equalisation off.
+  const unsigned ex = float_bits(amax.x) >> 23, ey = float_bits(amax.y) >> 23;      // biased exponents; 0: zero / denormal
+  const unsigned quiet = __reduce_min_sync(grp_mask, ex < ey ? ex : ey);
+  const int sx = (int)__reduce_add_sync(grp_mask, ex), sy = (int)__reduce_add_sync(grp_mask, ey);
+  constexpr int LOG_L = L == 32 ? 5 : 4;
+  static_assert((1 << LOG_L) == L, "lanes per frame");
+  int shift = quiet == 0 ? 0 : (sy - sx + L / 2) >> LOG_L;          // arithmetic shift: floor((d + L/2) / L) = round(d / L)
+  // Levels within a factor of 4 stay as they are: that is every frame once training has brought the prediction near the
+  // target, where the roundings of X^ and Y out of ONE transform are correlated and partly cancel in A_y - A_x (measured:
+  // equalising by a single binade there doubles the gradient's distance from fp64, 2.8e-5 -> 6.1e-5).
+  shift = (shift > -2 && shift < 2) ? 0 : shift;
+  shift = shift < -96 ? -96 : (shift > 96 ? 96 : shift);
+  if (shift != 0) {
+    const float sc = bits_to_float((127 + shift) << 23);
+#pragma unroll
+    for (int n2 = 0; n2 < R; ++n2) v[n2].x *= sc;
+  }
+  return bits_to_float((127 - shift) << 23);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -407,9 +445,9 @@ SPL_DEVICE bool load_taps(float2 (&v)[Geo<NFFT>::R], const float* __restrict__ x
 // eq: prediction and target frames are bit-identical; Y := X then makes every difference term exactly zero
 // (d = 0, lg2(p) - lg2(p) = 0, sign(0) = 0).
 template <bool GRAD>
-SPL_DEVICE void stft_pair(float2 a, float2 bm, bool self, bool eq, float eps4, float& s1, float& s2, float& s3,
+SPL_DEVICE void stft_pair(float2 a, float2 bm, bool self, bool eq, float eps4, float inv_s, float& s1, float& s2, float& s3,
                           float2& ha, float2& hb) {
-  const float2 x2 = __fadd2_rn(a, make_float2(bm.x, -bm.y));
+  const float2 x2 = __fmul2_rn(__fadd2_rn(a, make_float2(bm.x, -bm.y)), make_float2(inv_s, inv_s));   // exact: power of two
   float2 y2 = __fadd2_rn(make_float2(a.y, -a.x), make_float2(bm.y, bm.x));
   y2 = eq ? x2 : y2;
   const float px = fmaf(x2.x, x2.x, x2.y * x2.y);
@@ -436,7 +474,7 @@ SPL_DEVICE void stft_pair(float2 a, float2 bm, bool self, bool eq, float eps4, f
 // all pairs of one lane.  In: columns < L/2 of this lane's rows in A (PARK: in the slot), mirror halves in the slot.
 // Out (GRAD): H in the same places.
 template <int NFFT, bool GRAD>
-SPL_DEVICE void stft_epilogue(float2 (&A)[Geo<NFFT>::AROWS][Geo<NFFT>::HL], float2* S, int l, bool eq, float eps4,
+SPL_DEVICE void stft_epilogue(float2 (&A)[Geo<NFFT>::AROWS][Geo<NFFT>::HL], float2* S, int l, bool eq, float eps4, float inv_s,
                               float& s1, float& s2, float& s3) {
   using G = Geo<NFFT>;
 #pragma unroll(G::PARK ? 1 : G::RPL)
@@ -454,7 +492,7 @@ SPL_DEVICE void stft_epilogue(float2 (&A)[Geo<NFFT>::AROWS][Geo<NFFT>::HL], floa
         bm = self ? a : bm;
       }
       float2 ha, hb;
-      stft_pair<GRAD>(a, bm, self, eq, eps4, s1, s2, s3, ha, hb);
+      stft_pair<GRAD>(a, bm, self, eq, eps4, inv_s, s1, s2, s3, ha, hb);
       if (GRAD) {
         if (G::PARK) arow[k1] = ha;
         else         A[G::PARK ? 0 : j][k1] = ha;
@@ -465,15 +503,15 @@ SPL_DEVICE void stft_epilogue(float2 (&A)[Geo<NFFT>::AROWS][Geo<NFFT>::HL], floa
   if (l == 0) {                                      // bin N/2 = (row 0, column L/2) mirrors itself
     const float2 a = S[G::HL];
     float2 ha, hb;
-    stft_pair<GRAD>(a, a, true, eq, eps4, s1, s2, s3, ha, hb);
+    stft_pair<GRAD>(a, a, true, eq, eps4, inv_s, s1, s2, s3, ha, hb);
     if (GRAD) S[G::HL] = ha;
   }
 }
 
 // [region: mel epilogue]
 // mel, pass 1 on one mirror pair: 2X[k] and the amplitudes (Ax, Ay) = sqrt(max(|.|^2, eps)); eq: Y := X
-SPL_DEVICE void mel_pair_amp(float2 a, float2 bm, bool eq, float eps4, float2& x2, float2& amp) {
-  x2 = __fadd2_rn(a, make_float2(bm.x, -bm.y));
+SPL_DEVICE void mel_pair_amp(float2 a, float2 bm, bool eq, float eps4, float2& x2, float2& amp, float inv_s = 1.f) {
+  x2 = __fmul2_rn(__fadd2_rn(a, make_float2(bm.x, -bm.y)), make_float2(inv_s, inv_s));      // un-scale (equalise_pair)
   float2 y2 = __fadd2_rn(make_float2(a.y, -a.x), make_float2(bm.y, bm.x));
   y2 = eq ? x2 : y2;
   const float pxc = fmaxf(fmaf(x2.x, x2.x, x2.y * x2.y), eps4);
@@ -526,7 +564,7 @@ SPL_DEVICE void mel_project_pairs(const float2* S, float2* msum, int l, int mel_
 template <int NFFT, bool GRAD>
 SPL_DEVICE void mel_epilogue(float2 (&A)[Geo<NFFT>::AROWS][Geo<NFFT>::HL], float2* S, float2* msum, int l, bool eq,
                              bool active, const TransformParams& p, const int4* mel_tasks, const int2* mel_entries,
-                             const int4* bin_tab, float& s1) {
+                             const int4* bin_tab, float inv_s, float& s1) {
   using G = Geo<NFFT>;
   constexpr int L = G::L, R = G::R;
   const float eps4 = 4.f * p.eps;
@@ -543,7 +581,7 @@ SPL_DEVICE void mel_epilogue(float2 (&A)[Geo<NFFT>::AROWS][Geo<NFFT>::HL], float
       float2 bm = pb[-k1];
       if (k1 == 0) bm = (row == 0) ? a : bm;
       float2 x2, amp;
-      mel_pair_amp(a, bm, eq, eps4, x2, amp);
+      mel_pair_amp(a, bm, eq, eps4, x2, amp, inv_s);
       if (G::PARK) pb[-k1] = x2;
       else         A[G::PARK ? 0 : j][k1] = x2;
       arow[k1] = amp;
@@ -552,7 +590,7 @@ SPL_DEVICE void mel_epilogue(float2 (&A)[Geo<NFFT>::AROWS][Geo<NFFT>::HL], float
   if (l == 0) {
     const float2 a = S[G::HL];
     float2 amp;
-    mel_pair_amp(a, a, eq, eps4, xh, amp);
+    mel_pair_amp(a, a, eq, eps4, xh, amp, inv_s);
     S[G::HL] = amp;
   }
   __syncwarp();
@@ -657,9 +695,12 @@ SPL_DEVICE void transform_body(const TransformParams& p, float* smem, int block,
     for (int phase = 0; phase < (GRAD ? 2 : 1); ++phase) {
       float2 v[R];              // defined afresh by each phase: nothing is carried around the loop in registers
       bool frame_equal = false;
+      float inv_s = 1.f;
       if (phase == 0) {
+        float2 amax = make_float2(0.f, 0.f);
         const bool same = load_taps<NFFT, WIN_T>(v, p.x + (size_t)b * p.T, p.y + (size_t)b * p.T, p.T,
-                                                 t * p.hop - HALF, win, left, wtab, l, active);
+                                                 t * p.hop - HALF, win, left, wtab, l, active, amax);
+        inv_s = equalise_pair<L, R>(v, amax, grp_mask);
         // A frame whose prediction and target taps are bit-identical must contribute exactly zero (the reference
         // returns sc = mag = mel = 0 and a zero gradient for x == y); the packed FFT would leave ~1e-7 of rounding
         // asymmetry between X and Y, so such frames reuse X for Y.
@@ -680,10 +721,10 @@ SPL_DEVICE void transform_body(const TransformParams& p, float* smem, int block,
         float2* Sr = G::PARK ? launder_ptr(S) : S;
         fwd_pass_b<NFFT>(A, Sr, lr);
         if (KIND == kKindStft) {
-          stft_epilogue<NFFT, GRAD>(A, Sr, lr, frame_equal, 4.f * p.eps, s1, s2, s3);
+          stft_epilogue<NFFT, GRAD>(A, Sr, lr, frame_equal, 4.f * p.eps, inv_s, s1, s2, s3);
           __syncwarp();    // mirror halves: all reads (and the H written back over them) done before the slot is reused
         } else {
-          mel_epilogue<NFFT, GRAD>(A, Sr, msum, lr, frame_equal, active, p, mel_tasks, mel_entries, bin_tab, s1);
+          mel_epilogue<NFFT, GRAD>(A, Sr, msum, lr, frame_equal, active, p, mel_tasks, mel_entries, bin_tab, inv_s, s1);
         }
         if (active) { d1 += (double)s1; d2 += (double)s2; d3 += (double)s3; }
         if (GRAD) inv_pass_b<NFFT>(A, Sr, tw, lr);

@@ -1,0 +1,6 @@
+set -u
+OUT=gpurun_out; mkdir -p $OUT; T=r4f
+timeout 1500 python -m pytest tests -m gpu -q -x -s > $OUT/${T}_tests.log 2>&1; echo "tests rc=$?"; tail -3 $OUT/${T}_tests.log
+timeout 900 python bench.py --steps 20 --warmup 5 > $OUT/${T}_bench_n1.json 2> $OUT/${T}_bench_n1.err; echo "bench rc=$?"; python -c "
+import json; d=json.load(open('$OUT/${T}_bench_n1.json')); print(d['ms_per_step'], d['value'], d['e2e']['value'], d['config']['one_call_extension'], d['cpu_baseline']['value'], d['cpu_baseline']['cores'])"
+tail -3 $OUT/${T}_bench_n1.err

@@ -71,19 +71,27 @@ static inline unsigned __shfl_xor_sync(unsigned, unsigned v, int lane_mask) {
   emu_warp->bar.arrive_and_wait();
   return r;
 }
-static inline unsigned __reduce_max_sync(unsigned, unsigned v) {
+static inline unsigned __reduce_max_sync(unsigned mask, unsigned v) {      // over the lanes named in mask (sub-warp groups)
   emu_warp->votes[emu_lane] = v;
   emu_warp->bar.arrive_and_wait();
   unsigned r = 0;
-  for (int i = 0; i < 32; ++i) r = std::max(r, emu_warp->votes[i]);
+  for (int i = 0; i < 32; ++i) if ((mask >> i) & 1u) r = std::max(r, emu_warp->votes[i]);
   emu_warp->bar.arrive_and_wait();
   return r;
 }
-static inline unsigned __reduce_min_sync(unsigned, unsigned v) {
+static inline unsigned __reduce_add_sync(unsigned mask, unsigned v) {
+  emu_warp->votes[emu_lane] = v;
+  emu_warp->bar.arrive_and_wait();
+  unsigned r = 0;
+  for (int i = 0; i < 32; ++i) if ((mask >> i) & 1u) r += emu_warp->votes[i];
+  emu_warp->bar.arrive_and_wait();
+  return r;
+}
+static inline unsigned __reduce_min_sync(unsigned mask, unsigned v) {
   emu_warp->votes[emu_lane] = v;
   emu_warp->bar.arrive_and_wait();
   unsigned r = 0xffffffffu;
-  for (int i = 0; i < 32; ++i) r = std::min(r, emu_warp->votes[i]);
+  for (int i = 0; i < 32; ++i) if ((mask >> i) & 1u) r = std::min(r, emu_warp->votes[i]);
   emu_warp->bar.arrive_and_wait();
   return r;
 }

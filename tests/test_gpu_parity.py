@@ -580,3 +580,35 @@ def test_explicit_magnitude_losses_both_gradients(dev):
         assert abs(float(loss.detach()) - float(ref.detach())) <= 1e-6 * float(ref.detach())
         assert rel_l2(xg.grad.cpu().numpy(), xr.grad.numpy()) <= 1e-5
         assert rel_l2(yg.grad.cpu().numpy(), yr.grad.numpy()) <= 1e-5
+
+
+def _weak_predictions(batch, t_len):
+    """Early-training regime (an untrained decoder): the prediction is 40 dB below the target, white or band-limited."""
+    g = torch.Generator().manual_seed(77)
+    y = 0.1 * torch.randn(batch, t_len, generator=g)
+    white = 1e-3 * torch.randn(batch, t_len, generator=g)
+    k = torch.hann_window(65)
+    lowpass = 1e-3 * torch.nn.functional.conv1d(torch.randn(batch, 1, t_len + 64, generator=g), (k / k.sum()).view(1, 1, -1)).squeeze(1)
+    loud = 10.0 * torch.randn(batch, t_len, generator=g)          # and the mirror case: prediction 40 dB ABOVE the target
+    return y, {"weak_white": white, "weak_lowpass": lowpass, "loud": loud}
+
+
+@pytest.mark.parametrize("case", ["weak_white", "weak_lowpass", "loud"])
+def test_weak_prediction_gradient_as_accurate_as_reference_fp32(dev, case):
+    """Prediction and target share one complex FFT in the STFT kernels; without the per-frame power-of-two equalisation
+    (equalise_pair, specloss_kernels.cuh) a prediction 40 dB below the target inherited the target's rounding noise and
+    the MR-STFT gradient was 5e-5 ... 2e-2 from fp64 where the reference's own fp32 evaluation is at 1e-6 (profiles/
+    README.md r4g).  Bar: losses 1e-5, gradient vs the fp64 oracle within 1e-5 or 3 x the fp32 reference route's own distance."""
+    from oracle import spectral_oracle as so
+
+    y, preds = _weak_predictions(4, 24000)
+    x = preds[case]
+    stft, mel = _modules({}, MEL48, dev)
+    vals, g = _run(stft, mel, x, y, dev)
+    mel_res = so.mel_from_kwargs(**MEL48)
+    l64, g64 = so.losses_and_grad(x, y, so.DEFAULT_STFT, mel_res, dtype=torch.float64, use_torch_stft=True)
+    l32, g32 = so.losses_and_grad(x, y, so.DEFAULT_STFT, mel_res, dtype=torch.float32, use_torch_stft=True)
+    np.testing.assert_allclose(vals, l64, rtol=1e-5)
+    e_ours, e_ref = rel_l2(g, g64), rel_l2(g32, g64)
+    print(f"{case}: gradient rel-L2 vs fp64: this repo {e_ours:.2e}, reference op sequence in fp32 {e_ref:.2e}")
+    assert e_ours <= max(3.0 * e_ref, 1e-5), (case, e_ours, e_ref)
