@@ -347,10 +347,24 @@ SPL_DEVICE void inv_pass_b(float2 (&A)[Geo<NFFT>::AROWS][Geo<NFFT>::HL], float2*
   __syncwarp();
 }
 
+// Register slots whose taps enter the level statistic of equalise_pair(): four per lane, spread over the slots the window
+// covers completely (compile-time for the shipped windows).  With L lanes that is 4 L taps per frame, each lane's share a
+// uniformly strided subsample; the estimator (mean binade of the lane maxima, applied to both signals alike) needs no more,
+// and every tap would cost 2 R FMNMX per frame instead of 8.
+template <int NFFT, int WIN_T>
+SPL_DEVICE constexpr bool level_slot(int n2) {
+  constexpr int L = Geo<NFFT>::L, R = Geo<NFFT>::R;
+  constexpr int left = WIN_T > 0 ? (NFFT - WIN_T) / 2 : 0;
+  constexpr int first = WIN_T > 0 ? (left + L - 1) / L : 0;                 // first slot whose L taps all lie under the window
+  constexpr int last = WIN_T > 0 ? (left + WIN_T) / L - 1 : R - 1;          // last such slot
+  constexpr int span = last - first + 1;
+  return n2 == first + span / 8 || n2 == first + (3 * span) / 8 || n2 == first + (5 * span) / 8 || n2 == first + (7 * span) / 8;
+}
+
 // [region: tap load]
 // Taps of frame t of utterance rows xb / yb: reflect-pad, window, pack z = x*w + i*y*w into v[n2] (element
 // n = l + L*n2).  Returns whether every tap of this lane has x*w == y*w bit for bit; amax = (max |x w|, max |y w|) over
-// this lane's taps (FMNMX: not on the FMA pipe), the input of equalise_pair() below.
+// four sampled taps of this lane (level_slot; FMNMX: not on the FMA pipe), the input of equalise_pair() below.
 template <int NFFT, int WIN_T>
 SPL_DEVICE bool load_taps(float2 (&v)[Geo<NFFT>::R], const float* __restrict__ xb, const float* __restrict__ yb, int T,
                           int s0, int win, int left, const float* wtab, int l, bool active, float2& amax) {
@@ -374,9 +388,7 @@ SPL_DEVICE bool load_taps(float2 (&v)[Geo<NFFT>::R], const float* __restrict__ x
         xy = __fmul2_rn(make_float2(__ldg(xp + L * n2), __ldg(yp + L * n2)), make_float2(w, w));
       }
       same = same && (xy.x == xy.y);
-      // level statistic over EVERY tap: a subset (the centre half of the window was tried) misjudges frames whose energy
-      // sits in a transient near the frame edge and then scales the wrong way (trainer tensors: gradient error 8e-2)
-      amax = make_float2(fmaxf(amax.x, fabsf(xy.x)), fmaxf(amax.y, fabsf(xy.y)));
+      if (level_slot<NFFT, WIN_T>(n2)) amax = make_float2(fmaxf(amax.x, fabsf(xy.x)), fmaxf(amax.y, fabsf(xy.y)));
       v[n2] = xy;
     }
   } else {
@@ -393,7 +405,7 @@ SPL_DEVICE bool load_taps(float2 (&v)[Geo<NFFT>::R], const float* __restrict__ x
         yv = __ldg(&yb[sidx]) * w;
       }
       same = same && (xv == yv);
-      amax = make_float2(fmaxf(amax.x, fabsf(xv)), fmaxf(amax.y, fabsf(yv)));
+      if (level_slot<NFFT, WIN_T>(n2)) amax = make_float2(fmaxf(amax.x, fabsf(xv)), fmaxf(amax.y, fabsf(yv)));
       v[n2] = make_float2(xv, yv);
     }
   }
@@ -408,10 +420,17 @@ SPL_DEVICE bool load_taps(float2 (&v)[Geo<NFFT>::R], const float* __restrict__ x
 // again exact: the packed transform then sees two signals of equal level and each spectrum carries the rounding error of
 // its own level, as in a transform of its own.  Bit-identical frames have equal maxima: no scaling, and the exact-zero
 // property of loss(x, x) is untouched.  Returns 1 / s; v[].x is scaled in place.  Cost: ~3 % of a transform kernel.
+// One binade of bias towards the prediction: the gradient is taken w.r.t. the prediction, whose PHASE at weak bins enters
+// through X^ / |X^| and 1 / |X^|, while the target enters through magnitudes only -- so the prediction may be the louder
+// of the two in the shared transform (measured on DC-dominated decoder outputs whose rms is half the target's: 8.0e-5 from
+// fp64 without the bias, 4.7e-5 with it = the reference's fp32).  Equal levels still give shift = 1: untouched.
+#ifndef SPL_EQ_BIAS
+#define SPL_EQ_BIAS 1
+#endif
 template <int L, int R>
 SPL_DEVICE float equalise_pair(float2 (&v)[R], float2 amax, unsigned grp_mask) {
-  // Level of a signal in this frame = the mean binade, over the lanes, of each lane's largest tap (a lane holds every L-th
-  // tap): one integer redux.sync per signal.  Unlike the frame maximum it is not fooled by a single spike (an untrained
+  // Level of a signal in this frame = the mean binade, over the lanes, of each lane's largest sampled tap (a lane holds every
+  // L-th tap): one integer redux.sync per signal.  Unlike the frame maximum it is not fooled by a single spike (an untrained
   // HiFiGAN decoder emits them: max / rms = 34 on the vocoder trainer's tensors), unlike an energy sum it costs nothing on
   // the FMA pipe.  A lane without any signal (digital silence) switches the equalisation off.
   const unsigned ex = float_bits(amax.x) >> 23, ey = float_bits(amax.y) >> 23;      // biased exponents; 0: zero / denormal
@@ -419,7 +438,7 @@ SPL_DEVICE float equalise_pair(float2 (&v)[R], float2 amax, unsigned grp_mask) {
   const int sx = (int)__reduce_add_sync(grp_mask, ex), sy = (int)__reduce_add_sync(grp_mask, ey);
   constexpr int LOG_L = L == 32 ? 5 : 4;
   static_assert((1 << LOG_L) == L, "lanes per frame");
-  int shift = quiet == 0 ? 0 : (sy - sx + L / 2) >> LOG_L;          // arithmetic shift: floor((d + L/2) / L) = round(d / L)
+  int shift = quiet == 0 ? 0 : (sy - sx + L / 2 + SPL_EQ_BIAS * L) >> LOG_L;   // arithmetic shift: floor((d + L/2) / L) = round(d / L)
   // Levels within a factor of 4 stay as they are: that is every frame once training has brought the prediction near the
   // target, where the roundings of X^ and Y out of ONE transform are correlated and partly cancel in A_y - A_x (measured:
   // equalising by a single binade there doubles the gradient's distance from fp64, 2.8e-5 -> 6.1e-5).
