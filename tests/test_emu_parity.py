@@ -440,3 +440,29 @@ def test_weak_prediction_keeps_reference_accuracy(emu_engine, case):
     np.testing.assert_allclose([float(o.detach()) for o in outs], l64, rtol=1e-5)
     e_ours, e_ref = rel_l2(xx.grad.numpy(), g64.numpy()), rel_l2(g32.numpy(), g64.numpy())
     assert e_ours <= max(3.0 * e_ref, 1e-5), (case, e_ours, e_ref)
+
+
+@pytest.mark.parametrize("x_level,y_level", [(1e-30, 1.0), (1e3, 1e-20), (1e-12, 1e-12)])
+def test_level_equalisation_extremes_stay_finite(emu_engine, x_level, y_level):
+    """Level disparities far beyond anything audio produces: the power-of-two shift is clamped (2^+-96), nothing overflows,
+    the losses equal the fp64 oracle's and, where every bin of the prediction sits below the clamp floor of stft(), the
+    gradient is exactly zero as in the reference."""
+    from dl_speech_enhancement_b200 import modules
+    from dl_speech_enhancement_b200.functional import spectral_losses
+    from oracle import spectral_oracle as so
+
+    g = torch.Generator().manual_seed(5)
+    x = x_level * torch.randn(2, 3000, generator=g)
+    y = y_level * torch.randn(2, 3000, generator=g)
+    stft = modules.MultiResolutionSTFTLoss()
+    xx = x.clone().requires_grad_(True)
+    outs = spectral_losses(xx, y, stft.plans(), engine=emu_engine)
+    sum(outs).backward()
+    l64, g64 = so.losses_and_grad(x, y, so.DEFAULT_STFT, None, dtype=torch.float64, use_torch_stft=True)
+    got = [float(o.detach()) for o in outs]
+    assert all(np.isfinite(got)) and bool(torch.isfinite(xx.grad).all())
+    np.testing.assert_allclose(got, l64[:2], rtol=1e-4)
+    if float(g64.abs().max()) == 0.0:
+        assert float(xx.grad.abs().max()) == 0.0
+    else:
+        assert rel_l2(xx.grad.numpy(), g64.numpy()) <= GRAD_RTOL

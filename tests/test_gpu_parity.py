@@ -612,3 +612,23 @@ def test_weak_prediction_gradient_as_accurate_as_reference_fp32(dev, case):
     e_ours, e_ref = rel_l2(g, g64), rel_l2(g32, g64)
     print(f"{case}: gradient rel-L2 vs fp64: this repo {e_ours:.2e}, reference op sequence in fp32 {e_ref:.2e}")
     assert e_ours <= max(3.0 * e_ref, 1e-5), (case, e_ours, e_ref)
+
+
+@pytest.mark.parametrize("x_level,y_level", [(1e-30, 1.0), (1e3, 1e-20), (1e-12, 1e-12)])
+def test_level_equalisation_extremes_stay_finite(dev, x_level, y_level):
+    """As tests/test_emu_parity.py::test_level_equalisation_extremes_stay_finite, on the hardware (flush-to-zero MUFU
+    approximations, redux.sync): clamped shift, finite results, oracle losses, exact-zero gradient below the clamp floor."""
+    from oracle import spectral_oracle as so
+
+    g = torch.Generator().manual_seed(5)
+    x = x_level * torch.randn(2, 3000, generator=g)
+    y = y_level * torch.randn(2, 3000, generator=g)
+    stft, _ = _modules({}, None, dev)
+    vals, grad = _run(stft, None, x, y, dev)
+    l64, g64 = so.losses_and_grad(x, y, so.DEFAULT_STFT, None, dtype=torch.float64, use_torch_stft=True)
+    assert all(np.isfinite(vals)) and bool(np.isfinite(grad).all())
+    np.testing.assert_allclose(vals[:2], l64[:2], rtol=1e-4)
+    if float(g64.abs().max()) == 0.0:
+        assert float(np.abs(grad).max()) == 0.0
+    else:
+        assert rel_l2(grad, g64) <= GRAD_RTOL
