@@ -63,7 +63,7 @@ int check_transform(const spl_transform* t, int B, int T) {
   if (t->kind != SPL_KIND_STFT && t->kind != SPL_KIND_MEL) return fail(SPL_E_INVALID, "kind %d unknown", t->kind);
   if (!supported_nfft(t->n_fft)) return fail(SPL_E_INVALID, "n_fft %d not in {512,1024,2048}", t->n_fft);
   if (t->win < 1 || t->win > t->n_fft) return fail(SPL_E_INVALID, "win %d must be in [1, n_fft=%d]", t->win, t->n_fft);
-  if (t->hop < 1 || t->hop > t->win) return fail(SPL_E_INVALID, "hop %d must be in [1, win=%d]", t->hop, t->win);
+  if (t->hop < 1) return fail(SPL_E_INVALID, "hop %d < 1", t->hop);      // hop > win is legal (torch.stft): frames with gaps
   if (B < 1) return fail(SPL_E_INVALID, "batch %d < 1", B);
   if (T <= t->n_fft / 2) return fail(SPL_E_INVALID, "reflect padding needs T > n_fft/2 (T=%d, n_fft=%d)", T, t->n_fft);
   if ((long long)B * (1 + T / t->hop) > 0x7fffffffLL) return fail(SPL_E_INVALID, "B * frames exceeds 2^31");
@@ -129,7 +129,7 @@ void plan_static(const spl_transform* t, int B, int T, bool grad, LaunchPlan* lp
   lp->run_frames = 1; lp->runs_per_utt = n_frames; lp->run_len = t->win;
   lp->table_bytes = table_bytes; lp->warp_bytes = warp_bytes;
   lp->items = ((long long)B * n_frames + fpw - 1) / fpw;
-  if (!grad || t->kind != SPL_KIND_STFT || eo) return;
+  if (!grad || t->kind != SPL_KIND_STFT || eo || t->hop >= t->win) return;     // no overlap: nothing for a ring to add up
   // Runs: the gradient of a run of m frames is (m - 1) hop + win taps instead of m win.  Worth it when the per-frame
   // slots no longer fit the L2 (they then make a round trip through HBM) and only while every resident warp still gets
   // several runs; the ring costs win * 8 bytes of shared memory per frame in flight.

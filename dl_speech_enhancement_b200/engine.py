@@ -218,8 +218,8 @@ class TransformPlan:
         fft_geometry(self.n_fft)
         if not (1 <= self.win <= self.n_fft):
             raise RuntimeError(f"win_length {self.win} must be in [1, fft_size={self.n_fft}] (torch.stft raises likewise)")
-        if not (1 <= self.hop <= self.win):
-            raise NotImplementedError(f"hop_size {self.hop} > win_length {self.win} is outside the kernels' envelope")
+        if self.hop < 1:
+            raise RuntimeError(f"hop_size {self.hop} < 1")          # hop > win_length is legal, as in torch.stft
         if self.window.dtype != torch.float32 or self.window.numel() != self.win:
             raise RuntimeError("window buffer must be float32 with win_length taps (fp32-only implementation)")
 

@@ -70,13 +70,20 @@ def test_geometry(lib):
 
 
 @pytest.mark.parametrize("kw,frag", [
-    (dict(n_fft=768), "n_fft"), (dict(win=2000), "win"), (dict(hop=700), "hop"),
+    (dict(n_fft=768), "n_fft"), (dict(win=2000), "win"), (dict(hop=0), "hop"),
     (dict(kind=7), "kind"),
 ])
 def test_invalid_arguments_are_reported(lib, kw, frag):
     g = _abi.SplGeometry()
     assert lib.spl_geometry_of(ctypes.byref(_tr(**kw)), 2, 4800, ctypes.byref(g)) == -1
     assert frag in lib.spl_last_error().decode()
+
+
+def test_hop_larger_than_window_is_legal(lib):
+    """torch.stft accepts hop > win_length (frames with gaps between them); so does the library."""
+    g = _abi.SplGeometry()
+    assert lib.spl_geometry_of(ctypes.byref(_tr(hop=700)), 2, 4800, ctypes.byref(g)) == 0
+    assert g.n_frames == 1 + 4800 // 700
 
 
 def test_too_short_signal_is_an_error(lib):

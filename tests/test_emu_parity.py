@@ -466,3 +466,26 @@ def test_level_equalisation_extremes_stay_finite(emu_engine, x_level, y_level):
         assert float(xx.grad.abs().max()) == 0.0
     else:
         assert rel_l2(xx.grad.numpy(), g64.numpy()) <= GRAD_RTOL
+
+
+@pytest.mark.parametrize("fft,hop,win,t_len", [(512, 300, 240, 3001), (1024, 700, 600, 4000), (2048, 2100, 1200, 9000),
+                                               (1024, 1024, 1024, 5000)])
+def test_hop_larger_than_window(emu_engine, fft, hop, win, t_len):
+    """hop >= win_length (legal in torch.stft, hence in the reference modules): frames with gaps between them, samples no
+    frame covers get zero gradient.  STFT and mel losses, forward and gradient, against the fp64 oracle."""
+    from dl_speech_enhancement_b200 import modules
+    from dl_speech_enhancement_b200.functional import spectral_losses
+    from oracle import spectral_oracle as so
+
+    y_hat, y = so.synth_pair(2, t_len, seed=hop)
+    stft_kw = dict(fft_sizes=[fft], hop_sizes=[hop], win_lengths=[win], window="hann_window")
+    mel_kw = dict(fs=24000, fft_sizes=[fft], hop_sizes=[hop], win_lengths=[win], window="hann_window", num_mels=40,
+                  fmin=0, fmax=12000, log_base=None)
+    plans = modules.MultiResolutionSTFTLoss(**stft_kw).plans() + modules.MultiMelSpectrogramLoss(**mel_kw).plans()
+    x = y_hat.clone().requires_grad_(True)
+    outs = spectral_losses(x, y, plans, engine=emu_engine)
+    sum(outs).backward()
+    ref, gref = so.losses_and_grad(y_hat, y, so.stft_from_kwargs(**stft_kw), so.mel_from_kwargs(**mel_kw), dtype=torch.float64,
+                                   use_torch_stft=True)
+    np.testing.assert_allclose([float(o.detach()) for o in outs], ref, rtol=LOSS_RTOL)
+    assert rel_l2(x.grad.numpy(), gref.numpy().reshape(x.grad.shape)) <= GRAD_RTOL

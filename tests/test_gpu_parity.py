@@ -632,3 +632,21 @@ def test_level_equalisation_extremes_stay_finite(dev, x_level, y_level):
         assert float(np.abs(grad).max()) == 0.0
     else:
         assert rel_l2(grad, g64) <= GRAD_RTOL
+
+
+@pytest.mark.parametrize("fft,hop,win,t_len", [(512, 300, 240, 24001), (1024, 700, 600, 24000), (2048, 2100, 1200, 48000),
+                                               (1024, 1024, 1024, 30000)])
+def test_hop_larger_than_window(dev, fft, hop, win, t_len):
+    """hop >= win_length (legal in torch.stft, hence in the reference modules): frames with gaps, zero gradient in between."""
+    from oracle import spectral_oracle as so
+
+    y_hat, y = so.synth_pair(3, t_len, seed=hop)
+    stft_kw = dict(fft_sizes=[fft], hop_sizes=[hop], win_lengths=[win], window="hann_window")
+    mel_kw = dict(fs=24000, fft_sizes=[fft], hop_sizes=[hop], win_lengths=[win], window="hann_window", num_mels=40,
+                  fmin=0, fmax=12000, log_base=None)
+    stft, mel = _modules(stft_kw, mel_kw, dev)
+    vals, g = _run(stft, mel, y_hat, y, dev)
+    ref, gref = so.losses_and_grad(y_hat, y, so.stft_from_kwargs(**stft_kw), so.mel_from_kwargs(**mel_kw), dtype=torch.float64,
+                                   use_torch_stft=True)
+    np.testing.assert_allclose(vals, ref, rtol=LOSS_RTOL)
+    assert rel_l2(g, gref.numpy().reshape(g.shape)) <= GRAD_RTOL
