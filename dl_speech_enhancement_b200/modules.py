@@ -55,6 +55,14 @@ def _explicit_input(x: torch.Tensor, what: str) -> torch.Tensor:
     return x.contiguous()
 
 
+def _target_needs_grad(y: torch.Tensor) -> bool:
+    return torch.is_grad_enabled() and y.requires_grad
+
+
+def _flatten_channels(x: torch.Tensor) -> torch.Tensor:
+    return x.reshape(-1, x.size(-1)) if x.dim() == 3 else x          # stft_loss.py:158-160
+
+
 def stft(x, fft_size, hop_size, win_length, window, eps=1e-7):
     """Magnitude spectrogram (B, #frames, fft_size // 2 + 1) of x (B, T): losses/stft_loss.py:19-35, i.e.
     sqrt(clamp(|torch.stft(x, fft_size, hop_size, win_length, window)|^2, eps)).transpose(2, 1), computed by the
@@ -131,7 +139,21 @@ class STFTLoss(torch.nn.Module):
                              self.window, self._twiddle, twiddle_eo=getattr(self, "_twiddle_eo", None))
 
     def forward(self, x, y):
+        if _target_needs_grad(y):
+            return self._forward_explicit(x, y, getattr(self, "process_group", None))
         return spectral_losses(x, y, _cached_plans(self, [self]), group=getattr(self, "process_group", None))
+
+    def _forward_explicit(self, x, y, group=None):
+        """The reference's own composition (stft_loss.py:99-117) on the explicit kernels -- stft() of both signals, then the
+        two magnitude losses, each differentiable w.r.t. both arguments: the route taken when the TARGET requires a gradient
+        (the fused kernels produce the prediction's only).  No caller in the reference needs it; it exists because the
+        reference's modules would deliver that gradient."""
+        if group is not None:
+            raise NotImplementedError("a gradient w.r.t. the target is not available together with process_group (sharded mode)")
+        x, y = _flatten_channels(x), _flatten_channels(y)
+        x_mag = stft(x, self.fft_size, self.hop_size, self.win_length, self.window)
+        y_mag = stft(y, self.fft_size, self.hop_size, self.win_length, self.window)
+        return self.spectral_convergence_loss(x_mag, y_mag), self.log_stft_magnitude_loss(x_mag, y_mag)
 
 
 class MultiResolutionSTFTLoss(torch.nn.Module):
@@ -151,6 +173,13 @@ class MultiResolutionSTFTLoss(torch.nn.Module):
         return _cached_plans(self, self.stft_losses)
 
     def forward(self, x, y):
+        if _target_needs_grad(y):                # stft_loss.py:161-168 over the explicit route of every resolution
+            sc_loss, mag_loss = 0.0, 0.0
+            for f in self.stft_losses:
+                sc_l, mag_l = f._forward_explicit(x, y, self.process_group)
+                sc_loss = sc_loss + sc_l
+                mag_loss = mag_loss + mag_l
+            return sc_loss / len(self.stft_losses), mag_loss / len(self.stft_losses)
         return spectral_losses(x, y, self.plans(), group=self.process_group)
 
 
@@ -239,6 +268,15 @@ class MultiMelSpectrogramLoss(torch.nn.Module):
         return _cached_plans(self, self.mel_transfers)
 
     def forward(self, y_hat, y):
+        if _target_needs_grad(y):
+            # mel_loss.py:151-154 on the explicit log-mel tensors (tensor-core projection forward, banded adjoint backward),
+            # differentiable w.r.t. both signals: the route for a target that requires a gradient
+            if self.process_group is not None:
+                raise NotImplementedError("a gradient w.r.t. the target is not available together with process_group (sharded mode)")
+            mel_loss = 0.0
+            for f in self.mel_transfers:
+                mel_loss = mel_loss + torch.nn.functional.l1_loss(f(y_hat), f(y))
+            return mel_loss / len(self.mel_transfers)
         (mel,) = spectral_losses(y_hat, y, self.plans(), group=self.process_group)
         return mel
 

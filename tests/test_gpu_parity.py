@@ -650,3 +650,36 @@ def test_hop_larger_than_window(dev, fft, hop, win, t_len):
                                    use_torch_stft=True)
     np.testing.assert_allclose(vals, ref, rtol=LOSS_RTOL)
     assert rel_l2(g, gref.numpy().reshape(g.shape)) <= GRAD_RTOL
+
+
+def test_target_gradient_through_the_explicit_route(dev):
+    """The reference's modules differentiate w.r.t. BOTH arguments (stft_loss.py:112-116, mel_loss.py:151-154).  No caller
+    needs the target's gradient, and the fused kernels produce the prediction's only; a target that requires grad therefore
+    takes the reference's own composition on the explicit kernels (stft() / MelSpectrogram.forward of both signals +
+    magnitude losses).  Losses and both gradients against fp64 autograd of the oracle."""
+    from oracle import spectral_oracle as so
+
+    y_hat, y = so.synth_pair(3, 24000, seed=31)
+    stft, mel = _modules({}, MEL48, dev)
+    x = y_hat.to(dev).reshape(3, 1, -1).clone().requires_grad_(True)          # (B, 1, T) as the trainers pass it
+    t = y.to(dev).reshape(3, 1, -1).clone().requires_grad_(True)
+    sc, mag = stft(x, t)
+    ml = mel(x, t)
+    (sc + mag + ml).backward()
+    x64 = y_hat.double().clone().requires_grad_(True)
+    t64 = y.double().clone().requires_grad_(True)
+    sc64, mag64 = so.mr_stft_loss(x64, t64, so.DEFAULT_STFT, use_torch_stft=True)
+    ml64 = so.multi_mel_loss(x64, t64, so.mel_from_kwargs(**MEL48), use_torch_stft=True)
+    (sc64 + mag64 + ml64).backward()
+    np.testing.assert_allclose([float(sc.detach()), float(mag.detach()), float(ml.detach())],
+                               [float(sc64), float(mag64), float(ml64)], rtol=LOSS_RTOL)
+    assert rel_l2(x.grad.cpu().numpy(), x64.grad.numpy().reshape(3, 1, -1)) <= GRAD_RTOL
+    assert rel_l2(t.grad.cpu().numpy(), t64.grad.numpy().reshape(3, 1, -1)) <= GRAD_RTOL
+    # and the fused route (target without grad) gives the same losses and the same prediction gradient
+    x2 = y_hat.to(dev).reshape(3, 1, -1).clone().requires_grad_(True)
+    sc2, mag2 = stft(x2, y.to(dev).reshape(3, 1, -1))
+    ml2 = mel(x2, y.to(dev).reshape(3, 1, -1))
+    (sc2 + mag2 + ml2).backward()
+    np.testing.assert_allclose([float(sc2.detach()), float(mag2.detach()), float(ml2.detach())],
+                               [float(sc.detach()), float(mag.detach()), float(ml.detach())], rtol=1e-5)
+    assert rel_l2(x2.grad.cpu().numpy(), x.grad.cpu().numpy()) <= GRAD_RTOL
