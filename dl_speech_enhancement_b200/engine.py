@@ -18,6 +18,27 @@ import torch
 from . import _abi
 from ._abi import SPL_KIND_MEL, SPL_KIND_STFT, SplGeometry, SplTransform
 
+# SPECLOSS_NVTX=1: every engine entry point opens an NVTX range ("specloss.forward", ...) around its launches, so a
+# timeline tool (nsys, torch.profiler) shows where the criteria sit inside a trainer step.  Off by default: two extra
+# Python calls per entry point are measurable on the host-bound small-batch path.
+_NVTX = os.environ.get("SPECLOSS_NVTX", "0") not in ("", "0")
+
+
+def _nvtx(name):
+    def wrap(fn):
+        if not _NVTX:
+            return fn
+
+        def inner(*a, **k):
+            torch.cuda.nvtx.range_push("specloss." + name)
+            try:
+                return fn(*a, **k)
+            finally:
+                torch.cuda.nvtx.range_pop()
+        inner.__name__, inner.__doc__ = fn.__name__, fn.__doc__
+        return inner
+    return wrap
+
 SUPPORTED_NFFT = (512, 1024, 2048)
 MAX_MELS = 512           # check_transform() in csrc/specloss_host.inl enforces the same bound
 COUNTER_SLOTS = 1024     # reduce tickets per device, handed out by recipe serial (see Engine._counter)
@@ -524,6 +545,7 @@ class Engine:
 
     # -- forward ---------------------------------------------------------------------------------
     @_on_tensor_device(1)
+    @_nvtx("forward")
     def forward(self, plans: Sequence[TransformPlan], x: torch.Tensor, y: torch.Tensor, need_grad: bool,
                 group=None, global_batch: Optional[int] = None) -> ForwardState:
         """x, y: (B, T) fp32 contiguous on one device.  Launches on the current stream; one workspace
@@ -591,6 +613,7 @@ class Engine:
 
     # -- explicit spectrogram / log-mel spectrogram -----------------------------------------------------
     @_on_tensor_device(0)
+    @_nvtx("spectrogram")
     def spectrogram(self, x: torch.Tensor, n_fft: int, hop: int, win: int, window: torch.Tensor,
                     twiddle: torch.Tensor, eps: float, ld: Optional[int] = None, split: bool = False):
         """(B, T) fp32 -> magnitude spectrogram (B, 1 + T // hop, n_fft // 2 + 1), the tensor the reference's
@@ -625,6 +648,7 @@ class Engine:
         return out
 
     @_on_tensor_device(1)
+    @_nvtx("spectrogram_backward")
     def spectrogram_backward(self, plan: TransformPlan, x: torch.Tensor, g: torch.Tensor) -> torch.Tensor:
         """dL/dx (B, T) from the gradient of an explicit spectrogram of x: g = dL/d stft(x) (B, F, K) for an STFT plan
         (stft_loss.py:19-35), g = dL/d MelSpectrogram(x) (B, n_mels, F) for a mel plan (mel_loss.py:74-94).  Two
@@ -662,6 +686,7 @@ class Engine:
 
     # -- waveform shape loss ---------------------------------------------------------------------
     @_on_tensor_device(0)
+    @_nvtx("shape_forward")
     def shape_forward(self, x: torch.Tensor, y: torch.Tensor, winlens: Sequence[int], group=None,
                       global_rows: Optional[int] = None):
         """x, y: (rows, T) fp32 contiguous.  Returns (loss 0-dim, records, rows_global): MultiWindowShapeLoss.forward
@@ -690,6 +715,7 @@ class Engine:
         return loss, records, rows_global
 
     @_on_tensor_device(0)
+    @_nvtx("shape_backward")
     def shape_backward(self, records: torch.Tensor, rows: int, rows_global: int, t_len: int, winlens: Sequence[int],
                        g: torch.Tensor) -> torch.Tensor:
         dev = records.device
@@ -705,6 +731,7 @@ class Engine:
 
     # -- power-mel L1 metric (Mel_L1 of the reference's evaluation scripts) ------------------------------------
     @_on_tensor_device(0)
+    @_nvtx("melpow_l1")
     def melpow_l1(self, x: torch.Tensor, y: torch.Tensor, n_fft: int, hop: int, window: torch.Tensor, twiddle: torch.Tensor,
                   n_mels: int, mel_ptr: torch.Tensor, mel_ent: torch.Tensor, want_mels: bool = False):
         """x, y: (rows, T) fp32 contiguous -> (loss 0-dim, mel_x, mel_y): nn.L1Loss()(M(x), M(y)) with M the power-mel
@@ -728,6 +755,7 @@ class Engine:
 
     # -- losses on explicit magnitude tensors ----------------------------------------------------
     @_on_tensor_device(0)
+    @_nvtx("mag_loss_forward")
     def mag_loss_forward(self, x_mag: torch.Tensor, y_mag: torch.Tensor, want_sc: bool, want_mag: bool):
         """x_mag, y_mag: fp32 contiguous, same shape.  Returns (sc or None, mag or None, sums): SpectralConvergenceLoss /
         LogSTFTMagnitudeLoss.forward (stft_loss.py:38-77) on the streaming kernels."""
@@ -745,6 +773,7 @@ class Engine:
         return sc, mag, sums
 
     @_on_tensor_device(0)
+    @_nvtx("mag_loss_backward")
     def mag_loss_backward(self, x_mag, y_mag, sums, g_sc, g_mag, need_x: bool, need_y: bool):
         dev = x_mag.device
 
@@ -764,6 +793,7 @@ class Engine:
         return gx, gy
 
     # -- backward --------------------------------------------------------------------------------
+    @_nvtx("backward")
     def backward(self, st: ForwardState, g_sc: Optional[torch.Tensor], g_mag: Optional[torch.Tensor],
                  g_mel: Optional[torch.Tensor]) -> torch.Tensor:
         if not st.has_grad:
