@@ -125,7 +125,10 @@ def slot_offset_eo(k: int) -> int:
     return 32 if k == 1024 else (k % 32) * 33 + k // 32
 
 
-MEL_ITER_TARGET = int(os.environ.get("SPECLOSS_MEL_ITER", "16"))     # bins summed per lane per round of the projection schedule (tuning knob)
+# bins summed per lane per round of the projection schedule: 0 (default) picks, per filterbank, the target that minimises the
+# modelled cost of the schedule (sum over rounds of its longest lane + a fixed per-round cost); a positive value forces it
+MEL_ITER_TARGET = int(os.environ.get("SPECLOSS_MEL_ITER", "0"))
+MEL_ROUND_COST = 5            # task load + shuffle reduction + store of one round, in units of one table entry
 
 
 def slot_offset(n_fft: int, k: int) -> int:
@@ -138,7 +141,7 @@ def mel_tables(melmat: np.ndarray, n_fft: int):
     """Band structure of the (K, n_mels) filterbank, as the kernels consume it.
 
     Forward projection: every mel row is a run of consecutive non-zero bins; a group of 1..L lanes
-    (power of two, sized so each lane sums about MEL_ITER_TARGET bins) strides over the run and the
+    (power of two, sized so each lane sums about `target` bins, see schedule()) strides over the run and the
     group is reduced with shuffles.  Groups are packed into rounds of L lanes, largest first, which
     keeps them aligned to their size.  Each lane walks a dense list of (amplitude slot, weight)
     entries, so the inner loop has no index arithmetic; padding entries carry weight 0.
@@ -156,22 +159,33 @@ def mel_tables(melmat: np.ndarray, n_fft: int):
         nz = np.flatnonzero(melmat[:, m])
         rows.append((m, int(nz[0]), int(nz[-1] - nz[0] + 1)) if nz.size else (m, 0, 0))
 
-    def group_size(length):
-        g = 1
-        while g < lanes and g * MEL_ITER_TARGET < length:
-            g *= 2
-        return g
+    def schedule(target):
+        """Groups (lanes, mel row, first bin, bins) packed into rounds of `lanes` lanes: largest groups first (keeps every group
+        aligned to its size), longest lanes first within a size (rounds then hold lanes of similar length: a round costs its
+        longest lane)."""
+        def group_size(length):
+            g = 1
+            while g < lanes and g * target < length:
+                g *= 2
+            return g
 
-    groups = sorted(((group_size(ln), m, st, ln) for m, st, ln in rows), key=lambda t: (-t[0], t[1]))
-    rounds, cur, used = [], [], 0
-    for g in groups:
-        if used + g[0] > lanes:
-            rounds.append(cur)
-            cur, used = [], 0
-        cur.append(g)
-        used += g[0]
-    if cur:
-        rounds.append(cur)
+        groups = sorted(((group_size(ln), m, st, ln) for m, st, ln in rows), key=lambda t: (-t[0], -(-(-t[3] // t[0])), t[1]))
+        out, cur, used = [], [], 0
+        for g in groups:
+            if used + g[0] > lanes:
+                out.append(cur)
+                cur, used = [], 0
+            cur.append(g)
+            used += g[0]
+        if cur:
+            out.append(cur)
+        cost = sum(max((-(-ln // g) for g, _, _, ln in r), default=0) + MEL_ROUND_COST for r in out)
+        return cost, out
+
+    if MEL_ITER_TARGET > 0:
+        rounds = schedule(MEL_ITER_TARGET)[1]
+    else:
+        rounds = min((schedule(t) for t in (8, 10, 12, 14, 16, 20, 24, 28, 32)), key=lambda c: c[0])[1]
     tasks = np.zeros((len(rounds), lanes, 4), np.int32)
     entries, entries_eo = [], []
     amp_slot = lambda k: slot_offset(n_fft, k)      # noqa: E731
