@@ -782,7 +782,7 @@ int32_t spl_melpow_geometry(int32_t rows, int32_t T, int32_t n_fft, int32_t hop,
   int rc = melpow_check(rows, T, n_fft, hop);
   if (rc) return rc;
   int grid = 0, wpc = 0;
-  rc = spl_shape_dims((long long)rows * (1 + T / hop), &grid, &wpc);
+  rc = spl_shape_dims(((long long)rows * (1 + T / hop) + 1) / 2, &grid, &wpc);      // a warp takes two frames at a time
   if (rc) return rc;
   *partial_count = (int64_t)grid * wpc;
   return SPL_OK;
@@ -800,7 +800,7 @@ int32_t spl_melpow_l1(const float* x, const float* y, int32_t rows, int32_t T, i
   if (nnz < 1 || nnz > spl::kMpMaxNnz) return fail(SPL_E_INVALID, "filterbank non-zeros %d must be in [1, %d]", nnz, spl::kMpMaxNnz);
   const int n_frames = 1 + T / hop;
   int grid = 0, wpc = 0;
-  rc = spl_shape_dims((long long)rows * n_frames, &grid, &wpc);
+  rc = spl_shape_dims(((long long)rows * n_frames + 1) / 2, &grid, &wpc);
   if (rc) return rc;
   spl::MelPowParams p;
   std::memset(&p, 0, sizeof(p));
